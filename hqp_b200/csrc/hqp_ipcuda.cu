@@ -1,0 +1,606 @@
+// libhqpcuda.so -- host side of the C ABI declared in include/hqp_ipcuda.h.
+//
+// Owns every device allocation of one matrix-module instance, builds the
+// stage-sorted / column-sorted index maps the kernels need from the caller's
+// CSR structure, launches the factor / solve kernels (lq_factor.cuh,
+// lq_solve.cuh) on the handle's stream and mirrors the reference's control
+// flow that sits directly above them (Hqp_IpMatrix::solve refinement loop,
+// hqp/Hqp_IpMatrix.C:65-128).  There is no CPU fallback: every entry point
+// either runs the CUDA path or returns an error status.
+
+#include "../../include/hqp_ipcuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lq_device.cuh"
+#include "lq_factor.cuh"
+#include "lq_solve.cuh"
+
+static thread_local std::string g_err;
+
+#define CU(call)                                                              \
+  do {                                                                        \
+    cudaError_t e_ = (call);                                                  \
+    if (e_ != cudaSuccess) {                                                  \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e_);             \
+      return HQPCU_E_CUDA;                                                    \
+    }                                                                         \
+  } while (0)
+
+struct hqpcu_handle {
+  LqDev d;
+  hqpcu_dims dims;
+  cudaStream_t stream = nullptr;
+  long long launches = 0;
+  int device = 0;
+  int nseg_req = 0;
+  std::vector<void *> allocs;
+  // owned device copies
+  double *Q = nullptr, *fx = nullptr, *fu = nullptr, *cval = nullptr, *z = nullptr, *w = nullptr;
+  // staging for the host-pointer API and the refinement loop
+  double *u_r1 = nullptr, *u_r2 = nullptr, *u_r3 = nullptr, *u_r4 = nullptr;
+  double *u_dx = nullptr, *u_dy = nullptr, *u_dz = nullptr, *u_dw = nullptr;
+  double *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *t4 = nullptr;
+  double *e1 = nullptr, *e2 = nullptr, *e3 = nullptr, *e4 = nullptr;
+  double *res_dev = nullptr;
+  double *res_host = nullptr;  // pinned
+  int *status_host = nullptr;  // pinned
+  bool factored = false;
+  size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0;
+  int thr_factor = 128, thr_chain = 128, thr_stage = 64;
+};
+
+template <typename T>
+static int dev_alloc(hqpcu_handle *h, T **p, size_t count) {
+  void *q = nullptr;
+  CU(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  CU(cudaMemset(q, 0, std::max<size_t>(count, 1) * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = static_cast<T *>(q);
+  return HQPCU_OK;
+}
+
+template <typename T>
+static int dev_upload(hqpcu_handle *h, const T **p, const std::vector<T> &v) {
+  T *q = nullptr;
+  int rc = dev_alloc(h, &q, v.size());
+  if (rc) return rc;
+  if (!v.empty()) CU(cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *p = q;
+  return HQPCU_OK;
+}
+
+static size_t pad2(size_t n) { return (n + 1) & ~size_t(1); }
+
+// segments per instance and stages per segment
+static void choose_segments(hqpcu_handle *h, int nseg) {
+  const int K = h->dims.K;
+  int P = nseg;
+  if (P <= 0) {
+    // enough independent instances already fill the machine: sequential sweep
+    if (h->dims.batch >= 64 || K < 32)
+      P = 1;
+    else
+      P = (int)std::lround(std::sqrt(1.5 * K));
+  }
+  P = std::max(1, std::min(P, std::max(1, K / 2)));
+  int L = (K + P - 1) / P;
+  if (L < 1) L = 1;
+  P = std::max(1, (K + L - 1) / L);
+  h->d.P = P;
+  h->d.L = L;
+}
+
+static int set_smem(const void *fn, size_t bytes) {
+  if (bytes > 48 * 1024)
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return HQPCU_OK;
+}
+
+extern "C" {
+
+const char *hqpcu_last_error(void) { return g_err.c_str(); }
+
+int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
+  if (!dims || !out) return HQPCU_E_NULL;
+  *out = nullptr;
+  if (dims->K < 1 || dims->nx < 1 || dims->nu < 0 || dims->batch < 1 || dims->n_ineq < 0 ||
+      dims->n_eq < 0) {
+    g_err = "hqpcu_create: bad dimensions";
+    return HQPCU_E_SIZES;
+  }
+  if (dims->nu < 1) {
+    g_err = "hqpcu_create: nu = 0 is not supported";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  if (dims->n_eq > 0) {
+    g_err = "hqpcu_create: general stage equality rows are not supported yet";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  if (dims->n_ineq > 0 && (!dims->ineq_stage || !dims->ineq_ptr || !dims->ineq_lcol))
+    return HQPCU_E_NULL;
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (dims->device < 0 || dims->device >= ndev) {
+    g_err = "hqpcu_create: no such CUDA device";
+    return HQPCU_E_CUDA;
+  }
+  CU(cudaSetDevice(dims->device));
+
+  hqpcu_handle *h = new hqpcu_handle;
+  h->dims = *dims;
+  h->device = dims->device;
+  h->nseg_req = dims->nseg;
+  LqDev &d = h->d;
+  memset(&d, 0, sizeof d);
+  const int K = dims->K, nx = dims->nx, nu = dims->nu, nm = nx + nu, B = dims->batch;
+  const int m = dims->n_ineq;
+  d.K = K; d.nx = nx; d.nu = nu; d.nm = nm; d.batch = B;
+  d.fixed_x0 = dims->fixed_x0 ? 1 : 0;
+  d.m = m;
+  d.nnz = m ? dims->ineq_ptr[m] : 0;
+  d.N = K * nm + nx;
+  d.me = K * nx + (d.fixed_x0 ? nx : 0);
+  choose_segments(h, dims->nseg);
+
+  // ---- index maps -------------------------------------------------------
+  std::vector<int> stage(dims->ineq_stage, dims->ineq_stage + m);
+  std::vector<int> ptr(m + 1, 0), lcol(d.nnz);
+  if (m) {
+    std::copy(dims->ineq_ptr, dims->ineq_ptr + m + 1, ptr.begin());
+    std::copy(dims->ineq_lcol, dims->ineq_lcol + d.nnz, lcol.begin());
+  }
+  for (int r = 0; r < m; r++) {
+    const int k = stage[r];
+    if (k < 0 || k > K || ptr[r + 1] < ptr[r]) {
+      delete h;
+      g_err = "hqpcu_create: inequality row outside the horizon";
+      return HQPCU_E_SIZES;
+    }
+    const int dk = k < K ? nm : nx;
+    for (int e = ptr[r]; e < ptr[r + 1]; e++)
+      if (lcol[e] < 0 || lcol[e] >= dk) {
+        delete h;
+        g_err = "hqpcu_create: inequality column outside its stage block";
+        return HQPCU_E_SIZES;
+      }
+  }
+  std::vector<int> srow_ptr(K + 2, 0), srow(m);
+  for (int r = 0; r < m; r++) srow_ptr[stage[r] + 1]++;
+  for (int k = 0; k <= K; k++) srow_ptr[k + 1] += srow_ptr[k];
+  {
+    std::vector<int> fill(srow_ptr.begin(), srow_ptr.end() - 1);
+    for (int r = 0; r < m; r++) srow[fill[stage[r]]++] = r;
+  }
+  std::vector<int> vcol_ptr(d.N + 1, 0), vcol_row(d.nnz), vcol_nz(d.nnz);
+  for (int r = 0; r < m; r++)
+    for (int e = ptr[r]; e < ptr[r + 1]; e++) vcol_ptr[stage[r] * nm + lcol[e] + 1]++;
+  for (int j = 0; j < d.N; j++) vcol_ptr[j + 1] += vcol_ptr[j];
+  {
+    std::vector<int> fill(vcol_ptr.begin(), vcol_ptr.end() - 1);
+    for (int r = 0; r < m; r++)
+      for (int e = ptr[r]; e < ptr[r + 1]; e++) {
+        const int pos = fill[stage[r] * nm + lcol[e]]++;
+        vcol_row[pos] = r;
+        vcol_nz[pos] = e;
+      }
+  }
+  int rc = HQPCU_OK;
+#define TRY(x) do { if ((rc = (x)) != HQPCU_OK) { hqpcu_destroy(h); return rc; } } while (0)
+  TRY(dev_upload(h, &d.ineq_stage, stage));
+  TRY(dev_upload(h, &d.ineq_ptr, ptr));
+  TRY(dev_upload(h, &d.ineq_lcol, lcol));
+  TRY(dev_upload(h, &d.srow_ptr, srow_ptr));
+  TRY(dev_upload(h, &d.srow, srow));
+  TRY(dev_upload(h, &d.vcol_ptr, vcol_ptr));
+  TRY(dev_upload(h, &d.vcol_row, vcol_row));
+  TRY(dev_upload(h, &d.vcol_nz, vcol_nz));
+
+  // ---- slabs --------------------------------------------------------------
+  const size_t SB = (size_t)B;
+  TRY(dev_alloc(h, &h->Q, SB * (K + 1) * nm * nm));
+  TRY(dev_alloc(h, &h->fx, SB * K * nx * nx));
+  TRY(dev_alloc(h, &h->fu, SB * K * nx * nu));
+  TRY(dev_alloc(h, &h->cval, SB * d.nnz));
+  TRY(dev_alloc(h, &h->z, SB * m));
+  TRY(dev_alloc(h, &h->w, SB * m));
+  d.Q = h->Q; d.fx = h->fx; d.fu = h->fu; d.cval = h->cval; d.z = h->z; d.w = h->w;
+  TRY(dev_alloc(h, &d.V, SB * (K + 1) * nx * nx));
+  TRY(dev_alloc(h, &d.Rux, SB * K * nu * nx));
+  TRY(dev_alloc(h, &d.LD, SB * K * nu * nu));
+  TRY(dev_alloc(h, &d.Phi, SB * K * nx * nx));
+  // segment arrays are sized for the largest P this handle may use (K)
+  const size_t PM = (size_t)std::max(d.P, 1);
+  h->dims.nseg = d.P;
+  TRY(dev_alloc(h, &d.segA, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segC, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segJ, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segPsi, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segVb, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.V0f, SB * nx * nx));
+  TRY(dev_alloc(h, &d.status, 1));
+  TRY(dev_alloc(h, &d.g, SB * d.N));
+  TRY(dev_alloc(h, &d.wv, SB * K * nx));
+  TRY(dev_alloc(h, &d.q, SB * K * nx));
+  TRY(dev_alloc(h, &d.v, SB * (K + 1) * nx));
+  TRY(dev_alloc(h, &d.Ru, SB * K * nu));
+  TRY(dev_alloc(h, &d.c, SB * K * nx));
+  TRY(dev_alloc(h, &d.x, SB * (K + 1) * nx));
+  TRY(dev_alloc(h, &d.segv0, SB * PM * nx));
+  TRY(dev_alloc(h, &d.segvb, SB * PM * nx));
+  TRY(dev_alloc(h, &d.segx0, SB * PM * nx));
+  TRY(dev_alloc(h, &d.segxa, SB * PM * nx));
+  TRY(dev_alloc(h, &h->u_r1, SB * d.N)); TRY(dev_alloc(h, &h->u_dx, SB * d.N));
+  TRY(dev_alloc(h, &h->t1, SB * d.N));   TRY(dev_alloc(h, &h->e1, SB * d.N));
+  TRY(dev_alloc(h, &h->u_r2, SB * d.me)); TRY(dev_alloc(h, &h->u_dy, SB * d.me));
+  TRY(dev_alloc(h, &h->t2, SB * d.me));   TRY(dev_alloc(h, &h->e2, SB * d.me));
+  TRY(dev_alloc(h, &h->u_r3, SB * m)); TRY(dev_alloc(h, &h->u_dz, SB * m));
+  TRY(dev_alloc(h, &h->t3, SB * m));   TRY(dev_alloc(h, &h->e3, SB * m));
+  TRY(dev_alloc(h, &h->u_r4, SB * m)); TRY(dev_alloc(h, &h->u_dw, SB * m));
+  TRY(dev_alloc(h, &h->t4, SB * m));   TRY(dev_alloc(h, &h->e4, SB * m));
+  TRY(dev_alloc(h, &h->res_dev, 1));
+  if (cudaMallocHost(&h->res_host, sizeof(double)) != cudaSuccess ||
+      cudaMallocHost(&h->status_host, sizeof(int)) != cudaSuccess) {
+    g_err = "cudaMallocHost failed";
+    hqpcu_destroy(h);
+    return HQPCU_E_CUDA;
+  }
+
+  // ---- launch geometry ------------------------------------------------------
+  h->thr_factor = nm <= 32 ? 128 : 256;
+  h->thr_chain = 4 * (((nx + 31) / 32) * 32);
+  h->thr_stage = std::max(32, ((nm + 31) / 32) * 32);
+  const size_t nn = pad2((size_t)nx * nx), nf = pad2((size_t)nx * nm), gg = pad2((size_t)nm * nm),
+               ru = pad2((size_t)nu * nx), xu = pad2((size_t)nx * nu);
+  h->smem_k1 = (4 * nn + 2 * nf + gg + ru + nn + 2 * xu) * sizeof(double);
+  h->smem_k2 = (3 * nn + pad2((size_t)2 * nx * nx) + gg) * sizeof(double);
+  h->smem_k3 = (nn + 2 * nf + gg + ru + 3 * nn) * sizeof(double);
+  const size_t smem_max = 227 * 1024;
+  if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max) {
+    g_err = "hqpcu_create: stage blocks too large for the shared-memory kernels";
+    hqpcu_destroy(h);
+    return HQPCU_E_UNSUPPORTED;
+  }
+  TRY(set_smem((const void *)seg_element_kernel, h->smem_k1));
+  TRY(set_smem((const void *)seg_scan_kernel, h->smem_k2));
+  TRY(set_smem((const void *)seg_riccati_kernel, h->smem_k3));
+  TRY(set_smem((const void *)x0_factor_kernel, nn * sizeof(double)));
+#undef TRY
+  *out = h;
+  return HQPCU_OK;
+}
+
+int hqpcu_destroy(hqpcu_handle *h) {
+  if (!h) return HQPCU_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (void *p : h->allocs) cudaFree(p);
+  if (h->res_host) cudaFreeHost(h->res_host);
+  if (h->status_host) cudaFreeHost(h->status_host);
+  delete h;
+  return HQPCU_OK;
+}
+
+int hqpcu_set_stream(hqpcu_handle *h, void *s) {
+  if (!h) return HQPCU_E_NULL;
+  h->stream = static_cast<cudaStream_t>(s);
+  return HQPCU_OK;
+}
+
+long long hqpcu_launch_count(const hqpcu_handle *h) { return h ? h->launches : 0; }
+int hqpcu_nseg(const hqpcu_handle *h) { return h ? h->d.P : 0; }
+
+// ------------------------------------------------------------------ update --
+static int update_impl(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
+                       const double *cv, cudaMemcpyKind kind) {
+  if (!h || !Q || !fx || !fu || (h->d.nnz && !cv)) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  const size_t B = d.batch;
+  CU(cudaSetDevice(h->device));
+  CU(cudaMemcpyAsync(h->Q, Q, B * (d.K + 1) * d.nm * d.nm * sizeof(double), kind, h->stream));
+  CU(cudaMemcpyAsync(h->fx, fx, B * d.K * d.nx * d.nx * sizeof(double), kind, h->stream));
+  CU(cudaMemcpyAsync(h->fu, fu, B * d.K * d.nx * d.nu * sizeof(double), kind, h->stream));
+  if (d.nnz)
+    CU(cudaMemcpyAsync(h->cval, cv, B * d.nnz * sizeof(double), kind, h->stream));
+  h->factored = false;
+  return HQPCU_OK;
+}
+
+int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
+                 const double *ineq_val, const double *) {
+  int rc = update_impl(h, Q, fx, fu, ineq_val, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  CU(cudaStreamSynchronize(h->stream));
+  return HQPCU_OK;
+}
+
+int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
+                     const double *ineq_val, const double *) {
+  return update_impl(h, Q, fx, fu, ineq_val, cudaMemcpyDeviceToDevice);
+}
+
+// ------------------------------------------------------------------ factor --
+static int launch_factor(hqpcu_handle *h) {
+  const LqDev &d = h->d;
+  CU(cudaMemsetAsync(d.status, 0, sizeof(int), h->stream));
+  const dim3 gseg(d.P, d.batch);
+  if (d.P > 1) {
+    seg_element_kernel<<<gseg, h->thr_factor, h->smem_k1, h->stream>>>(d);
+    h->launches++;
+  }
+  seg_scan_kernel<<<d.batch, h->thr_factor, h->smem_k2, h->stream>>>(d);
+  seg_riccati_kernel<<<gseg, h->thr_factor, h->smem_k3, h->stream>>>(d);
+  h->launches += 2;
+  if (!d.fixed_x0) {
+    x0_factor_kernel<<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), h->stream>>>(d);
+    h->launches++;
+  }
+  CU(cudaGetLastError());
+  h->factored = true;
+  return HQPCU_OK;
+}
+
+static int read_status(hqpcu_handle *h) {
+  CU(cudaMemcpyAsync(h->status_host, h->d.status, sizeof(int), cudaMemcpyDeviceToHost,
+                     h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  const int st = *h->status_host;
+  if (st & LQ_FLAG_SING) return HQPCU_E_SING;
+  if (st & LQ_FLAG_NOTPD) return HQPCU_E_NOTPD;
+  return HQPCU_OK;
+}
+
+static int factor_impl(hqpcu_handle *h, const double *z, const double *w, cudaMemcpyKind kind) {
+  if (!h) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  if (d.m && (!z || !w)) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  if (d.m) {
+    const size_t bytes = (size_t)d.batch * d.m * sizeof(double);
+    CU(cudaMemcpyAsync(h->z, z, bytes, kind, h->stream));
+    CU(cudaMemcpyAsync(h->w, w, bytes, kind, h->stream));
+  }
+  return launch_factor(h);
+}
+
+int hqpcu_factor_dev(hqpcu_handle *h, const double *z, const double *w) {
+  return factor_impl(h, z, w, cudaMemcpyDeviceToDevice);
+}
+
+int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w) {
+  int rc = factor_impl(h, z, w, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  rc = read_status(h);
+  if (rc == HQPCU_E_NOTPD && h->d.P > 1) {
+    // the zero-terminal-cost segment condensation needs Huu > 0 at segment
+    // ends; fall back to the sequential sweep ON THE GPU (still no CPU path)
+    choose_segments(h, 1);
+    rc = launch_factor(h);
+    if (rc) return rc;
+    rc = read_status(h);
+  }
+  if (rc == HQPCU_E_NOTPD) rc = HQPCU_OK;  // indefinite but non-singular: accepted
+  return rc;
+}
+
+// status of everything enqueued so far by the _dev entry points (synchronises)
+int hqpcu_sync_status(hqpcu_handle *h) {
+  if (!h) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  return read_status(h);
+}
+
+int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
+  if (!h) return HQPCU_E_NULL;
+  if (nseg > h->dims.nseg && h->dims.nseg > 0 && nseg > 1) {
+    g_err = "hqpcu_set_nseg: cannot exceed the segment count of hqpcu_create";
+    return HQPCU_E_SIZES;
+  }
+  choose_segments(h, nseg);
+  h->factored = false;
+  return HQPCU_OK;
+}
+
+// -------------------------------------------------------------------- step --
+static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                       const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  const LqDev &d = h->d;
+  if (!h->factored) {
+    g_err = "step before factor";
+    return HQPCU_E_NULL;
+  }
+  const dim3 gall(d.K + 1, d.batch), gk(d.K, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
+  const size_t sc = (size_t)(d.nx + 2) * sizeof(double);
+  cudaStream_t s = h->stream;
+  solve_pre_kernel<<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4);
+  solve_back_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 0);
+  solve_back_scan_kernel<<<d.batch, h->thr_chain, sc, s>>>(d);
+  solve_back_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 1);
+  solve_mid_kernel<<<gk, h->thr_stage, sv, s>>>(d, r2);
+  solve_fwd_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 0);
+  solve_fwd_scan_kernel<<<d.batch, h->thr_chain, sc, s>>>(d, r2);
+  solve_fwd_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 1);
+  solve_post_kernel<<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw);
+  h->launches += 9;
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+int hqpcu_step_dev(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                   const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
+  if (h->d.m && (!r3 || !r4 || !dz || !dw)) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  return launch_step(h, r1, r2, r3, r4, dx, dy, dz, dw);
+}
+
+static int h2d_rhs(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                   const double *r4) {
+  const LqDev &d = h->d;
+  const size_t B = d.batch;
+  CU(cudaMemcpyAsync(h->u_r1, r1, B * d.N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->u_r2, r2, B * d.me * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (d.m) {
+    CU(cudaMemcpyAsync(h->u_r3, r3, B * d.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->u_r4, r4, B * d.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  return HQPCU_OK;
+}
+
+static int d2h_sol(hqpcu_handle *h, double *dx, double *dy, double *dz, double *dw) {
+  const LqDev &d = h->d;
+  const size_t B = d.batch;
+  CU(cudaMemcpyAsync(dx, h->u_dx, B * d.N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaMemcpyAsync(dy, h->u_dy, B * d.me * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (d.m) {
+    CU(cudaMemcpyAsync(dz, h->u_dz, B * d.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(dw, h->u_dw, B * d.m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(cudaStreamSynchronize(h->stream));
+  return HQPCU_OK;
+}
+
+int hqpcu_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+               const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
+  if (h->d.m && (!r3 || !r4 || !dz || !dw)) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  int rc = h2d_rhs(h, r1, r2, r3, r4);
+  if (rc) return rc;
+  rc = launch_step(h, h->u_r1, h->u_r2, h->u_r3, h->u_r4, h->u_dx, h->u_dy, h->u_dz, h->u_dw);
+  if (rc) return rc;
+  return d2h_sol(h, dx, dy, dz, dw);
+}
+
+// ---------------------------------------------------------------- residuum --
+static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                           const double *r4, const double *dx, const double *dy,
+                           const double *dz, const double *dw, bool keep, double *res) {
+  const LqDev &d = h->d;
+  CU(cudaMemsetAsync(h->res_dev, 0, sizeof(double), h->stream));
+  const dim3 gall(d.K + 1, d.batch);
+  const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
+  residuum_kernel<<<gall, h->thr_stage, sv, h->stream>>>(
+      d, r1, r2, r3, r4, dx, dy, dz, dw, keep ? h->t1 : nullptr, keep ? h->t2 : nullptr,
+      keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev);
+  h->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(cudaStreamSynchronize(h->stream));
+  *res = *h->res_host;
+  return HQPCU_OK;
+}
+
+int hqpcu_residuum_dev(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                       const double *r4, const double *dx, const double *dy, const double *dz,
+                       const double *dw, double *res) {
+  if (!h || !res) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  return launch_residuum(h, r1, r2, r3, r4, dx, dy, dz, dw, false, res);
+}
+
+int hqpcu_residuum(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                   const double *r4, const double *dx, const double *dy, const double *dz,
+                   const double *dw, double *res) {
+  if (!h || !res) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  const LqDev &d = h->d;
+  const size_t B = d.batch;
+  int rc = h2d_rhs(h, r1, r2, r3, r4);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(h->u_dx, dx, B * d.N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(cudaMemcpyAsync(h->u_dy, dy, B * d.me * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (d.m) {
+    CU(cudaMemcpyAsync(h->u_dz, dz, B * d.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->u_dw, dw, B * d.m * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  }
+  return launch_residuum(h, h->u_r1, h->u_r2, h->u_r3, h->u_r4, h->u_dx, h->u_dy, h->u_dz,
+                         h->u_dw, false, res);
+}
+
+// ------------------------------------------------------------------- solve --
+// Hqp_IpMatrix::solve (hqp/Hqp_IpMatrix.C:65-128) on device-resident vectors.
+static int solve_core(hqpcu_handle *h, double eps, const double *r1, const double *r2,
+                      const double *r3, const double *r4, double *dx, double *dy, double *dz,
+                      double *dw, double *res_out, int *nsteps) {
+  const LqDev &d = h->d;
+  const size_t B = d.batch;
+  const size_t n1 = B * d.N, n2 = B * d.me, n3 = B * d.m;
+  int steps = 1;
+  int rc = launch_step(h, r1, r2, r3, r4, dx, dy, dz, dw);
+  if (rc) return rc;
+  double res = 0.0;
+  rc = launch_residuum(h, r1, r2, r3, r4, dx, dy, dz, dw, true, &res);
+  if (rc) return rc;
+  const int ablocks = (int)std::min<size_t>((std::max(n1, n2) + 255) / 256, 148 * 8);
+  for (int it = 0; it < 5 && res > eps; it++) {
+    const double res_last = res;
+    rc = launch_step(h, h->t1, h->t2, h->t3, h->t4, h->e1, h->e2, h->e3, h->e4);
+    if (rc) return rc;
+    steps++;
+    double alpha = 1.0;
+    do {
+      axpy4_kernel<<<ablocks, 256, 0, h->stream>>>(alpha, h->e1, dx, n1, h->e2, dy, n2, h->e3,
+                                                   dz, n3, h->e4, dw, n3);
+      h->launches++;
+      rc = launch_residuum(h, r1, r2, r3, r4, dx, dy, dz, dw, true, &res);
+      if (rc) return rc;
+      if (res > res_last) {
+        axpy4_kernel<<<ablocks, 256, 0, h->stream>>>(-alpha, h->e1, dx, n1, h->e2, dy, n2,
+                                                     h->e3, dz, n3, h->e4, dw, n3);
+        h->launches++;
+        alpha -= 0.3;
+      }
+    } while (res > res_last && alpha > 0.0);
+    if (alpha <= 0.0) break;
+  }
+  if (res_out) *res_out = res;
+  if (nsteps) *nsteps = steps;
+  return HQPCU_OK;
+}
+
+int hqpcu_solve_dev(hqpcu_handle *h, double eps, const double *r1, const double *r2,
+                    const double *r3, const double *r4, double *dx, double *dy, double *dz,
+                    double *dw, double *res, int *nsteps) {
+  if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  return solve_core(h, eps, r1, r2, r3, r4, dx, dy, dz, dw, res, nsteps);
+}
+
+int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
+                const double *r3, const double *r4, double *dx, double *dy, double *dz,
+                double *dw, double *res, int *nsteps) {
+  if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
+  if (h->d.m && (!r3 || !r4 || !dz || !dw)) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  int rc = h2d_rhs(h, r1, r2, r3, r4);
+  if (rc) return rc;
+  rc = solve_core(h, eps, h->u_r1, h->u_r2, h->u_r3, h->u_r4, h->u_dx, h->u_dy, h->u_dz,
+                  h->u_dw, res, nsteps);
+  if (rc) return rc;
+  return d2h_sol(h, dx, dy, dz, dw);
+}
+
+int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {
+  if (!h) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  if (Vxx)
+    CU(cudaMemcpy(Vxx, d.V, (size_t)d.batch * (d.K + 1) * d.nx * d.nx * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+  if (Rux)
+    CU(cudaMemcpy(Rux, d.Rux, (size_t)d.batch * d.K * d.nu * d.nx * sizeof(double),
+                  cudaMemcpyDeviceToHost));
+  return HQPCU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,145 @@
+/*
+ * hqp_ipcuda.h -- C ABI of libhqpcuda.so, the B200 (sm_100a) KKT engine behind
+ * HQP's Hqp_IpMatrix plugin interface.
+ *
+ * Drop-in boundary: the reference's interior-point solvers call a
+ * matrix module through  init / update / factor / step / solve / residuum
+ * (hqp/Hqp_IpMatrix.h:63-88).  The host module hqp_b200/host/Hqp_IpCuda.C
+ * implements that C++ interface and forwards every call to the functions below,
+ * exactly as hqp/Hqp_IpPARDISO.C:161-166 forwards to hqp/pardiso_wrapper.h:32-48.
+ *
+ * Conventions
+ *  - plain C: pointers, ints, doubles; no C++ types, no exceptions.
+ *  - every function returns an int status (HQPCU_OK = 0).  HQPCU_E_SING = 4 is
+ *    Meschach's E_SING (meschach/err.h:88): the host module turns it into
+ *    m_error(E_SING, ...) AFTER the call returned, so no longjmp crosses a CUDA
+ *    call in flight ("Failure detection").
+ *  - all arithmetic is FP64.  Vectors use the reference's QP layout
+ *    (hqp/Hqp_Docp.C:465-755):
+ *        x  (N  = K*(nx+nu)+nx)      [x0,u0,x1,u1,...,xK]
+ *        y  (me = K*nx [+nx] +n_eq)  dynamics rows, then the nx rows fixing x0
+ *                                    (if fixed_x0), then general equality rows
+ *        z,w (m = n_ineq)            rows of C in the caller's order
+ *    With batch > 1 every vector / slab is the concatenation of `batch`
+ *    instances (instance-major).
+ *  - The linear system solved (hqp/Hqp_IpsMehrotra.C:27-31):
+ *        -Q dx + A' dy + C' dz      = r1
+ *         A dx                      = r2
+ *         C dx              - dw    = r3
+ *                 W dz    + Z dw    = r4
+ *  - "_dev" entry points take DEVICE pointers and enqueue on the handle's
+ *    stream without synchronising; the others take HOST pointers, copy in/out
+ *    and return after the results are on the host.
+ */
+#ifndef HQP_IPCUDA_H
+#define HQP_IPCUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HQPCU_OK 0
+#define HQPCU_E_SIZES 1   /* inconsistent dimensions (Meschach E_SIZES)          */
+#define HQPCU_E_SING 4    /* zero pivot in a stage LDL^T / LU (Meschach E_SING)  */
+#define HQPCU_E_NULL 8    /* NULL argument (Meschach E_NULL)                     */
+#define HQPCU_E_CUDA 100  /* CUDA runtime error; see hqpcu_last_error()          */
+#define HQPCU_E_UNSUPPORTED 101 /* structure outside the supported scope         */
+#define HQPCU_E_NOTPD 102 /* parallel-in-time factor met a non-positive pivot at
+                             a segment end; caller may retry with nseg = 1       */
+
+typedef struct hqpcu_handle hqpcu_handle;
+
+/* Stage structure of the QP: what Hqp_IpLQDOCP::init derives from the sparsity
+ * of A and C (Get_Dim hqp/Hqp_IpLQDOCP.C:201-287, Get_Constr_Dim :368-407,
+ * Check_Structure :298-354). */
+typedef struct hqpcu_dims {
+  int K;        /* stages with controls (_kmax); states x_0..x_K               */
+  int nx, nu;   /* uniform stage dimensions (_nk[k], _mk[k])                    */
+  int batch;    /* independent instances sharing this structure (>= 1)          */
+  int fixed_x0; /* 1: x_0 is fixed by nx identity rows (_fixed_x0, :344-351)    */
+  int n_ineq;   /* rows of C per instance                                       */
+  const int *ineq_stage; /* [n_ineq]   stage of each row (_rcki, :391-406)      */
+  const int *ineq_ptr;   /* [n_ineq+1] CSR row pointers                         */
+  const int *ineq_lcol;  /* [nnz]      column inside the stage block, 0..nx+nu-1*/
+  int n_eq;     /* general stage equality rows per instance (_raki, :381-388)   */
+  const int *eq_stage;   /* [n_eq]                                              */
+  const int *eq_ptr;     /* [n_eq+1]                                            */
+  const int *eq_lcol;    /* [nnz_eq]                                            */
+  int device;   /* CUDA device ordinal                                          */
+  int nseg;     /* horizon segments per instance for the parallel-in-time
+                   factor/solve; 0 = choose automatically, 1 = sequential sweep */
+} hqpcu_dims;
+
+/* --- life cycle (Hqp_IpCuda ctor/dtor + init; If_Module deletes and re-creates
+ *     the module object on every "qp_mat_solver" write, iftcl/If_Module.h:66-90) */
+int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out);
+int hqpcu_destroy(hqpcu_handle *h);
+/* cudaStream_t to enqueue on (NULL = default stream) */
+int hqpcu_set_stream(hqpcu_handle *h, void *cuda_stream);
+const char *hqpcu_last_error(void);
+/* kernels launched by this handle since creation (bench.py "gpu_launches") */
+long long hqpcu_launch_count(const hqpcu_handle *h);
+/* segments actually used per instance */
+int hqpcu_nseg(const hqpcu_handle *h);
+
+/* --- update: once per SQP iteration (Hqp_IpLQDOCP::update, :722-787) -------
+ * Q   [batch][(K+1)][(nx+nu)^2] full symmetric stage blocks (block K uses its
+ *                               leading nx x nx part)
+ * fx  [batch][K][nx*nx], fu [batch][K][nx*nu]  row-major dynamics Jacobians
+ * ineq_val [batch][nnz], eq_val [batch][nnz_eq] values on the CSR patterns     */
+int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx,
+                 const double *fu, const double *ineq_val, const double *eq_val);
+int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx,
+                     const double *fu, const double *ineq_val,
+                     const double *eq_val);
+
+/* --- factor: once per IP iteration (Hqp_IpLQDOCP::factor, :796-862) --------- */
+int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w);
+int hqpcu_factor_dev(hqpcu_handle *h, const double *z, const double *w);
+
+/* status of everything enqueued so far by the _dev entry points; synchronises
+ * the stream.  HQPCU_E_NOTPD after hqpcu_factor_dev: call hqpcu_set_nseg(h, 1)
+ * and factor again (hqpcu_factor does this by itself).                         */
+int hqpcu_sync_status(hqpcu_handle *h);
+/* change the number of horizon segments (<= the count chosen at create) */
+int hqpcu_set_nseg(hqpcu_handle *h, int nseg);
+
+/* --- step: one KKT solve with the current factor (Hqp_IpLQDOCP::step,
+ *     :869-976).  z,w are the ones given to the last factor call.              */
+int hqpcu_step(hqpcu_handle *h, const double *r1, const double *r2,
+               const double *r3, const double *r4, double *dx, double *dy,
+               double *dz, double *dw);
+int hqpcu_step_dev(hqpcu_handle *h, const double *r1, const double *r2,
+                   const double *r3, const double *r4, double *dx, double *dy,
+                   double *dz, double *dw);
+
+/* --- residuum: inf-norm of the four block residuals
+ *     (Hqp_IpMatrix::residuum, hqp/Hqp_IpMatrix.C:131-178)                      */
+int hqpcu_residuum(hqpcu_handle *h, const double *r1, const double *r2,
+                   const double *r3, const double *r4, const double *dx,
+                   const double *dy, const double *dz, const double *dw,
+                   double *res);
+int hqpcu_residuum_dev(hqpcu_handle *h, const double *r1, const double *r2,
+                       const double *r3, const double *r4, const double *dx,
+                       const double *dy, const double *dz, const double *dw,
+                       double *res /* host */);
+
+/* --- solve: step + up to 5 damped refinement steps until res <= eps
+ *     (Hqp_IpMatrix::solve, hqp/Hqp_IpMatrix.C:65-128).  nsteps (may be NULL)
+ *     receives the number of step() calls performed.                           */
+int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
+                const double *r3, const double *r4, double *dx, double *dy,
+                double *dz, double *dw, double *res, int *nsteps);
+int hqpcu_solve_dev(hqpcu_handle *h, double eps, const double *r1,
+                    const double *r2, const double *r3, const double *r4,
+                    double *dx, double *dy, double *dz, double *dw,
+                    double *res /* host */, int *nsteps);
+
+/* --- read-back of factor state for tests: Vxx [batch][(K+1)][nx*nx],
+ *     Rux [batch][K][nu*nx] (either may be NULL)                               */
+int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,158 @@
+"""ctypes wrapper around oracle/_ref/libhqpharness.so (the UNMODIFIED reference).
+
+TEST INFRASTRUCTURE ONLY.  Importable from tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never from hqp_b200/.
+The shared objects are prebuilt in the build container by `make -C oracle ref`
+(they travel to the GPU box with the snapshot; /root/reference does not).
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_DIR = os.path.join(_HERE, "_ref")
+_LIB = None
+
+HQP_RESULT = ["optimal", "feasible", "infeasible", "suboptimal", "degenerate"]
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "libhqpharness.so"))
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(REF_DIR, "libhqpharness.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} missing: run `make -C oracle ref` where "
+                               "/root/reference exists")
+        _LIB = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        _LIB.ref_qp_create.restype = ctypes.c_void_p
+        _LIB.ref_mat_create.restype = ctypes.c_void_p
+        _LIB.ref_last_error.restype = ctypes.c_char_p
+        _LIB.ref_get_real.restype = ctypes.c_double
+        _LIB.ref_init()
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+class RefQP:
+    """An Hqp_Program built from an hqp_b200.problem.LQProblem."""
+
+    def __init__(self, prob):
+        self.prob = prob
+        L = lib()
+        self._keep = (prob.csr_Q_upper(), prob.csr_A(), prob.csr_C())
+        (qp, qj, qv), (ap, aj, av), (cp, cj, cv) = self._keep
+        self.n, self.me, self.m = prob.N, prob.me, prob.m
+        d = prob.d if prob.m else np.zeros(1)
+        self.h = ctypes.c_void_p(L.ref_qp_create(
+            self.n, self.me, self.m, _ip(qp), _ip(qj), _dp(qv), _dp(prob.c),
+            _ip(ap), _ip(aj), _dp(av), _dp(prob.b), _ip(cp), _ip(cj), _dp(cv), _dp(d)))
+
+    def close(self):
+        if self.h:
+            lib().ref_qp_free(self.h)
+            self.h = None
+
+
+class RefMatrix:
+    """A reference Hqp_IpMatrix plugin ("LQDOCP", "RedSpBKP", "SpBKP", ...)."""
+
+    def __init__(self, name, qp: RefQP):
+        L = lib()
+        self.qp = qp
+        self.h = ctypes.c_void_p(L.ref_mat_create(name.encode()))
+        if not self.h:
+            raise RuntimeError(f"unknown matrix module {name}")
+        self._check(L.ref_mat_init(self.h, qp.h), "init")
+
+    @staticmethod
+    def _check(err, what):
+        if err:
+            raise ArithmeticError(f"reference raised Meschach error {err} in {what}")
+
+    def update(self):
+        self._check(lib().ref_mat_update(self.h, self.qp.h), "update")
+
+    def factor(self, z, w):
+        z = np.ascontiguousarray(z, np.float64)
+        w = np.ascontiguousarray(w, np.float64)
+        self._check(lib().ref_mat_factor(self.h, self.qp.h, len(z), _dp(z), _dp(w)), "factor")
+
+    def _apply(self, mode, z, w, r1, r2, r3, r4, sol=None):
+        q = self.qp
+        if sol is None:
+            dx, dy, dz, dw = np.zeros(q.n), np.zeros(q.me), np.zeros(max(q.m, 1)), np.zeros(max(q.m, 1))
+        else:
+            dx, dy, dz, dw = (np.ascontiguousarray(a, np.float64).copy() for a in sol)
+        res = ctypes.c_double(0)
+        args = [np.ascontiguousarray(a, np.float64) for a in (z, w, r1, r2, r3, r4)]
+        err = lib().ref_mat_apply(self.h, q.h, mode, *[_dp(a) for a in args],
+                                  _dp(dx), _dp(dy), _dp(dz), _dp(dw), ctypes.byref(res))
+        self._check(err, "step/solve")
+        return dx, dy, dz[:q.m], dw[:q.m], res.value
+
+    def step(self, z, w, r1, r2, r3, r4):
+        return self._apply(0, z, w, r1, r2, r3, r4)[:4]
+
+    def solve(self, z, w, r1, r2, r3, r4):
+        return self._apply(1, z, w, r1, r2, r3, r4)
+
+    def residuum(self, z, w, r1, r2, r3, r4, dx, dy, dz, dw):
+        return self._apply(2, z, w, r1, r2, r3, r4, (dx, dy, dz, dw))[4]
+
+    def time(self, z, w, r1, r2, r3, r4, reps=3, nstep=2):
+        tf, ts = ctypes.c_double(0), ctypes.c_double(0)
+        args = [np.ascontiguousarray(a, np.float64) for a in (z, w, r1, r2, r3, r4)]
+        err = lib().ref_mat_time(self.h, self.qp.h, *[_dp(a) for a in args],
+                                 reps, nstep, ctypes.byref(tf), ctypes.byref(ts))
+        self._check(err, "time")
+        return tf.value, ts.value
+
+    def close(self):
+        if self.h:
+            lib().ref_mat_free(self.h)
+            self.h = None
+
+
+def ips_solve(qp: RefQP, solver="Mehrotra", mat="LQDOCP", eps=1e-9, max_iters=0):
+    """Cold-started IP solve; returns dict(x,y,z,iters,result,seconds)."""
+    x, y, z = np.zeros(qp.n), np.zeros(qp.me), np.zeros(max(qp.m, 1))
+    it, res, sec = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
+    err = lib().ref_ips_solve(qp.h, solver.encode(), mat.encode(), ctypes.c_double(eps),
+                              max_iters, _dp(x), _dp(y), _dp(z), ctypes.byref(it),
+                              ctypes.byref(res), ctypes.byref(sec))
+    if err:
+        raise ArithmeticError(f"reference IP solve failed with code {err}")
+    return dict(x=x, y=y, z=z[:qp.m], iters=it.value, result=HQP_RESULT[res.value],
+                seconds=sec.value)
+
+
+def load_plugin(path):
+    if lib().ref_load_plugin(os.fsencode(path)):
+        raise RuntimeError(lib().ref_last_error().decode())
+
+
+def docp_did(kmax=60, qp_solver="", mat_solver="LQDOCP", plugin="", with_cns=1, env=None):
+    """Run the hqp_docp example in a subprocess (global solver state)."""
+    exe = os.path.join(REF_DIR, "docp_ref")
+    out = subprocess.run([exe, str(kmax), qp_solver, mat_solver, plugin, str(with_cns), "0"],
+                         capture_output=True, text=True, timeout=600, env=env)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    if not lines:
+        raise RuntimeError(f"docp_ref failed: rc={out.returncode}\n{out.stdout}\n{out.stderr}")
+    return json.loads(lines[-1])
