@@ -224,3 +224,39 @@ def synth_rhs(prob: LQProblem, seed=4321):
                       ctypes.c_ulonglong(seed), _dp(z), _dp(w), _dp(r1),
                       _dp(r2), _dp(r3), _dp(r4))
     return z, w, r1, r2, r3, r4
+
+
+def add_random_stage_ineq(prob: LQProblem, rows_per_stage=2, nnz_per_row=3, seed=7,
+                          include_terminal=True):
+    """Append general stage-local inequality rows  c'[x_k;u_k] + d >= 0  (mixed
+    state/control constraints like Prg_DID's x2 + 0.5 dt x1 <= 0.01,
+    hqp_docp/Prg_DID.C) to the problem's C; used to exercise the dense
+    C'(z/w)C path of Hqp_IpLQDOCP::factor (hqp/Hqp_IpLQDOCP.C:68-103)."""
+    rng = np.random.default_rng(seed)
+    ptr = list(prob.ineq_ptr)
+    col = list(prob.ineq_col)
+    val = list(prob.ineq_val)
+    d = list(prob.d)
+    nm = prob.nm
+    for k in range(prob.K + (1 if include_terminal else 0)):
+        dk = nm if k < prob.K else prob.nx
+        for _ in range(rows_per_stage):
+            nz = min(nnz_per_row, dk)
+            cols = np.sort(rng.choice(dk, size=nz, replace=False))
+            col.extend((k * nm + cols).tolist())
+            val.extend(rng.uniform(-1, 1, nz).tolist())
+            d.append(float(rng.uniform(0.5, 2.0)))
+            ptr.append(len(col))
+    prob.ineq_ptr = np.asarray(ptr, np.int32)
+    prob.ineq_col = np.asarray(col, np.int32)
+    prob.ineq_val = np.asarray(val, np.float64)
+    prob.d = np.asarray(d, np.float64)
+    return prob
+
+
+def rhs_for(prob: LQProblem, seed=4321):
+    """like synth_rhs but numpy-seeded (works for any row count)"""
+    rng = np.random.default_rng(seed)
+    m = prob.m
+    return (rng.uniform(0.5, 1.5, m), rng.uniform(0.5, 1.5, m), rng.uniform(-1, 1, prob.N),
+            rng.uniform(-1, 1, prob.me), rng.uniform(-1, 1, m), rng.uniform(-1, 1, m))

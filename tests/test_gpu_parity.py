@@ -1,0 +1,198 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle on identical seeded inputs, against the golden fixtures produced by the
+unmodified reference, and -- at full BASELINE sizes -- through size-independent
+properties (KKT residual, linearity, refinement fixed point)."""
+import numpy as np
+import pytest
+
+from common import golden_step_cases, load_golden, make_problem, relerr
+from hqp_b200.ipcuda import IpCuda, SingularError
+from hqp_b200.problem import add_random_stage_ineq, rhs_for, synth_lqdocp, synth_rhs
+from oracle.portoracle import PortOracle
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10  # north star: KKT solutions within relative 1e-10 of the reference
+
+
+@pytest.mark.parametrize("name", golden_step_cases())
+@pytest.mark.parametrize("nseg", [1, 0, 3])
+def test_step_and_solve_match_reference_golden(name, nseg):
+    g, cfg = load_golden(name)
+    p = make_problem(*cfg)
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    e.factor(g["z"], g["w"])
+    dx, dy, dz, dw = e.step(g["r1"], g["r2"], g["r3"], g["r4"])
+    for mine, key in ((dx, "dx"), (dy, "dy"), (dz, "dz"), (dw, "dw")):
+        assert relerr(mine, g[key]) < TOL, (key, nseg)
+    sx, sy, sz, sw, res, nsteps = e.solve(g["r1"], g["r2"], g["r3"], g["r4"])
+    for mine, key in ((sx, "sx"), (sy, "sy"), (sz, "sz"), (sw, "sw")):
+        assert relerr(mine, g[key]) < TOL, (key, nseg)
+    assert res <= 1e-10 and nsteps == 1  # the reference needs no refinement either
+    e.close()
+
+
+SHAPES = [  # nx nu K bounds gen fixed nseg
+    (2, 1, 1, 1, 0, 1, 1), (2, 1, 2, 1, 0, 1, 0), (1, 1, 9, 1, 0, 1, 3), (3, 1, 33, 1, 1, 1, 4),
+    (12, 4, 50, 1, 0, 1, 1), (12, 4, 50, 1, 2, 0, 7), (20, 10, 128, 1, 0, 1, 0),
+    (20, 10, 131, 0, 0, 0, 9), (33, 7, 40, 1, 0, 1, 5), (40, 10, 64, 1, 0, 1, 0),
+    (8, 24, 40, 1, 0, 1, 4),
+]
+
+
+@pytest.mark.parametrize("cfg", SHAPES)
+def test_matches_cpu_oracle(cfg):
+    *pc, nseg = cfg
+    p = make_problem(*pc)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=17)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < TOL
+    V, R = e.get_factor()
+    assert relerr(V[0], o.Vxx()) < TOL and relerr(R[0], o.Rux()) < TOL
+    # both residuum implementations agree on the same vectors
+    rg = e.residuum(r1, r2, r3, r4, *mine)
+    ro = o.residuum(r1, r2, r3, r4, *mine)
+    assert abs(rg - ro) <= 1e-12 * max(1.0, ro)
+    e.close(); o.close()
+
+
+def test_batched_instances_match_single():
+    """config 3 shape: independent MPC QPs, one CTA per instance."""
+    nx, nu, K, B = 12, 4, 50, 5
+    probs = [synth_lqdocp(nx, nu, K, seed=100 + i) for i in range(B)]
+    rhs = [rhs_for(p, seed=200 + i) for i, p in enumerate(probs)]
+    e = IpCuda(probs[0], batch=B)
+    e.update(Q=np.stack([p.Q for p in probs]), fx=np.stack([p.fx for p in probs]),
+             fu=np.stack([p.fu for p in probs]), ineq_val=np.stack([p.ineq_val for p in probs]))
+    cat = [np.concatenate([r[i] for r in rhs]) for i in range(6)]
+    e.factor(cat[0], cat[1])
+    out = e.step(*cat[2:])
+    sizes = (probs[0].N, probs[0].me, probs[0].m, probs[0].m)
+    for i, p in enumerate(probs):
+        o = PortOracle(p)
+        o.factor(rhs[i][0], rhs[i][1])
+        ref = o.step(*rhs[i][2:])
+        for a, b, n in zip(out, ref, sizes):
+            assert relerr(a[i * n:(i + 1) * n], b) < TOL
+        o.close()
+    e.close()
+
+
+def test_ill_conditioned_ip_iterate_with_refinement():
+    """late-IP regime: z/w over 20 decades; solve() must converge like the oracle's."""
+    p = synth_lqdocp(10, 4, 96)
+    _, _, r1, r2, r3, r4 = rhs_for(p, seed=8)
+    rng = np.random.default_rng(1)
+    z = 10.0 ** rng.uniform(-10, 0, p.m)
+    w = 10.0 ** rng.uniform(-10, 0, p.m)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ox, oy, oz, ow, ores, _ = o.solve(r1, r2, r3, r4)
+    for nseg in (1, 6):
+        e = IpCuda(p, nseg=nseg)
+        e.update()
+        e.factor(z, w)
+        dx, dy, dz, dw, res, nsteps = e.solve(r1, r2, r3, r4)
+        assert np.isfinite(res) and res <= max(10 * ores, 1e-10)
+        assert relerr(dx, ox) < 1e-8 and relerr(dy, oy) < 1e-8
+        e.close()
+    o.close()
+
+
+def test_singular_stage_reports_e_sing():
+    """Guu == 0 (no cost on u, fu = 0): the reference's BKPsolve raises E_SING
+    (meschach/bkpfacto.c:273-286); the ABI must return the same code."""
+    p = synth_lqdocp(3, 2, 6, bounds=False)
+    p.Q[:] = 0.0
+    p.fu[:] = 0.0
+    e = IpCuda(p, nseg=1)
+    e.update()
+    with pytest.raises(SingularError):
+        e.factor(np.zeros(0), np.zeros(0))
+    e.close()
+
+
+def test_update_changes_values_factor_reuses_structure():
+    p = synth_lqdocp(6, 3, 40, seed=1)
+    p2 = synth_lqdocp(6, 3, 40, seed=2)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=3)
+    e = IpCuda(p)
+    for prob in (p, p2, p):
+        e.update(Q=prob.Q, fx=prob.fx, fu=prob.fu, ineq_val=prob.ineq_val)
+        e.factor(z, w)
+        mine = e.step(r1, r2, r3, r4)
+        o = PortOracle(prob)
+        o.factor(z, w)
+        ref = o.step(r1, r2, r3, r4)
+        for a, b in zip(mine, ref):
+            assert relerr(a, b) < TOL
+        o.close()
+    e.close()
+
+
+def test_no_inequalities_m_zero():
+    """factor/solve with m = 0 (z,w,r3,r4 of dim 0) must work."""
+    p = synth_lqdocp(5, 2, 20, bounds=False)
+    _, _, r1, r2, r3, r4 = rhs_for(p, seed=4)
+    e = IpCuda(p)
+    e.update()
+    e.factor(np.zeros(0), np.zeros(0))
+    dx, dy, dz, dw, res, _ = e.solve(r1, r2, r3, r4)
+    assert dz.size == 0 and res <= 1e-10
+    e.close()
+
+
+# ---- full BASELINE sizes: properties that need no CPU oracle ------------------
+@pytest.fixture(scope="module")
+def c2():
+    p = synth_lqdocp(20, 10, 10000)
+    e = IpCuda(p)
+    e.update()
+    rhs = synth_rhs(p)
+    e.factor(rhs[0], rhs[1])
+    yield p, e, rhs
+    e.close()
+
+
+def test_c2_residual_and_refinement(c2):
+    p, e, (z, w, r1, r2, r3, r4) = c2
+    assert e.nseg > 1  # the parallel-in-time path is the one under test
+    dx, dy, dz, dw, res, nsteps = e.solve(r1, r2, r3, r4)
+    assert res <= 1e-10 and nsteps == 1
+    assert e.residuum(r1, r2, r3, r4, dx, dy, dz, dw) == res
+
+
+def test_c2_linearity_and_segment_independence(c2):
+    p, e, (z, w, r1, r2, r3, r4) = c2
+    a = e.step(r1, r2, r3, r4)
+    b = e.step(2 * r1, 2 * r2, 2 * r3, 2 * r4)
+    for u, v in zip(a, b):
+        assert relerr(v, 2 * u) < 1e-12
+    e2 = IpCuda(p, nseg=37)
+    e2.update()
+    e2.factor(z, w)
+    c = e2.step(r1, r2, r3, r4)
+    for u, v in zip(a, c):
+        assert relerr(v, u) < 1e-10
+    e2.close()
+
+
+def test_c2_prefix_matches_oracle_on_truncated_horizon():
+    """the first 300 stages of the C2 workload, checked against the CPU oracle"""
+    p = synth_lqdocp(20, 10, 300)
+    z, w, r1, r2, r3, r4 = synth_rhs(p)
+    o = PortOracle(p); o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p); e.update(); e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < TOL
+    e.close(); o.close()
