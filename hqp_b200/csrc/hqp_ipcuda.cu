@@ -53,9 +53,31 @@ struct hqpcu_handle {
   double *res_host = nullptr;  // pinned
   int *status_host = nullptr;  // pinned
   bool factored = false;
+  // optional per-kernel CUDA-event timing (bench.py roofline section)
+  bool profiling = false;
+  struct Span { const char *name; cudaEvent_t e0, e1; };
+  std::vector<Span> spans;
   size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0;
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
 };
+
+// launch wrapper: counts the launch and, when profiling, brackets it with
+// CUDA events on the launching stream
+#define LAUNCH(h, kname, ...)                                                 \
+  do {                                                                        \
+    hqpcu_handle::Span sp_{#kname, nullptr, nullptr};                         \
+    if ((h)->profiling) {                                                     \
+      cudaEventCreate(&sp_.e0);                                               \
+      cudaEventCreate(&sp_.e1);                                               \
+      cudaEventRecord(sp_.e0, (h)->stream);                                   \
+    }                                                                         \
+    kname __VA_ARGS__;                                                        \
+    (h)->launches++;                                                          \
+    if ((h)->profiling) {                                                     \
+      cudaEventRecord(sp_.e1, (h)->stream);                                   \
+      (h)->spans.push_back(sp_);                                              \
+    }                                                                         \
+  } while (0)
 
 template <typename T>
 static int dev_alloc(hqpcu_handle *h, T **p, size_t count) {
@@ -331,17 +353,12 @@ static int launch_factor(hqpcu_handle *h) {
   const LqDev &d = h->d;
   CU(cudaMemsetAsync(d.status, 0, sizeof(int), h->stream));
   const dim3 gseg(d.P, d.batch);
-  if (d.P > 1) {
-    seg_element_kernel<<<gseg, h->thr_factor, h->smem_k1, h->stream>>>(d);
-    h->launches++;
-  }
-  seg_scan_kernel<<<d.batch, h->thr_factor, h->smem_k2, h->stream>>>(d);
-  seg_riccati_kernel<<<gseg, h->thr_factor, h->smem_k3, h->stream>>>(d);
-  h->launches += 2;
-  if (!d.fixed_x0) {
-    x0_factor_kernel<<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), h->stream>>>(d);
-    h->launches++;
-  }
+  if (d.P > 1) LAUNCH(h, seg_element_kernel, <<<gseg, h->thr_factor, h->smem_k1, h->stream>>>(d));
+  LAUNCH(h, seg_scan_kernel, <<<d.batch, h->thr_factor, h->smem_k2, h->stream>>>(d));
+  LAUNCH(h, seg_riccati_kernel, <<<gseg, h->thr_factor, h->smem_k3, h->stream>>>(d));
+  if (!d.fixed_x0)
+    LAUNCH(h, x0_factor_kernel,
+           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), h->stream>>>(d));
   CU(cudaGetLastError());
   h->factored = true;
   return HQPCU_OK;
@@ -420,16 +437,15 @@ static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, cons
   const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
   const size_t sc = (size_t)(d.nx + 2) * sizeof(double);
   cudaStream_t s = h->stream;
-  solve_pre_kernel<<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4);
-  solve_back_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 0);
-  solve_back_scan_kernel<<<d.batch, h->thr_chain, sc, s>>>(d);
-  solve_back_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 1);
-  solve_mid_kernel<<<gk, h->thr_stage, sv, s>>>(d, r2);
-  solve_fwd_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 0);
-  solve_fwd_scan_kernel<<<d.batch, h->thr_chain, sc, s>>>(d, r2);
-  solve_fwd_kernel<<<gseg, h->thr_chain, sc, s>>>(d, 1);
-  solve_post_kernel<<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw);
-  h->launches += 9;
+  LAUNCH(h, solve_pre_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4));
+  LAUNCH(h, solve_back_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 0));
+  LAUNCH(h, solve_back_scan_kernel, <<<d.batch, h->thr_chain, sc, s>>>(d));
+  LAUNCH(h, solve_back_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 1));
+  LAUNCH(h, solve_mid_kernel, <<<gk, h->thr_stage, sv, s>>>(d, r2));
+  LAUNCH(h, solve_fwd_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 0));
+  LAUNCH(h, solve_fwd_scan_kernel, <<<d.batch, h->thr_chain, sc, s>>>(d, r2));
+  LAUNCH(h, solve_fwd_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 1));
+  LAUNCH(h, solve_post_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -488,10 +504,9 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
   CU(cudaMemsetAsync(h->res_dev, 0, sizeof(double), h->stream));
   const dim3 gall(d.K + 1, d.batch);
   const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
-  residuum_kernel<<<gall, h->thr_stage, sv, h->stream>>>(
+  LAUNCH(h, residuum_kernel, <<<gall, h->thr_stage, sv, h->stream>>>(
       d, r1, r2, r3, r4, dx, dy, dz, dw, keep ? h->t1 : nullptr, keep ? h->t2 : nullptr,
-      keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev);
-  h->launches++;
+      keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
@@ -548,15 +563,13 @@ static int solve_core(hqpcu_handle *h, double eps, const double *r1, const doubl
     steps++;
     double alpha = 1.0;
     do {
-      axpy4_kernel<<<ablocks, 256, 0, h->stream>>>(alpha, h->e1, dx, n1, h->e2, dy, n2, h->e3,
-                                                   dz, n3, h->e4, dw, n3);
-      h->launches++;
+      LAUNCH(h, axpy4_kernel, <<<ablocks, 256, 0, h->stream>>>(alpha, h->e1, dx, n1, h->e2, dy, n2,
+                                                              h->e3, dz, n3, h->e4, dw, n3));
       rc = launch_residuum(h, r1, r2, r3, r4, dx, dy, dz, dw, true, &res);
       if (rc) return rc;
       if (res > res_last) {
-        axpy4_kernel<<<ablocks, 256, 0, h->stream>>>(-alpha, h->e1, dx, n1, h->e2, dy, n2,
-                                                     h->e3, dz, n3, h->e4, dw, n3);
-        h->launches++;
+        LAUNCH(h, axpy4_kernel, <<<ablocks, 256, 0, h->stream>>>(-alpha, h->e1, dx, n1, h->e2, dy,
+                                                                n2, h->e3, dz, n3, h->e4, dw, n3));
         alpha -= 0.3;
       }
     } while (res > res_last && alpha > 0.0);
@@ -587,6 +600,47 @@ int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
                   h->u_dw, res, nsteps);
   if (rc) return rc;
   return d2h_sol(h, dx, dy, dz, dw);
+}
+
+int hqpcu_profile(hqpcu_handle *h, int on) {
+  if (!h) return HQPCU_E_NULL;
+  h->profiling = on != 0;
+  return HQPCU_OK;
+}
+
+// Synchronises, sums the CUDA-event time of every launch recorded since the
+// last call and writes {"kernel": {"ms": total, "n": launches}, ...} to buf.
+int hqpcu_profile_read(hqpcu_handle *h, char *buf, int len) {
+  if (!h || !buf || len < 3) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  std::vector<std::string> names;
+  std::vector<double> ms;
+  std::vector<int> cnt;
+  for (auto &sp : h->spans) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, sp.e0, sp.e1);
+    cudaEventDestroy(sp.e0);
+    cudaEventDestroy(sp.e1);
+    size_t i = 0;
+    for (; i < names.size(); i++)
+      if (names[i] == sp.name) break;
+    if (i == names.size()) { names.push_back(sp.name); ms.push_back(0); cnt.push_back(0); }
+    ms[i] += t;
+    cnt[i]++;
+  }
+  h->spans.clear();
+  std::string out = "{";
+  for (size_t i = 0; i < names.size(); i++) {
+    char tmp[160];
+    snprintf(tmp, sizeof tmp, "%s\"%s\": {\"ms\": %.6f, \"n\": %d}", i ? ", " : "",
+             names[i].c_str(), ms[i], cnt[i]);
+    out += tmp;
+  }
+  out += "}";
+  if ((int)out.size() + 1 > len) return HQPCU_E_SIZES;
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return HQPCU_OK;
 }
 
 int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {

@@ -126,6 +126,15 @@ class IpCuda:
     def sync_status(self):
         return lib().hqpcu_sync_status(self.h)
 
+    def profile(self, on=True):
+        _check(lib().hqpcu_profile(self.h, int(on)), "hqpcu_profile")
+
+    def profile_read(self):
+        import json
+        buf = ctypes.create_string_buffer(8192)
+        _check(lib().hqpcu_profile_read(self.h, buf, len(buf)), "hqpcu_profile_read")
+        return json.loads(buf.value.decode())
+
     # -- host-pointer API (what the plugin calls) --------------------------
     def update(self, Q=None, fx=None, fu=None, ineq_val=None):
         p = self.prob

@@ -135,6 +135,13 @@ int hqpcu_solve_dev(hqpcu_handle *h, double eps, const double *r1,
                     double *dx, double *dy, double *dz, double *dw,
                     double *res /* host */, int *nsteps);
 
+/* --- per-kernel timing with CUDA events on the launching stream (bench.py's
+ *     roofline section).  hqpcu_profile_read synchronises and writes a JSON
+ *     object {"kernel": {"ms": total, "n": launches}, ...} for everything
+ *     launched since the previous read.                                         */
+int hqpcu_profile(hqpcu_handle *h, int on);
+int hqpcu_profile_read(hqpcu_handle *h, char *buf, int len);
+
 /* --- read-back of factor state for tests: Vxx [batch][(K+1)][nx*nx],
  *     Rux [batch][K][nu*nx] (either may be NULL)                               */
 int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux);
