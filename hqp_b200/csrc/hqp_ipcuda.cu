@@ -25,6 +25,24 @@
 
 static thread_local std::string g_err;
 
+// Compile-time specialisations of the factor kernels for the stage shapes named
+// in BASELINE.json; any other shape runs the <0,0> (runtime-dimension) build of
+// the same code.
+#define LQ_DISPATCH_NXNU(nx_, nu_, CALL)                                       \
+  do {                                                                        \
+    if ((nx_) == 20 && (nu_) == 10) { CALL(20, 10); }                         \
+    else if ((nx_) == 12 && (nu_) == 4) { CALL(12, 4); }                      \
+    else if ((nx_) == 40 && (nu_) == 10) { CALL(40, 10); }                    \
+    else { CALL(0, 0); }                                                      \
+  } while (0)
+#define LQ_DISPATCH_NX(nx_, nu_, CALL)                                         \
+  do {                                                                        \
+    if ((nx_) == 20 && (nu_) == 10) { CALL(20); }                             \
+    else if ((nx_) == 12 && (nu_) == 4) { CALL(12); }                         \
+    else if ((nx_) == 40 && (nu_) == 10) { CALL(40); }                        \
+    else { CALL(0); }                                                         \
+  } while (0)
+
 #define CU(call)                                                              \
   do {                                                                        \
     cudaError_t e_ = (call);                                                  \
@@ -57,8 +75,9 @@ struct hqpcu_handle {
   bool profiling = false;
   struct Span { const char *name; cudaEvent_t e0, e1; };
   std::vector<Span> spans;
-  size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0;
+  size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0, smem_cmp = 0, smem_psi = 0, smem_chain = 0;
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
+  int max_el = 0;  // elements per instance the seg* arrays were sized for
 };
 
 // launch wrapper: counts the launch and, when profiling, brackets it with
@@ -101,23 +120,42 @@ static int dev_upload(hqpcu_handle *h, const T **p, const std::vector<T> &v) {
 
 static size_t pad2(size_t n) { return (n + 1) & ~size_t(1); }
 
-// segments per instance and stages per segment
+static void build_tree(LqTree &t, int P, int R) {
+  t.R = R;
+  t.nlev = 0;
+  int cnt = P, off = 0;
+  for (;;) {
+    t.cnt[t.nlev] = cnt;
+    t.off[t.nlev] = off;
+    off += cnt;
+    t.nlev++;
+    if (cnt <= R || t.nlev == LQ_MAXLEV) break;
+    cnt = (cnt + R - 1) / R;
+  }
+  t.nel = off;
+}
+
+// segments per instance, stages per segment and the hierarchies above them
 static void choose_segments(hqpcu_handle *h, int nseg) {
   const int K = h->dims.K;
+  LqDev &d = h->d;
   int P = nseg;
   if (P <= 0) {
     // enough independent instances already fill the machine: sequential sweep
     if (h->dims.batch >= 64 || K < 32)
       P = 1;
     else
-      P = (int)std::lround(std::sqrt(1.5 * K));
+      P = std::max(2, K / 12);  // ~12 stages per segment
   }
   P = std::max(1, std::min(P, std::max(1, K / 2)));
+  P = std::min(P, 16384);
   int L = (K + P - 1) / P;
   if (L < 1) L = 1;
   P = std::max(1, (K + L - 1) / L);
-  h->d.P = P;
-  h->d.L = L;
+  d.P = P;
+  d.L = L;
+  build_tree(d.ft, P, 2);
+  build_tree(d.st, P, 32);
 }
 
 static int set_smem(const void *fn, size_t bytes) {
@@ -140,6 +178,10 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   }
   if (dims->nu < 1) {
     g_err = "hqpcu_create: nu = 0 is not supported";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  if (dims->nx > 64) {
+    g_err = "hqpcu_create: nx > 64 needs the tiled large-block kernels (not built yet)";
     return HQPCU_E_UNSUPPORTED;
   }
   if (dims->n_eq > 0) {
@@ -201,6 +243,12 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     std::vector<int> fill(srow_ptr.begin(), srow_ptr.end() - 1);
     for (int r = 0; r < m; r++) srow[fill[stage[r]]++] = r;
   }
+  std::vector<int> grow_ptr(K + 2, 0), grow;
+  for (int k = 0; k <= K; k++) {
+    for (int rr = srow_ptr[k]; rr < srow_ptr[k + 1]; rr++)
+      if (ptr[srow[rr] + 1] - ptr[srow[rr]] > 1) grow.push_back(srow[rr]);
+    grow_ptr[k + 1] = (int)grow.size();
+  }
   std::vector<int> vcol_ptr(d.N + 1, 0), vcol_row(d.nnz), vcol_nz(d.nnz);
   for (int r = 0; r < m; r++)
     for (int e = ptr[r]; e < ptr[r + 1]; e++) vcol_ptr[stage[r] * nm + lcol[e] + 1]++;
@@ -221,6 +269,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_upload(h, &d.ineq_lcol, lcol));
   TRY(dev_upload(h, &d.srow_ptr, srow_ptr));
   TRY(dev_upload(h, &d.srow, srow));
+  TRY(dev_upload(h, &d.grow_ptr, grow_ptr));
+  TRY(dev_upload(h, &d.grow, grow));
   TRY(dev_upload(h, &d.vcol_ptr, vcol_ptr));
   TRY(dev_upload(h, &d.vcol_row, vcol_row));
   TRY(dev_upload(h, &d.vcol_nz, vcol_nz));
@@ -238,16 +288,23 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_alloc(h, &d.Rux, SB * K * nu * nx));
   TRY(dev_alloc(h, &d.LD, SB * K * nu * nu));
   TRY(dev_alloc(h, &d.Phi, SB * K * nx * nx));
-  // segment arrays are sized for the largest P this handle may use (K)
-  const size_t PM = (size_t)std::max(d.P, 1);
+  // bulk-copy (TMA) path needs every per-stage slab to be a 16-byte multiple
+  d.use_tma = (nx % 2 == 0 && nu % 2 == 0) ? 1 : 0;
+  TRY(dev_alloc(h, &d.hdiag, SB * d.N));
+  // element arrays are sized for the hierarchy chosen here; hqpcu_set_nseg may
+  // only shrink it
+  const size_t PM = (size_t)std::max(d.st.nel, 1);
+  const size_t PF = (size_t)std::max(d.ft.nel, 1);
+  h->max_el = d.P;
   h->dims.nseg = d.P;
-  TRY(dev_alloc(h, &d.segA, SB * PM * nx * nx));
-  TRY(dev_alloc(h, &d.segC, SB * PM * nx * nx));
-  TRY(dev_alloc(h, &d.segJ, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segA, SB * PF * nx * nx));
+  TRY(dev_alloc(h, &d.segC, SB * PF * nx * nx));
+  TRY(dev_alloc(h, &d.segJ, SB * PF * nx * nx));
   TRY(dev_alloc(h, &d.segPsi, SB * PM * nx * nx));
-  TRY(dev_alloc(h, &d.segVb, SB * PM * nx * nx));
+  TRY(dev_alloc(h, &d.segVb, SB * PF * nx * nx));
   TRY(dev_alloc(h, &d.V0f, SB * nx * nx));
   TRY(dev_alloc(h, &d.status, 1));
+  TRY(dev_alloc(h, &d.dbg, 16));
   TRY(dev_alloc(h, &d.g, SB * d.N));
   TRY(dev_alloc(h, &d.wv, SB * K * nx));
   TRY(dev_alloc(h, &d.q, SB * K * nx));
@@ -280,20 +337,44 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   h->thr_chain = 4 * (((nx + 31) / 32) * 32);
   h->thr_stage = std::max(32, ((nm + 31) / 32) * 32);
   const size_t nn = pad2((size_t)nx * nx), nf = pad2((size_t)nx * nm), gg = pad2((size_t)nm * nm),
-               ru = pad2((size_t)nu * nx), xu = pad2((size_t)nx * nu);
-  h->smem_k1 = (4 * nn + 2 * nf + gg + ru + nn + 2 * xu) * sizeof(double);
-  h->smem_k2 = (3 * nn + pad2((size_t)2 * nx * nx) + gg) * sizeof(double);
-  h->smem_k3 = (nn + 2 * nf + gg + ru + 3 * nn) * sizeof(double);
+               ru = pad2((size_t)nu * nx), xu = pad2((size_t)nx * nu), hd = pad2((size_t)nm);
+  const size_t pipe = 2 * (gg + nn + xu + hd) * sizeof(double) + 2 * sizeof(uint64_t);
+  h->smem_k1 = pipe + (4 * nn + nf + ru + nn + 2 * xu) * sizeof(double);
+  h->smem_k3 = pipe + (nn + nf + ru + 3 * nn) * sizeof(double);
+  h->smem_k2 = (4 * nn + pad2((size_t)2 * nx * nx)) * sizeof(double);
+  h->smem_cmp = (5 * nn + pad2((size_t)3 * nx * nx) + 2 * nn + pad2((size_t)2 * nx * nx)) *
+                sizeof(double);
+  h->smem_psi = 3 * nn * sizeof(double);
+  h->smem_chain = (pad2((size_t)LQ_RING * (nx * nx + 2 * nx)) + pad2((size_t)nx)) * sizeof(double) +
+                  LQ_RING * sizeof(uint64_t);
   const size_t smem_max = 227 * 1024;
-  if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max) {
+  if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max ||
+      h->smem_cmp > smem_max) {
     g_err = "hqpcu_create: stage blocks too large for the shared-memory kernels";
     hqpcu_destroy(h);
     return HQPCU_E_UNSUPPORTED;
   }
-  TRY(set_smem((const void *)seg_element_kernel, h->smem_k1));
-  TRY(set_smem((const void *)seg_scan_kernel, h->smem_k2));
-  TRY(set_smem((const void *)seg_riccati_kernel, h->smem_k3));
+#define SET_A(NX_, NU_)                                                        \
+  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_>, h->smem_k1));      \
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_>, h->smem_k3));
+#define SET_B(NX_)                                                             \
+  TRY(set_smem((const void *)elem_scan_kernel<NX_>, h->smem_k2));             \
+  TRY(set_smem((const void *)elem_compose_kernel<NX_>, h->smem_cmp));         \
+  TRY(set_smem((const void *)psi_compose_kernel<NX_>, h->smem_psi));
+  LQ_DISPATCH_NXNU(nx, nu, SET_A);
+  LQ_DISPATCH_NX(nx, nu, SET_B);
+#undef SET_A
+#undef SET_B
   TRY(set_smem((const void *)x0_factor_kernel, nn * sizeof(double)));
+  if (h->smem_chain > smem_max) {
+    g_err = "hqpcu_create: chain ring exceeds shared memory";
+    hqpcu_destroy(h);
+    return HQPCU_E_UNSUPPORTED;
+  }
+  TRY(set_smem((const void *)solve_back_kernel, h->smem_chain));
+  TRY(set_smem((const void *)solve_fwd_kernel, h->smem_chain));
+  TRY(set_smem((const void *)solve_scan_kernel<true>, h->smem_chain));
+  TRY(set_smem((const void *)solve_scan_kernel<false>, h->smem_chain));
 #undef TRY
   *out = h;
   return HQPCU_OK;
@@ -351,14 +432,46 @@ int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx, const d
 // ------------------------------------------------------------------ factor --
 static int launch_factor(hqpcu_handle *h) {
   const LqDev &d = h->d;
-  CU(cudaMemsetAsync(d.status, 0, sizeof(int), h->stream));
+  cudaStream_t s = h->stream;
+  CU(cudaMemsetAsync(d.status, 0, sizeof(int), s));
   const dim3 gseg(d.P, d.batch);
-  if (d.P > 1) LAUNCH(h, seg_element_kernel, <<<gseg, h->thr_factor, h->smem_k1, h->stream>>>(d));
-  LAUNCH(h, seg_scan_kernel, <<<d.batch, h->thr_factor, h->smem_k2, h->stream>>>(d));
-  LAUNCH(h, seg_riccati_kernel, <<<gseg, h->thr_factor, h->smem_k3, h->stream>>>(d));
+  if (d.m) {
+    const size_t tot = (size_t)d.batch * d.N;
+    const int blocks = (int)std::min<size_t>((tot + 255) / 256, 148 * 8);
+    LAUNCH(h, hdiag_kernel, <<<blocks, 256, 0, s>>>(d));
+  }
+#define L_K1(NX_, NU_) LAUNCH(h, (seg_element_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k1, s>>>(d))
+#define L_K3(NX_, NU_) LAUNCH(h, (seg_riccati_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k3, s>>>(d))
+#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, 128, h->smem_cmp, s>>>(d, l))
+#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), 128, h->smem_k2, s>>>(d, d.ft.nlev - 1, 1))
+#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, 128, h->smem_k2, s>>>(d, l, 0))
+#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, 128, h->smem_psi, s>>>(d, l))
+  if (d.P > 1) {
+    LQ_DISPATCH_NXNU(d.nx, d.nu, L_K1);
+    for (int l = 0; l + 1 < d.ft.nlev; l++) {
+      const dim3 gl(d.ft.cnt[l + 1], d.batch);
+      LQ_DISPATCH_NX(d.nx, d.nu, L_CMP);
+    }
+  }
+  LQ_DISPATCH_NX(d.nx, d.nu, L_TOP);
+  for (int l = d.ft.nlev - 2; l >= 0; l--) {
+    const dim3 gl(d.ft.cnt[l + 1], d.batch);
+    LQ_DISPATCH_NX(d.nx, d.nu, L_DWN);
+  }
+  LQ_DISPATCH_NXNU(d.nx, d.nu, L_K3);
+  for (int l = 0; l + 1 < d.st.nlev; l++) {
+    const dim3 gl(d.st.cnt[l + 1], d.batch);
+    LQ_DISPATCH_NX(d.nx, d.nu, L_PSI);
+  }
+#undef L_K1
+#undef L_K3
+#undef L_CMP
+#undef L_TOP
+#undef L_DWN
+#undef L_PSI
   if (!d.fixed_x0)
     LAUNCH(h, x0_factor_kernel,
-           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), h->stream>>>(d));
+           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
   CU(cudaGetLastError());
   h->factored = true;
   return HQPCU_OK;
@@ -416,11 +529,13 @@ int hqpcu_sync_status(hqpcu_handle *h) {
 
 int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
   if (!h) return HQPCU_E_NULL;
-  if (nseg > h->dims.nseg && h->dims.nseg > 0 && nseg > 1) {
+  const int oldP = h->d.P;
+  choose_segments(h, nseg);
+  if (h->d.P > h->max_el) {
+    choose_segments(h, oldP);
     g_err = "hqpcu_set_nseg: cannot exceed the segment count of hqpcu_create";
     return HQPCU_E_SIZES;
   }
-  choose_segments(h, nseg);
   h->factored = false;
   return HQPCU_OK;
 }
@@ -434,17 +549,28 @@ static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, cons
     return HQPCU_E_NULL;
   }
   const dim3 gall(d.K + 1, d.batch), gk(d.K, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
-  const size_t sc = (size_t)(d.nx + 2) * sizeof(double);
+  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const size_t sc = h->smem_chain;
+  const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
   LAUNCH(h, solve_pre_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4));
-  LAUNCH(h, solve_back_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 0));
-  LAUNCH(h, solve_back_scan_kernel, <<<d.batch, h->thr_chain, sc, s>>>(d));
-  LAUNCH(h, solve_back_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 1));
+  // backward: segment chains, hierarchy up / top / down, segment chains again
+  LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 0));
+  for (int l = 0; l + 1 < d.st.nlev; l++)
+    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
+  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, sc, s>>>(d, d.st.nlev - 1, 1, r2));
+  for (int l = d.st.nlev - 2; l >= 0; l--)
+    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
+  LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_mid_kernel, <<<gk, h->thr_stage, sv, s>>>(d, r2));
-  LAUNCH(h, solve_fwd_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 0));
-  LAUNCH(h, solve_fwd_scan_kernel, <<<d.batch, h->thr_chain, sc, s>>>(d, r2));
-  LAUNCH(h, solve_fwd_kernel, <<<gseg, h->thr_chain, sc, s>>>(d, 1));
+  // forward
+  LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 0));
+  for (int l = 0; l + 1 < d.st.nlev; l++)
+    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
+  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, sc, s>>>(d, d.st.nlev - 1, 1, r2));
+  for (int l = d.st.nlev - 2; l >= 0; l--)
+    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
+  LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_post_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
@@ -640,6 +766,14 @@ int hqpcu_profile_read(hqpcu_handle *h, char *buf, int len) {
   out += "}";
   if ((int)out.size() + 1 > len) return HQPCU_E_SIZES;
   memcpy(buf, out.c_str(), out.size() + 1);
+  return HQPCU_OK;
+}
+
+int hqpcu_debug_stamps(hqpcu_handle *h, long long *out16) {
+  if (!h || !out16) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  CU(cudaStreamSynchronize(h->stream));
+  CU(cudaMemcpy(out16, h->d.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
   return HQPCU_OK;
 }
 

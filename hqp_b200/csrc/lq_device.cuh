@@ -9,16 +9,35 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define LQ_MAXLEV 16
+#define LQ_NT 128  // threads per CTA of the factor kernels (compile-time)
+
+// R-ary hierarchy over the P level-0 segments of one instance
+struct LqTree {
+  int R;                // group size
+  int nlev;             // number of levels (level 0 = segments)
+  int cnt[LQ_MAXLEV];   // elements per level
+  int off[LQ_MAXLEV];   // element offset of the level inside the per-instance arrays
+  int nel;              // total elements per instance
+};
+
 struct LqDev {
   int K, nx, nu, nm, batch;
-  int P, L;           // segments per instance, stages per segment
+  int P, L;           // level-0 segments per instance, stages per segment
+  LqTree ft;          // factor hierarchy (segA/segC/segJ/segVb), binary: every
+                      // level is one fully parallel combine deep
+  LqTree st;          // solve hierarchy (segPsi and the boundary vectors), wide:
+                      // its per-element work is one mat-vec, launches dominate
   int fixed_x0;
   int m, nnz;         // inequality rows / nonzeros per instance
   int N, me;          // per-instance vector lengths
+  int use_tma;        // per-stage slabs are 16-byte multiples: bulk-copy path
   // inequality structure (shared by all instances)
   const int *ineq_stage, *ineq_ptr, *ineq_lcol;
   const int *srow_ptr;  // [K+2] rows sorted by stage
   const int *srow;      // [m]
+  const int *grow_ptr;  // [K+2] rows with more than one nonzero, sorted by stage
+  const int *grow;      // [..]
   const int *vcol_ptr;  // [N+1] per variable: entries of C in that column
   const int *vcol_row;  // [nnz] row of the entry
   const int *vcol_nz;   // [nnz] index of the entry in the CSR value array
@@ -26,16 +45,20 @@ struct LqDev {
   const double *Q, *fx, *fu, *cval;
   // captured at factor
   const double *z, *w;
+  double *hdiag;   // [batch][N] diagonal of C'(z/w)C contributed by single-entry rows
   // factor state
   double *V;       // [batch][K+1][nx*nx]   value-function Hessians Vxx
   double *Rux;     // [batch][K][nu*nx]     feedback gains
   double *LD;      // [batch][K][nu*nu]     LDL^T of Guu: unit L below, 1/D on the diagonal
   double *Phi;     // [batch][K][nx*nx]     closed loop fx - fu Rux
-  double *segA, *segC, *segJ;  // [batch][P][nx*nx] segment elements
-  double *segPsi;  // [batch][P][nx*nx]     closed-loop transition over the segment
-  double *segVb;   // [batch][P][nx*nx]     Vxx at the segment end
+  // factor hierarchy: element e of level l at [(b*ft.nel + ft.off[l] + e) * nx*nx]
+  double *segA, *segC, *segJ;  // boundary elements (zero-terminal-cost condensation)
+  double *segVb;   // Vxx at the element's end
+  // solve hierarchy: element e of level l at [(b*st.nel + st.off[l] + e) * ...]
+  double *segPsi;  // closed-loop transition across the element
   double *V0f;     // [batch][nx*nx]        LDL^T of Vxx[0] (free x0)
   int *status;     // device status word (0 ok)
+  long long *dbg;  // [16] clock64 stamps (LQ_TIMING builds only)
   // solve scratch
   double *g;       // [batch][N]     reduced gradient (gx,gu)
   double *wv;      // [batch][K][nx] gx - Rux' gu
@@ -44,7 +67,7 @@ struct LqDev {
   double *Ru;      // [batch][K][nu]
   double *c;       // [batch][K][nx] f_k - fu Ru
   double *x;       // [batch][K+1][nx]
-  double *segv0, *segvb, *segx0, *segxa;  // [batch][P][nx]
+  double *segv0, *segvb, *segx0, *segxa;  // [batch][st.nel][nx]
 };
 
 // status word bits (device) -> HQPCU_E_SING / HQPCU_E_NOTPD (host)
@@ -52,31 +75,101 @@ struct LqDev {
 #define LQ_FLAG_NOTPD 2
 
 // ---------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier helpers: cp.async.bulk global -> shared,
+// completion signalled on an mbarrier (SASS: UBLKCP / SYNCS).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy accesses to a buffer must be ordered before the async proxy
+// (TMA) overwrites it
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------
 // C(MxN, ldc) = beta*C0 + alpha * A * B with arbitrary element strides:
 //   A(i,l) = A[i*ar + l*ac],  B(l,j) = B[l*br + j*bc].
-// One output element per thread per pass; consecutive threads walk j, so B
-// rows are read conflict-free and A is a broadcast.
+// Each thread owns 2x2 output tiles (register blocking: 4 loads per 4 FMAs);
+// tiles are dealt round-robin over [tid, tid+nthr, ...).  All sizes and strides
+// are plain ints: inside the <NX,NU>-templated kernels they are compile-time
+// constants after inlining, so the l-loop unrolls into immediate-offset LDS +
+// DFMA with no address arithmetic; the <0,0> instantiation keeps runtime loops.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ void cta_mm(double *C, int ldc, const double *C0, int ldc0,
                                        double beta, double alpha, const double *A, int ar,
                                        int ac, const double *B, int br, int bc, int M, int N,
-                                       int Kd) {
-  const int total = M * N;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int i = idx / N, j = idx - i * N;
-    const double *a = A + i * ar;
-    const double *b = B + j * bc;
-    double s0 = 0.0, s1 = 0.0;
-    int l = 0;
-    for (; l + 1 < Kd; l += 2) {
-      s0 = fma(a[l * ac], b[l * br], s0);
-      s1 = fma(a[(l + 1) * ac], b[(l + 1) * br], s1);
+                                       int Kd, int tid, int nthr) {
+  const int TI = (M + 1) >> 1, TJ = (N + 1) >> 1;
+  for (int t = tid; t < TI * TJ; t += nthr) {
+    const int ti = t / TJ, tj = t - ti * TJ;
+    const int i0 = 2 * ti, j0 = 2 * tj;
+    const bool i1 = i0 + 1 < M, j1 = j0 + 1 < N;
+    const double *a0 = A + i0 * ar;
+    const double *a1 = i1 ? a0 + ar : a0;
+    const double *b0 = B + j0 * bc;
+    const double *b1 = j1 ? b0 + bc : b0;
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+    for (int l = 0; l < Kd; l++) {
+      const double x0 = a0[l * ac], x1 = a1[l * ac];
+      const double y0 = b0[l * br], y1 = b1[l * br];
+      c00 = fma(x0, y0, c00);
+      c01 = fma(x0, y1, c01);
+      c10 = fma(x1, y0, c10);
+      c11 = fma(x1, y1, c11);
     }
-    if (l < Kd) s0 = fma(a[l * ac], b[l * br], s0);
-    double r = alpha * (s0 + s1);
-    if (C0) r += beta * C0[i * ldc0 + j];
-    C[i * ldc + j] = r;
+    c00 *= alpha; c01 *= alpha; c10 *= alpha; c11 *= alpha;
+    if (C0) {
+      c00 = fma(beta, C0[i0 * ldc0 + j0], c00);
+      if (j1) c01 = fma(beta, C0[i0 * ldc0 + j0 + 1], c01);
+      if (i1) c10 = fma(beta, C0[(i0 + 1) * ldc0 + j0], c10);
+      if (i1 && j1) c11 = fma(beta, C0[(i0 + 1) * ldc0 + j0 + 1], c11);
+    }
+    C[i0 * ldc + j0] = c00;
+    if (j1) C[i0 * ldc + j0 + 1] = c01;
+    if (i1) C[(i0 + 1) * ldc + j0] = c10;
+    if (i1 && j1) C[(i0 + 1) * ldc + j0 + 1] = c11;
   }
+}
+__device__ __forceinline__ void cta_mm(double *C, int ldc, const double *C0, int ldc0,
+                                       double beta, double alpha, const double *A, int ar,
+                                       int ac, const double *B, int br, int bc, int M, int N,
+                                       int Kd) {
+  cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, threadIdx.x,
+         blockDim.x);
 }
 
 // A <- 0.5 (A + A')  (n x n, lda); one thread per (i<j) pair
@@ -93,10 +186,11 @@ __device__ __forceinline__ void cta_symmetrize(double *A, int lda, int n) {
 }
 
 // ---------------------------------------------------------------------------
-// In-place LDL^T (no pivoting) of the symmetric m x m block A (lda) by warp 0.
-// On exit: strictly lower part = unit L, diagonal = 1/D.  Returns (to all
-// lanes of warp 0) a bit set: LQ_FLAG_SING for a zero / non-finite pivot,
-// LQ_FLAG_NOTPD for a negative one (the factorisation continues).
+// In-place LDL^T (no pivoting) of the symmetric m x m block A (lda) by warp 0;
+// only the lower triangle is read.  On exit: strictly lower part = unit L,
+// diagonal = 1/D.  Returns (to all lanes of warp 0) a bit set: LQ_FLAG_SING for
+// a zero / non-finite pivot, LQ_FLAG_NOTPD for a negative one (the
+// factorisation continues).
 // The reference uses a scaled Bunch-Kaufman here (hqp/Hqp_IpLQDOCP.C:1860-1879);
 // on the convex QPs of an IP iteration Guu is positive definite and LDL^T
 // without interchanges is backward stable.
@@ -129,64 +223,139 @@ __device__ __forceinline__ int warp_ldlt(double *A, int lda, int m) {
 // i < m, by ONE thread.  LD as produced by warp_ldlt.
 __device__ __forceinline__ void thread_ldlt_solve(const double *LD, int lda, int m, double *y,
                                                   int ys) {
+#pragma unroll
   for (int i = 1; i < m; i++) {
     double s = y[i * ys];
+#pragma unroll
     for (int l = 0; l < i; l++) s = fma(-LD[i * lda + l], y[l * ys], s);
     y[i * ys] = s;
   }
+#pragma unroll
   for (int i = 0; i < m; i++) y[i * ys] *= LD[i * lda + i];
+#pragma unroll
   for (int i = m - 2; i >= 0; i--) {
     double s = y[i * ys];
+#pragma unroll
     for (int l = i + 1; l < m; l++) s = fma(-LD[l * lda + i], y[l * ys], s);
     y[i * ys] = s;
   }
 }
 
+// Same solve with the right-hand side held in registers (compile-time M): the
+// substitution chains stay in the register file instead of round-tripping
+// through shared memory on every step.
+template <int M>
+__device__ __forceinline__ void thread_ldlt_solve_reg(const double *LD, int lda, double *y,
+                                                      int ys) {
+  double r[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) r[i] = y[i * ys];
+#pragma unroll
+  for (int i = 1; i < M; i++) {
+#pragma unroll
+    for (int l = 0; l < i; l++) r[i] = fma(-LD[i * lda + l], r[l], r[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++) r[i] *= LD[i * lda + i];
+#pragma unroll
+  for (int i = M - 2; i >= 0; i--) {
+#pragma unroll
+    for (int l = i + 1; l < M; l++) r[i] = fma(-LD[l * lda + i], r[l], r[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++) y[i * ys] = r[i];
+}
+
+template <int M>
+__device__ __forceinline__ void ldlt_solve_any(const double *LD, int lda, int m, double *y,
+                                               int ys) {
+  if constexpr (M > 0 && M <= 16)
+    thread_ldlt_solve_reg<M>(LD, lda, y, ys);
+  else
+    thread_ldlt_solve(LD, lda, m, y, ys);
+}
+
 // ---------------------------------------------------------------------------
-// Gauss-Jordan with partial pivoting on the augmented n x nc matrix M (ldm),
-// nc >= n: on exit columns n..nc-1 hold A^{-1} B.  Whole CTA cooperates.
-// piv_s: shared scratch (>= 2 ints).  Returns status through *st_s (shared).
+// Gauss-Jordan with (implicit) partial pivoting on the augmented n x nc matrix
+// M (ldm), nc > n.  Rows are never swapped: column p is eliminated with the
+// not-yet-used row of largest modulus, the row permutation is kept in piv_s and
+// undone when the solution A^{-1} B is copied to X (n x (nc-n), ldx = nc-n).
+// Whole CTA cooperates; ONE barrier per pivot: every thread owns whole columns
+// j > p (column p itself is only read), and the owner of column p+1 picks the
+// next pivot row and its reciprocal while it updates that column.
+// piv_s: >= n ints, inv_s: 2 doubles (shared).  Status is OR-ed into *st_s.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int nc, int *piv_s,
-                                                 int *st_s) {
+template <int NX>
+__device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int nc, double *X,
+                                                 int *piv_s, double *inv_s, int *st_s) {
+  __syncthreads();
+  if (threadIdx.x < 32) {  // pivot row of column 0
+    double best = -1.0;
+    int bi = 0;
+    for (int i = (threadIdx.x & 31); i < n; i += 32) {
+      const double a = fabs(M[i * ldm]);
+      if (a > best) { best = a; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+      piv_s[0] = bi;
+      inv_s[0] = 1.0 / M[bi * ldm];
+      if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
+    }
+  }
+  __syncthreads();
+  unsigned long long used = 0ull;  // rows already consumed as pivot rows
   for (int p = 0; p < n; p++) {
-    __syncthreads();
-    if (threadIdx.x < 32) {  // pivot search in column p, rows p..n-1
-      double best = -1.0;
-      int bi = p;
-      for (int i = p + (threadIdx.x & 31); i < n; i += 32) {
-        const double a = fabs(M[i * ldm + p]);
-        if (a > best) { best = a; bi = i; }
+    const int r = piv_s[p];
+    const double inv = inv_s[p & 1];
+    used |= 1ull << r;
+    for (int j = p + 1 + threadIdx.x; j < nc; j += blockDim.x) {
+      const double prj = M[r * ldm + j] * inv;
+      const bool next = (j == p + 1) && (p + 1 < n);
+      double best = -1.0, bv = 0.0;
+      int bi = 0;
+      if constexpr (NX > 0) {
+        double f[NX], c[NX];
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          f[i] = M[i * ldm + p];
+          c[i] = M[i * ldm + j];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; i++) {
+          c[i] = fma(-f[i], prj, c[i]);
+          M[i * ldm + j] = c[i];
+        }
+        if (next) {
+#pragma unroll
+          for (int i = 0; i < NX; i++)
+            if (!((used >> i) & 1ull) && fabs(c[i]) > best) { best = fabs(c[i]); bv = c[i]; bi = i; }
+        }
+      } else {
+        for (int i = 0; i < n; i++) {
+          const double v = fma(-M[i * ldm + p], prj, M[i * ldm + j]);
+          M[i * ldm + j] = v;
+          if (next && !((used >> i) & 1ull) && fabs(v) > best) { best = fabs(v); bv = v; bi = i; }
+        }
       }
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (threadIdx.x == 0) {
-        piv_s[0] = bi;
+      M[r * ldm + j] = prj;  // pivot row: scaled, not eliminated
+      if (next) {
+        piv_s[p + 1] = bi;
+        inv_s[(p + 1) & 1] = 1.0 / bv;
         if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
       }
     }
     __syncthreads();
-    const int r = piv_s[0];
-    if (r != p)
-      for (int j = threadIdx.x; j < nc; j += blockDim.x) {
-        const double t = M[p * ldm + j];
-        M[p * ldm + j] = M[r * ldm + j];
-        M[r * ldm + j] = t;
-      }
-    __syncthreads();
-    const double inv = 1.0 / M[p * ldm + p];
-    __syncthreads();
-    for (int j = threadIdx.x; j < nc; j += blockDim.x) M[p * ldm + j] *= inv;
-    __syncthreads();
-    // eliminate column p from every other row; only columns > p matter
-    const int ncols = nc - p - 1;
-    for (int e = threadIdx.x; e < n * ncols; e += blockDim.x) {
-      const int i = e / ncols, j = p + 1 + (e - i * ncols);
-      if (i != p) M[i * ldm + j] = fma(-M[i * ldm + p], M[p * ldm + j], M[i * ldm + j]);
-    }
+  }
+  // X[p][:] = row piv_s[p] of the right-hand part
+  const int nr = nc - n;
+  for (int e = threadIdx.x; e < n * nr; e += blockDim.x) {
+    const int p = e / nr, j = e - p * nr;
+    X[e] = M[piv_s[p] * ldm + n + j];
   }
   __syncthreads();
 }
@@ -197,3 +366,19 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double val) {
   atomicMax(reinterpret_cast<unsigned long long *>(addr),
             static_cast<unsigned long long>(__double_as_longlong(fabs(val))));
 }
+
+// shared-memory carve-up helper (16-byte granularity)
+struct SmemCarver {
+  unsigned char *p;
+  __device__ explicit SmemCarver(void *base) : p(reinterpret_cast<unsigned char *>(base)) {}
+  __device__ double *take(int n) {
+    double *r = reinterpret_cast<double *>(p);
+    p += (size_t)((n + 1) & ~1) * sizeof(double);
+    return r;
+  }
+  __device__ uint64_t *take_bars(int n) {
+    uint64_t *r = reinterpret_cast<uint64_t *>(p);
+    p += (size_t)((n + 1) & ~1) * sizeof(uint64_t);
+    return r;
+  }
+};

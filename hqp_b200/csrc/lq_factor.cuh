@@ -2,140 +2,243 @@
 //
 // The reference sweeps the horizon sequentially (ExRiccatiFactorSc,
 // hqp/Hqp_IpLQDOCP.C:1811-1969: for k = K-1..0, each stage needs Vxx[k+1]).
-// Here the horizon of every instance is cut into P segments of L stages:
+// Here the horizon of every instance is cut into P segments of L stages, and
+// the segments are grouped R at a time into a small hierarchy (level 0 =
+// segments, level l+1 = groups of R level-l elements):
 //
-//   K1 seg_element_kernel   (P x batch CTAs)  each segment is condensed, with a
+//   hdiag_kernel        (stage-parallel) diagonal of C'(z/w)C from bound rows
+//   K1 seg_element_kernel (P x batch CTAs)  each segment is condensed, with a
 //        ZERO terminal cost, into its boundary element (A, C, J):
 //            J = Riccati value Hessian at the segment start,
 //            A = closed-loop transition across the segment,
 //            C = closed-loop controllability Gramian weighted by Guu^{-1},
 //        i.e. the segment's Schur complement onto (x_start, costate_end).
-//   K2 seg_scan_kernel      (batch CTAs)  back-substitutes across segments:
-//            Vb_s = V at the end of segment s,
-//            V at its start = J + A' (I + Vb C)^{-1} Vb A      (exact identity)
-//   K3 seg_riccati_kernel   (P x batch CTAs)  the ordinary Riccati recursion
+//   K2a elem_compose_kernel (per level, groups in parallel) composes R
+//        consecutive elements into one:  with M = (I + C_i J_j)^{-1},
+//            A = A_j M A_i,  C = A_j M C_i A_j' + C_j,  J = A_i' J_j M A_i + J_i
+//   K2b elem_scan_kernel   top level (one CTA per instance) and, going back
+//        down, every group in parallel: from the value Hessian S at an
+//        element's end,  V at its start = J + A' (I + S C)^{-1} S A  (exact).
+//   K3 seg_riccati_kernel (P x batch CTAs)  the ordinary Riccati recursion
 //        inside every segment from its now-known terminal Vb, storing
 //        Vxx[k], Rux[k], LDL'(Guu[k]), Phi[k] = fx - fu Rux and the segment
 //        transition Psi_s = Phi[b-1] ... Phi[a].
+//   K4 psi_compose_kernel (per level) Psi of a group = product of its children.
 //
-// With P = 1 only K2 (terminal block) and K3 run: the reference's sequential
+// Stage inputs (Q_k, fx_k, fu_k, hdiag_k) are staged into shared memory with
+// TMA bulk copies one stage ahead of the arithmetic (double buffer + mbarrier).
+// With P = 1 only the terminal block and K3 run: the reference's sequential
 // sweep, one CTA per instance (the batched-MPC configuration).
 #pragma once
 
 #include "lq_device.cuh"
 
-// shared-memory carve-up helper
-struct SmemCarver {
-  double *p;
-  __device__ explicit SmemCarver(void *base) : p(reinterpret_cast<double *>(base)) {}
-  __device__ double *take(int n) {
-    double *r = p;
-    p += (n + 1) & ~1;  // keep 16-byte alignment
-    return r;
+// ---------------------------------------------------------------------------
+// hdiag[b][j] = sum over single-entry rows r of C in column j of (z_r/w_r) c_r^2
+// (the bound rows of Hqp_Docp, hqp/Hqp_Docp.C:658-666).  grid-stride over
+// batch*N variables.
+// ---------------------------------------------------------------------------
+__global__ void hdiag_kernel(LqDev d) {
+  const size_t total = (size_t)d.batch * d.N;
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(t / d.N), j = (int)(t - (size_t)b * d.N);
+    const double *z = d.z + (size_t)b * d.m, *w = d.w + (size_t)b * d.m;
+    const double *cv = d.cval + (size_t)b * d.nnz;
+    double s = 0.0;
+    for (int e = d.vcol_ptr[j]; e < d.vcol_ptr[j + 1]; e++) {
+      const int r = d.vcol_row[e];
+      if (d.ineq_ptr[r + 1] - d.ineq_ptr[r] == 1) {
+        const double a = cv[d.vcol_nz[e]];
+        s = fma(z[r] / w[r], a * a, s);
+      }
+    }
+    d.hdiag[t] = s;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Double-buffered stage loader.
+// ---------------------------------------------------------------------------
+struct StagePipe {
+  double *base;   // two consecutive slots of [G | fx | fu | hd]
+  uint64_t *bar;  // [2]
+  int slot, o_fx, o_fu, o_hd;
+  __device__ __forceinline__ double *G(int buf) const { return base + buf * slot; }
+  __device__ __forceinline__ double *fx(int buf) const { return base + buf * slot + o_fx; }
+  __device__ __forceinline__ double *fu(int buf) const { return base + buf * slot + o_fu; }
+  __device__ __forceinline__ double *hd(int buf) const { return base + buf * slot + o_hd; }
 };
 
-// G(nm x nm) <- Q_k + C_k' diag(z/w) C_k for stage k of instance b
-// (factor prologue hqp/Hqp_IpLQDOCP.C:805-832 + CTDC :68-103), and
-// F(nx x nm) <- [fx_k fu_k] when k < K.  Ends with __syncthreads().
-__device__ __forceinline__ void load_stage(const LqDev &d, int b, int k, double *G, double *F) {
-  const int nx = d.nx, nu = d.nu, nm = d.nm;
+// issued by ONE thread: start the bulk copies of stage k into buffer `buf`
+__device__ __forceinline__ void stage_issue(const LqDev &d, int nx, int nu,
+                                            const StagePipe &sp, int b, int k, int buf) {
+  const int nm = nx + nu;
+  const uint32_t bq = nm * nm * 8, bx = nx * nx * 8, bu = nx * nu * 8, bh = nm * 8;
   const double *Qk = d.Q + ((size_t)b * (d.K + 1) + k) * nm * nm;
-  for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) G[i] = Qk[i];
-  if (k < d.K && F) {
-    const double *fx = d.fx + ((size_t)b * d.K + k) * nx * nx;
-    const double *fu = d.fu + ((size_t)b * d.K + k) * nx * nu;
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
-      const int r = i / nx, c = i - r * nx;
-      F[r * nm + c] = fx[i];
-    }
-    for (int i = threadIdx.x; i < nx * nu; i += blockDim.x) {
-      const int r = i / nu, c = i - r * nu;
-      F[r * nm + nx + c] = fu[i];
-    }
+  const double *hk = d.hdiag + (size_t)b * d.N + (size_t)k * nm;
+  if (k < d.K) {
+    mbar_expect_tx(&sp.bar[buf], bq + bx + bu + bh);
+    tma_load_1d(sp.G(buf), Qk, bq, &sp.bar[buf]);
+    tma_load_1d(sp.fx(buf), d.fx + ((size_t)b * d.K + k) * nx * nx, bx, &sp.bar[buf]);
+    tma_load_1d(sp.fu(buf), d.fu + ((size_t)b * d.K + k) * nx * nu, bu, &sp.bar[buf]);
+    tma_load_1d(sp.hd(buf), hk, bh, &sp.bar[buf]);
+  } else {
+    // terminal stage: only nx diagonal entries exist (nx*8 is a 16-byte multiple
+    // whenever use_tma holds)
+    mbar_expect_tx(&sp.bar[buf], bq + nx * 8);
+    tma_load_1d(sp.G(buf), Qk, bq, &sp.bar[buf]);
+    tma_load_1d(sp.hd(buf), hk, nx * 8, &sp.bar[buf]);
   }
-  __syncthreads();
-  const int r0 = d.srow_ptr[k], r1 = d.srow_ptr[k + 1];
+}
+
+// all threads: make stage k available in buffer `buf` as
+//   G = Q_k + C_k' diag(z/w) C_k   (factor prologue hqp/Hqp_IpLQDOCP.C:805-832,
+//   CTDC :68-103),  fx, fu.  `parity` = phase of the buffer's mbarrier.
+// Ends with __syncthreads().
+__device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
+                                              const StagePipe &sp, int b, int k, int buf,
+                                              uint32_t parity) {
+  const int nm = nx + nu;
+  const int dk = k < d.K ? nm : nx;
+  double *G = sp.G(buf);
+  if (d.use_tma) {
+    mbar_wait(&sp.bar[buf], parity);
+  } else {
+    const double *Qk = d.Q + ((size_t)b * (d.K + 1) + k) * nm * nm;
+    for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) G[i] = Qk[i];
+    if (k < d.K) {
+      const double *fx = d.fx + ((size_t)b * d.K + k) * nx * nx;
+      const double *fu = d.fu + ((size_t)b * d.K + k) * nx * nu;
+      for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) sp.fx(buf)[i] = fx[i];
+      for (int i = threadIdx.x; i < nx * nu; i += blockDim.x) sp.fu(buf)[i] = fu[i];
+    }
+    const double *hk = d.hdiag + (size_t)b * d.N + (size_t)k * nm;
+    for (int i = threadIdx.x; i < dk; i += blockDim.x) sp.hd(buf)[i] = hk[i];
+    __syncthreads();
+  }
+  for (int i = threadIdx.x; i < dk; i += blockDim.x) G[i * nm + i] += sp.hd(buf)[i];
+  // general rows (more than one nonzero): dense rank-1 updates, one row at a
+  // time so that the summation order is fixed
+  const int r0 = d.grow_ptr[k], r1 = d.grow_ptr[k + 1];
   if (r1 > r0) {
     const double *cv = d.cval + (size_t)b * d.nnz;
     const double *z = d.z + (size_t)b * d.m, *w = d.w + (size_t)b * d.m;
     for (int rr = r0; rr < r1; rr++) {
-      const int r = d.srow[rr];
+      __syncthreads();
+      const int r = d.grow[rr];
       const int e0 = d.ineq_ptr[r], ne = d.ineq_ptr[r + 1] - e0;
       const double wz = z[r] / w[r];
-      if (ne == 1) {  // simple bound: diagonal update
-        if (threadIdx.x == 0) {
-          const int c = d.ineq_lcol[e0];
-          const double a = cv[e0];
-          G[c * nm + c] += wz * a * a;
-        }
-      } else {
-        for (int e = threadIdx.x; e < ne * ne; e += blockDim.x) {
-          const int ea = e / ne, eb = e - ea * ne;
-          G[d.ineq_lcol[e0 + ea] * nm + d.ineq_lcol[e0 + eb]] +=
-              wz * cv[e0 + ea] * cv[e0 + eb];
-        }
+      for (int e = threadIdx.x; e < ne * ne; e += blockDim.x) {
+        const int ea = e / ne, eb = e - ea * ne;
+        G[d.ineq_lcol[e0 + ea] * nm + d.ineq_lcol[e0 + eb]] += wz * cv[e0 + ea] * cv[e0 + eb];
       }
-      // rows of one stage may hit the same entries: serialise them
-      __syncthreads();
     }
   }
+  __syncthreads();
 }
 
+// set up pipe storage and barriers; returns after a CTA barrier
+__device__ __forceinline__ void stage_pipe_init(int nx, int nu, SmemCarver &sm, StagePipe &sp) {
+  const int nm = nx + nu;
+  sp.o_fx = (nm * nm + 1) & ~1;
+  sp.o_fu = sp.o_fx + ((nx * nx + 1) & ~1);
+  sp.o_hd = sp.o_fu + ((nx * nu + 1) & ~1);
+  sp.slot = sp.o_hd + ((nm + 1) & ~1);
+  sp.base = sm.take(2 * sp.slot);
+  sp.bar = sm.take_bars(2);
+  if (threadIdx.x == 0) {
+    mbar_init(&sp.bar[0], 1);
+    mbar_init(&sp.bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
 // One Riccati stage on shared-memory blocks (FormGxx hqp/Hqp_IpLQDOCP.C:1077-1111
 // + unconstrained-u branch :1854-1882 + Vxx :1940-1961).
-//   in : V (nx x nx) = Vxx[k+1] (ignored when zero_V), F = [fx fu], G = H_k
-//   out: G = [Gxx Gxu; Gux LDL'(Guu)], Rux (nu x nx), V <- Vxx[k] (symmetric),
-//        Phi (nx x nx) = fx - fu Rux
-// T is scratch (nx x nm).  st_s: shared status word.
+//   in : V (nx x nx) = Vxx[k+1] (ignored when zero_V), fx, fu, G = H_k
+//   out: G = [Gxx . ; Gux LDL'(Guu)] (lower blocks), Rux (nu x nx),
+//        V <- Gxx - Gux' Rux (NOT yet symmetrised), Phi = fx - fu Rux
+// T is scratch (nx x nm).  When `el` (K1): also W = A fu, Y = W Guu^{-1},
+// Cg += Y W' are folded into the same barrier phases.
+// Ends with __syncthreads().
+// ---------------------------------------------------------------------------
+struct ElemAcc {
+  double *A, *W, *Y, *Cg;
+};
+
+template <int NU>
 __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, double *V,
-                                              const double *F, double *G, double *T,
-                                              double *Rux, double *Phi, int *st_s) {
+                                              const double *fx, const double *fu, double *G,
+                                              double *T, double *Rux, double *Phi, int *st_s,
+                                              const ElemAcc *el) {
   const int nm = nx + nu;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   if (!zero_V) {
-    // T = V F ; G += F' T
-    cta_mm(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, F, nm, 1, nx, nm, nx);
-    __syncthreads();
-    cta_mm(G, nm, G, nm, 1.0, 1.0, F, 1, nm, T, nm, 1, nm, nm, nx);
-    __syncthreads();
-    cta_symmetrize(G, nm, nm);
+    // T = V [fx fu]
+    cta_mm(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fx, nx, 1, nx, nx, nx);
+    cta_mm(T + nx, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fu, nu, 1, nx, nu, nx);
+  }
+  if (el)  // W = A fu
+    cta_mm(el->W, nu, nullptr, 0, 0.0, 1.0, el->A, nx, 1, fu, nu, 1, nx, nu, nx);
+  if (!zero_V || el) __syncthreads();
+  if (!zero_V) {
+    // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
+    cta_mm(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, nm, 1, nx, nx, nx);
+    cta_mm(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, nu, T, nm, 1, nu, nx, nx);
+    cta_mm(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, nu, T + nx, nm, 1, nu,
+           nu, nx);
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
-  if (threadIdx.x < 32) {
+  if (tid < 32) {
     const int st = warp_ldlt(Guu, nm, nu);
-    if (st && threadIdx.x == 0) atomicOr(st_s, st);
+    if (st && tid == 0) atomicOr(st_s, st);
   }
   __syncthreads();
-  // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread
-  for (int j = threadIdx.x; j < nx; j += blockDim.x) {
-    for (int i = 0; i < nu; i++) Rux[i * nx + j] = G[(nx + i) * nm + j];
-    thread_ldlt_solve(Guu, nm, nu, Rux + j, nx);
+  // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
+  // K1: rows of Y = W Guu^{-1} on the next nx threads
+  for (int j = tid; j < (el ? 2 * nx : nx); j += nthr) {
+    if (j < nx) {
+      for (int i = 0; i < nu; i++) Rux[i * nx + j] = G[(nx + i) * nm + j];
+      ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, nx);
+    } else {
+      const int i = j - nx;
+      for (int l = 0; l < nu; l++) el->Y[i * nu + l] = el->W[i * nu + l];
+      ldlt_solve_any<NU>(Guu, nm, nu, el->Y + i * nu, 1);
+    }
   }
   __syncthreads();
-  // V = Gxx - Gxu Rux ; Phi = fx - fu Rux
-  cta_mm(V, nx, G, nm, 1.0, -1.0, G + nx, nm, 1, Rux, nx, 1, nx, nx, nu);
-  cta_mm(Phi, nx, F, nm, 1.0, -1.0, F + nx, nm, 1, Rux, nx, 1, nx, nx, nu);
-  __syncthreads();
-  cta_symmetrize(V, nx, nx);
+  // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W'
+  cta_mm(V, nx, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, nx, 1, nx, nx, nu);
+  cta_mm(Phi, nx, fx, nx, 1.0, -1.0, fu, nu, 1, Rux, nx, 1, nx, nx, nu);
+  if (el) cta_mm(el->Cg, nx, el->Cg, nx, 1.0, 1.0, el->Y, nu, 1, el->W, 1, nu, nx, nx, nu);
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
 // K1: condense segment s of instance b with zero terminal cost.
 // ---------------------------------------------------------------------------
-__global__ void seg_element_kernel(LqDev d) {
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx, nu = d.nu, nm = d.nm;
+  const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   SmemCarver sm(smem_raw);
+  StagePipe sp;
+  stage_pipe_init(nx, nu, sm, sp);
   double *J = sm.take(nx * nx), *A0 = sm.take(nx * nx), *A1 = sm.take(nx * nx);
-  double *Cg = sm.take(nx * nx), *F = sm.take(nx * nm), *T = sm.take(nx * nm);
-  double *G = sm.take(nm * nm), *Rux = sm.take(nu * nx), *Phi = sm.take(nx * nx);
+  double *Cg = sm.take(nx * nx), *T = sm.take(nx * nm);
+  double *Rux = sm.take(nu * nx), *Phi = sm.take(nx * nx);
   double *W = sm.take(nx * nu), *Y = sm.take(nx * nu);
   __shared__ int st_s;
-  if (threadIdx.x == 0) st_s = 0;
+  if (threadIdx.x == 0) {
+    st_s = 0;
+    if (d.use_tma) stage_issue(d, nx, nu, sp, b, kb - 1, 0);
+  }
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
     const int r = i / nx, c = i - r * nx;
     J[i] = 0.0;
@@ -144,26 +247,26 @@ __global__ void seg_element_kernel(LqDev d) {
   }
   __syncthreads();
   double *A = A0, *An = A1;
-  for (int k = kb - 1; k >= ka; k--) {
-    load_stage(d, b, k, G, F);
-    riccati_stage(nx, nu, k == kb - 1, J, F, G, T, Rux, Phi, &st_s);
-    // W = A fu ; Y = W Guu^{-1} ; C += Y W' ; A <- A Phi
-    cta_mm(W, nu, nullptr, 0, 0.0, 1.0, A, nx, 1, F + nx, nm, 1, nx, nu, nx);
-    cta_mm(An, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, Phi, nx, 1, nx, nx, nx);
-    __syncthreads();
-    const double *LD = G + nx * nm + nx;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      for (int j = 0; j < nu; j++) Y[i * nu + j] = W[i * nu + j];
-      thread_ldlt_solve(LD, nm, nu, Y + i * nu, 1);
+  int it = 0;
+  for (int k = kb - 1; k >= ka; k--, it++) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && d.use_tma && k > ka) {
+      fence_proxy_async();
+      stage_issue(d, nx, nu, sp, b, k - 1, buf ^ 1);
     }
-    __syncthreads();
-    cta_mm(Cg, nx, Cg, nx, 1.0, 1.0, Y, nu, 1, W, 1, nu, nx, nx, nu);
+    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
+    ElemAcc el{A, W, Y, Cg};
+    riccati_stage<NU>(nx, nu, k == kb - 1, J, sp.fx(buf), sp.fu(buf), sp.G(buf), T, Rux, Phi,
+                  &st_s, &el);
+    // J symmetrised ; A <- A Phi
+    cta_symmetrize(J, nx, nx);
+    cta_mm(An, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, Phi, nx, 1, nx, nx, nx);
     double *t = A; A = An; An = t;
     __syncthreads();
   }
   cta_symmetrize(Cg, nx, nx);
   __syncthreads();
-  const size_t o = ((size_t)b * d.P + s) * nx * nx;
+  const size_t o = ((size_t)b * d.ft.nel + s) * nx * nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
     d.segA[o + i] = A[i];
     d.segC[o + i] = Cg[i];
@@ -174,32 +277,151 @@ __global__ void seg_element_kernel(LqDev d) {
 }
 
 // ---------------------------------------------------------------------------
-// K2: terminal block + back-substitution across the P segment elements.
+// K2a: compose the children [g*R, min((g+1)*R, cnt)) of level `lev` into
+// element g of level lev+1.  grid (cnt_{lev+1}, batch).
 // ---------------------------------------------------------------------------
-__global__ void seg_scan_kernel(LqDev d) {
+#ifdef LQ_TIMING
+#define LQ_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) d.dbg[i] = clock64(); } while (0)
+#else
+#define LQ_STAMP(i) do { } while (0)
+#endif
+
+template <int NX>
+__global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx, nm = d.nm;
-  const int b = blockIdx.x;
+  LQ_STAMP(0);
+  const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
   SmemCarver sm(smem_raw);
-  double *S = sm.take(nx * nx), *A = sm.take(nx * nx), *Cg = sm.take(nx * nx);
-  double *M = sm.take(nx * 2 * nx);
-  double *G = sm.take(nm * nm);
-  __shared__ int st_s, piv_s[2];
+  double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
+  double *Ai = sm.take(n2), *Ji = sm.take(n2);
+  double *M = sm.take(nx * n3), *T1 = sm.take(n2), *T2 = sm.take(n2);
+  double *X = sm.take(2 * n2);  // [X_A | X_C], ld = 2 nx
+  __shared__ int st_s, piv_s[64];
+  __shared__ double inv_s[2];
   if (threadIdx.x == 0) st_s = 0;
-  // terminal stage: Vxx[K] = H_K (hqp/Hqp_IpLQDOCP.C:1800-1804)
-  load_stage(d, b, d.K, G, nullptr);
-  double *VK = d.V + ((size_t)b * (d.K + 1) + d.K) * nx * nx;
-  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
-    const int r = i / nx, c = i - r * nx;
-    S[i] = G[r * nm + c];
-    VK[i] = S[i];
+  const size_t base = ((size_t)b * d.ft.nel + d.ft.off[lev]) * n2;
+  {
+    const size_t o = base + (size_t)(c1 - 1) * n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      Aj[i] = d.segA[o + i];
+      Cj[i] = d.segC[o + i];
+      Jj[i] = d.segJ[o + i];
+    }
   }
   __syncthreads();
-  for (int s = d.P - 1; s >= 0; s--) {
-    const size_t o = ((size_t)b * d.P + s) * nx * nx;
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) d.segVb[o + i] = S[i];
-    if (d.P == 1) break;
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
+  LQ_STAMP(1);
+  for (int c = c1 - 2; c >= c0; c--) {
+    const size_t o = base + (size_t)c * n2;
+    // M = [I + C_i J_j | A_i | C_i]
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const int r = i / nx, cc = i - r * nx;
+      const double ai = d.segA[o + i], ci = d.segC[o + i];
+      Ai[i] = ai;
+      Ji[i] = d.segJ[o + i];
+      M[r * n3 + nx + cc] = ai;
+      M[r * n3 + 2 * nx + cc] = ci;
+      T1[i] = ci;
+    }
+    __syncthreads();
+    LQ_STAMP(2);
+    cta_mm(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    __syncthreads();
+    LQ_STAMP(3);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * n3 + i] += 1.0;
+    cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
+    LQ_STAMP(4);
+    // T1 = A_j X_C ; T2 = J_j X_A
+    cta_mm(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
+    cta_mm(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    __syncthreads();
+    // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
+    cta_mm(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+    cta_mm(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
+    __syncthreads();
+    // A = A_j X_A (into T1, then copy)
+    cta_mm(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    cta_symmetrize(Cj, nx, nx);
+    cta_symmetrize(Jj, nx, nx);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) Aj[i] = T1[i];
+    __syncthreads();
+    LQ_STAMP(5);
+  }
+  const size_t o = ((size_t)b * d.ft.nel + d.ft.off[lev + 1] + g) * n2;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    d.segA[o + i] = Aj[i];
+    d.segC[o + i] = Cj[i];
+    d.segJ[o + i] = Jj[i];
+  }
+  if (threadIdx.x == 0 && st_s) atomicOr(d.status, st_s);
+  LQ_STAMP(6);
+}
+
+// ---------------------------------------------------------------------------
+// K2b: back-substitution of the value Hessian through the elements.
+//   top = 1: level `lev` is the top level; one CTA per instance starts from the
+//            terminal stage Vxx[K] = H_K (hqp/Hqp_IpLQDOCP.C:1800-1804) and walks
+//            all elements of the level.          grid (1, batch)
+//   top = 0: CTA g walks the children of element g of level lev+1 starting from
+//            that element's segVb.               grid (cnt_{lev+1}, batch)
+// For every element visited: segVb[e] = S (Vxx at its end), then
+//   S <- J + A' (I + S C)^{-1} S A.
+// ---------------------------------------------------------------------------
+template <int NX>
+__global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int top) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
+  const int g = blockIdx.x, b = blockIdx.y;
+  SmemCarver sm(smem_raw);
+  double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
+  double *M = sm.take(nx * 2 * nx);
+  double *X = sm.take(n2);
+  __shared__ int st_s, piv_s[64];
+  __shared__ double inv_s[2];
+  if (threadIdx.x == 0) st_s = 0;
+  int c0, c1;
+  if (top) {
+    c0 = 0;
+    c1 = d.ft.cnt[lev];
+    // terminal stage: Q_K + hdiag_K + general rows of stage K
+    const double *QK = d.Q + ((size_t)b * (d.K + 1) + d.K) * nm * nm;
+    const double *hk = d.hdiag + (size_t)b * d.N + (size_t)d.K * nm;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const int r = i / nx, c = i - r * nx;
+      S[i] = QK[r * nm + c] + (r == c ? hk[r] : 0.0);
+    }
+    const double *cv = d.cval + (size_t)b * d.nnz;
+    for (int rr = d.grow_ptr[d.K]; rr < d.grow_ptr[d.K + 1]; rr++) {
+      __syncthreads();
+      const int r = d.grow[rr];
+      const int e0 = d.ineq_ptr[r], ne = d.ineq_ptr[r + 1] - e0;
+      const double wz = d.z[(size_t)b * d.m + r] / d.w[(size_t)b * d.m + r];
+      for (int e = threadIdx.x; e < ne * ne; e += blockDim.x) {
+        const int ea = e / ne, eb = e - ea * ne;
+        S[d.ineq_lcol[e0 + ea] * nx + d.ineq_lcol[e0 + eb]] += wz * cv[e0 + ea] * cv[e0 + eb];
+      }
+    }
+    __syncthreads();
+    double *VK = d.V + ((size_t)b * (d.K + 1) + d.K) * n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) VK[i] = S[i];
+  } else {
+    c0 = g * d.ft.R;
+    c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
+    const size_t o = ((size_t)b * d.ft.nel + d.ft.off[lev + 1] + g) * n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) S[i] = d.segVb[o + i];
+  }
+  __syncthreads();
+  const size_t base = ((size_t)b * d.ft.nel + d.ft.off[lev]) * n2;
+  for (int c = c1 - 1; c >= c0; c--) {
+    const size_t o = base + (size_t)c * n2;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segVb[o + i] = S[i];
+    // the value at the start of the first child is the end value of the
+    // previous group (known to the parent level) or, at the very top, Vxx[0],
+    // which K3 produces itself: skip the last update
+    if (c == c0) break;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
       A[i] = d.segA[o + i];
       Cg[i] = d.segC[o + i];
     }
@@ -209,16 +431,12 @@ __global__ void seg_scan_kernel(LqDev d) {
     cta_mm(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
-    cta_gauss_jordan(M, 2 * nx, nx, 2 * nx, piv_s, &st_s);
+    cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised
-    cta_mm(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, M + nx, 2 * nx, 1, nx, nx, nx);
+    cta_mm(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);
     __syncthreads();
-    if (s > 0) {  // V at the boundary a_s: the value segment s-1 builds on
-      double *Va = d.V + ((size_t)b * (d.K + 1) + (size_t)s * d.L) * nx * nx;
-      for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) Va[i] = S[i];
-    }
   }
   if (threadIdx.x == 0 && st_s) atomicOr(d.status, st_s);
 }
@@ -226,49 +444,93 @@ __global__ void seg_scan_kernel(LqDev d) {
 // ---------------------------------------------------------------------------
 // K3: Riccati recursion inside segment s from its terminal Vb.
 // ---------------------------------------------------------------------------
-__global__ void seg_riccati_kernel(LqDev d) {
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx, nu = d.nu, nm = d.nm;
+  const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu, n2 = nx * nx;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   SmemCarver sm(smem_raw);
-  double *V = sm.take(nx * nx), *F = sm.take(nx * nm), *T = sm.take(nx * nm);
-  double *G = sm.take(nm * nm), *Rux = sm.take(nu * nx), *Phi = sm.take(nx * nx);
-  double *P0 = sm.take(nx * nx), *P1 = sm.take(nx * nx);
+  StagePipe sp;
+  stage_pipe_init(nx, nu, sm, sp);
+  double *V = sm.take(n2), *T = sm.take(nx * nm);
+  double *Rux = sm.take(nu * nx), *Phi = sm.take(n2);
+  double *P0 = sm.take(n2), *P1 = sm.take(n2);
   __shared__ int st_s;
-  if (threadIdx.x == 0) st_s = 0;
-  const size_t so = ((size_t)b * d.P + s) * nx * nx;
-  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
+  if (threadIdx.x == 0) {
+    st_s = 0;
+    if (d.use_tma) stage_issue(d, nx, nu, sp, b, kb - 1, 0);
+  }
+  const size_t so = ((size_t)b * d.ft.nel + s) * n2;   // factor tree (segVb)
+  const size_t po = ((size_t)b * d.st.nel + s) * n2;   // solve tree (segPsi)
+  double *Vend = d.V + ((size_t)b * (d.K + 1) + kb) * n2;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     const int r = i / nx, c = i - r * nx;
-    V[i] = d.segVb[so + i];
+    const double v = d.segVb[so + i];
+    V[i] = v;
+    Vend[i] = v;  // Vxx at the segment end (for the last segment: Vxx[K])
     P0[i] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
   double *Psi = P0, *Psin = P1;
-  for (int k = kb - 1; k >= ka; k--) {
-    load_stage(d, b, k, G, F);
-    riccati_stage(nx, nu, false, V, F, G, T, Rux, Phi, &st_s);
-    const size_t ks = (size_t)b * d.K + k;
-    // boundary values Vxx[a_s], s > 0, were fixed by K2
-    if (k > ka || s == 0) {
-      double *Vk = d.V + ((size_t)b * (d.K + 1) + k) * nx * nx;
-      for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) Vk[i] = V[i];
+  int it = 0;
+  for (int k = kb - 1; k >= ka; k--, it++) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && d.use_tma && k > ka) {
+      fence_proxy_async();
+      stage_issue(d, nx, nu, sp, b, k - 1, buf ^ 1);
     }
-    double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * nx * nx;
+    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
+    double *G = sp.G(buf);
+    riccati_stage<NU>(nx, nu, false, V, sp.fx(buf), sp.fu(buf), G, T, Rux, Phi, &st_s, nullptr);
+    const size_t ks = (size_t)b * d.K + k;
+    double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * n2;
+    cta_symmetrize(V, nx, nx);
     for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) Rk[i] = Rux[i];
     for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) {
       const int r = i / nu, c = i - r * nu;
       Lk[i] = G[(nx + r) * nm + nx + c];
     }
-    for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) Pk[i] = Phi[i];
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) Pk[i] = Phi[i];
     // Psi <- Psi Phi
     cta_mm(Psin, nx, nullptr, 0, 0.0, 1.0, Psi, nx, 1, Phi, nx, 1, nx, nx, nx);
     double *t = Psi; Psi = Psin; Psin = t;
     __syncthreads();
+    // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
+    // s-1 and is written there
+    if (k > ka || s == 0) {
+      double *Vk = d.V + ((size_t)b * (d.K + 1) + k) * n2;
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) Vk[i] = V[i];
+    }
   }
-  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) d.segPsi[so + i] = Psi[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segPsi[po + i] = Psi[i];
   // an indefinite (but non-singular) Guu is accepted like the reference's BKP
   if (threadIdx.x == 0 && (st_s & LQ_FLAG_SING)) atomicOr(d.status, LQ_FLAG_SING);
+}
+
+// K4: Psi of element g of level lev+1 = Psi[c1-1] ... Psi[c0] of its children.
+// grid (cnt_{lev+1}, batch)
+template <int NX>
+__global__ void __launch_bounds__(128) psi_compose_kernel(LqDev d, int lev) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
+  const int g = blockIdx.x, b = blockIdx.y;
+  const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
+  SmemCarver sm(smem_raw);
+  double *P0 = sm.take(n2), *P1 = sm.take(n2), *Pc = sm.take(n2);
+  const size_t base = ((size_t)b * d.st.nel + d.st.off[lev]) * n2;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) P0[i] = d.segPsi[base + (size_t)(c1 - 1) * n2 + i];
+  __syncthreads();
+  double *P = P0, *Pn = P1;
+  for (int c = c1 - 2; c >= c0; c--) {
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) Pc[i] = d.segPsi[base + (size_t)c * n2 + i];
+    __syncthreads();
+    cta_mm(Pn, nx, nullptr, 0, 0.0, 1.0, P, nx, 1, Pc, nx, 1, nx, nx, nx);
+    double *t = P; P = Pn; Pn = t;
+    __syncthreads();
+  }
+  const size_t o = ((size_t)b * d.st.nel + d.st.off[lev + 1] + g) * n2;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segPsi[o + i] = P[i];
 }
 
 // LDL^T of Vxx[0] for a free initial state (hqp/Hqp_IpLQDOCP.C:1971-1996 with

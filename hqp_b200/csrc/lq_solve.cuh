@@ -4,39 +4,121 @@
 // The reference's two dependent sweeps carry, per stage, a BKP solve and four
 // mat-vecs on the critical path.  Here everything that does not depend on the
 // sweep is hoisted into stage-parallel passes, so that the sequential chains
-// carry ONE nx x nx mat-vec per stage, and the chains themselves are cut into
-// the same P segments as the factor (segment transition Psi_s from K3):
+// carry ONE nx x nx mat-vec per stage; the chains are cut into the factor's P
+// segments, and the P segment boundaries are resolved through the same R-ary
+// hierarchy (segment / group transitions Psi from K3 / K4):
 //
-//   pre   (stage-parallel)  g = -r1 + C'((z r3 + r4)/w);  wv = gx - Rux' gu;
-//                           q = Vxx[k+1] f_k;  v[K] = gx_K
-//   back1 (segment chains)  v = wv + Phi'(v+ + q) from v_b = 0    -> segv0
-//   back2 (P-step chain)    segvb[s] = segv0[s+1] + Psi[s+1]' segvb[s+1]
-//   back3 (segment chains)  same chain from the true v_b, stores v[k]
-//   mid   (stage-parallel)  Ru = Guu^{-1}(gu + fu'(v+ + q));  c = f - fu Ru
-//   fwd1  (segment chains)  x+ = Phi x + c from x_a = 0            -> segx0
-//   fwd2  (P-step chain)    segxa[s+1] = Psi[s] segxa[s] + segx0[s]
-//   fwd3  (segment chains)  same chain from the true x_a, stores x[k]
-//   post  (stage-parallel)  u = -(Rux x + Ru); p = Vxx+ x+ + v+; dx,dy,dw,dz
+//   pre    (stage-parallel)  g = -r1 + C'((z r3 + r4)/w);  wv = gx - Rux' gu;
+//                            q = Vxx[k+1] f_k;  v[K] = gx_K
+//   back   fine chains       v = wv + Phi'(v+ + q) from v_b = 0         -> segv0
+//          up / top / down   t <- segv0[e] + Psi[e]' t over the hierarchy -> segvb
+//          fine chains again from the true v_b, storing v[k]
+//   mid    (stage-parallel)  Ru = Guu^{-1}(gu + fu'(v+ + q));  c = f - fu Ru
+//   fwd    fine chains       x+ = Phi x + c from x_a = 0                -> segx0
+//          up / top / down   t <- segx0[e] + Psi[e] t                    -> segxa
+//          fine chains again from the true x_a, storing x[k]
+//   post   (stage-parallel)  u = -(Rux x + Ru); p = Vxx+ x+ + v+; dx,dy,dw,dz
+//
+// Every chain is one instance of chain_run(): matrices and vectors of the next
+// steps are staged into a shared-memory ring by TMA bulk copies ahead of use.
 #pragma once
 
 #include "lq_device.cuh"
 
-// y(n) = [y0 +] A' t  or  A t for an n x n row-major matrix in GLOBAL memory,
-// 4 lanes per output row, result valid in every lane of the quad.
+#define LQ_RING 8  // stages in flight per chain (TMA ring depth)
+
+// One sequential affine chain executed by a whole CTA (4 lanes per row):
+//     for j = 0..cnt-1, e = first + j*dir:
+//         if pre:  pre[e] = t
+//         t <- a[e] + op(M[e]) (t + b[e])          op = transpose if TRANS
+//         if post: post[e + post_shift] = t
+// M: n x n row-major blocks (stride n*n), a/b/pre/post: n-vectors (stride n).
+// t lives in registers (valid for part == 0 lanes and replicated in the quad).
+// ring: LQ_RING slots of (n*n + 2n) doubles + LQ_RING mbarriers; tvec: n doubles.
 template <bool TRANS>
-__device__ __forceinline__ double quad_matvec(const double *__restrict__ A, const double *t,
-                                              int n, int i, int part) {
-  double s = 0.0;
-  if (i < n) {
-    if (TRANS) {
-      for (int l = part; l < n; l += 4) s = fma(A[l * n + i], t[l], s);
-    } else {
-      for (int l = part; l < n; l += 4) s = fma(A[i * n + l], t[l], s);
+__device__ __forceinline__ double chain_run(int n, bool use_tma, const double *M,
+                                            const double *a, const double *b, double *pre,
+                                            double *post, int post_shift, int first, int dir,
+                                            int cnt, double t, double *ring, uint64_t *bars,
+                                            double *tvec) {
+  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+  const int slot_sz = n * n + 2 * n;
+  const uint32_t bm = n * n * 8, bv = n * 8;
+  if (use_tma && threadIdx.x == 0) {
+    for (int j = 0; j < LQ_RING && j < cnt; j++) {
+      const int e = first + j * dir;
+      double *sl = ring + (size_t)j * slot_sz;
+      mbar_expect_tx(&bars[j], bm + bv + (b ? bv : 0));
+      tma_load_1d(sl, M + (size_t)e * n * n, bm, &bars[j]);
+      tma_load_1d(sl + n * n, a + (size_t)e * n, bv, &bars[j]);
+      if (b) tma_load_1d(sl + n * n + n, b + (size_t)e * n, bv, &bars[j]);
     }
   }
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  return s;
+  for (int j = 0; j < cnt; j++) {
+    const int e = first + j * dir;
+    const int slot = j % LQ_RING;
+    const double *Ms, *as, *bs;
+    if (use_tma) {
+      const double *sl = ring + (size_t)slot * slot_sz;
+      mbar_wait(&bars[slot], (j / LQ_RING) & 1);
+      Ms = sl;
+      as = sl + n * n;
+      bs = b ? sl + n * n + n : nullptr;
+    } else {
+      Ms = M + (size_t)e * n * n;
+      as = a + (size_t)e * n;
+      bs = b ? b + (size_t)e * n : nullptr;
+    }
+    if (i < n && part == 0) {
+      if (pre) pre[(size_t)e * n + i] = t;
+      tvec[i] = bs ? t + bs[i] : t;
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (i < n) {
+      if (TRANS) {
+        for (int l = part; l < n; l += 4) s = fma(Ms[l * n + i], tvec[l], s);
+      } else {
+        for (int l = part; l < n; l += 4) s = fma(Ms[i * n + l], tvec[l], s);
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (i < n) {
+      t = as[i] + s;
+      if (post && part == 0) post[(size_t)(e + post_shift) * n + i] = t;
+    }
+    __syncthreads();
+    if (use_tma && threadIdx.x == 0 && j + LQ_RING < cnt) {
+      const int e2 = first + (j + LQ_RING) * dir;
+      double *sl = ring + (size_t)slot * slot_sz;
+      fence_proxy_async();
+      mbar_expect_tx(&bars[slot], bm + bv + (b ? bv : 0));
+      tma_load_1d(sl, M + (size_t)e2 * n * n, bm, &bars[slot]);
+      tma_load_1d(sl + n * n, a + (size_t)e2 * n, bv, &bars[slot]);
+      if (b) tma_load_1d(sl + n * n + n, b + (size_t)e2 * n, bv, &bars[slot]);
+    }
+  }
+  return t;
+}
+
+struct ChainSmem {
+  double *ring, *tvec;
+  uint64_t *bars;
+};
+
+__device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw) {
+  SmemCarver sm(raw);
+  ChainSmem cs;
+  cs.ring = sm.take(LQ_RING * (n * n + 2 * n));
+  cs.tvec = sm.take(n);
+  cs.bars = sm.take_bars(LQ_RING);
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < LQ_RING; j++) mbar_init(&cs.bars[j], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  return cs;
 }
 
 // ---- pre ------------------------------------------------------------------
@@ -86,52 +168,98 @@ __global__ void solve_pre_kernel(LqDev d, const double *__restrict__ r1,
   }
 }
 
-// ---- backward chains -------------------------------------------------------
+// ---- fine chains -------------------------------------------------------------
 // grid (P, batch), block = 4 * ceil32(nx) threads.
-// mode 0: start from 0, write segv0[s]; mode 1: start from segvb[s], store v[k].
+// back: mode 0 from 0, writes segv0[s]; mode 1 from segvb[s], stores v[k]
 __global__ void solve_back_kernel(LqDev d, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *t = reinterpret_cast<double *>(smem_raw);  // nx
   const int nx = d.nx;
+  ChainSmem cs = chain_smem_init(nx, smem_raw);
+  const int s = blockIdx.x, b = blockIdx.y;
+  const int ka = s * d.L, kb = min(d.K, ka + d.L);
+  const int i = threadIdx.x >> 2;
+  const size_t so = ((size_t)b * d.st.nel + s) * nx;
+  const size_t ks0 = (size_t)b * d.K;
+  double t = 0.0;
+  if (mode == 1 && i < nx) t = d.segvb[so + i];
+  t = chain_run<true>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx,
+                      nullptr, mode == 1 ? d.v + (size_t)b * (d.K + 1) * nx : nullptr, 0,
+                      kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec);
+  if (mode == 0 && i < nx && (threadIdx.x & 3) == 0) d.segv0[so + i] = t;
+}
+
+// fwd: mode 0 from x_a = 0, writes segx0[s] (x at the segment end);
+//      mode 1 from segxa[s], stores x[k], k = a..b
+__global__ void solve_fwd_kernel(LqDev d, int mode) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nx = d.nx;
+  ChainSmem cs = chain_smem_init(nx, smem_raw);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
-  const size_t so = ((size_t)b * d.P + s) * nx;
-  double vi = 0.0;
-  if (mode == 1 && i < nx) vi = d.segvb[so + i];
-  for (int k = kb - 1; k >= ka; k--) {
-    const size_t ks = (size_t)b * d.K + k;
-    if (i < nx && part == 0) t[i] = vi + d.q[ks * nx + i];
-    __syncthreads();
-    const double a = quad_matvec<true>(d.Phi + ks * nx * nx, t, nx, i, part);
-    if (i < nx) {
-      vi = d.wv[ks * nx + i] + a;
-      if (mode == 1 && part == 0) d.v[((size_t)b * (d.K + 1) + k) * nx + i] = vi;
-    }
-    __syncthreads();
+  const size_t so = ((size_t)b * d.st.nel + s) * nx;
+  const size_t ks0 = (size_t)b * d.K;
+  double *xb = d.x + (size_t)b * (d.K + 1) * nx;
+  double t = 0.0;
+  if (mode == 1 && i < nx) {
+    t = d.segxa[so + i];
+    if (part == 0) xb[(size_t)ka * nx + i] = t;
   }
-  if (mode == 0 && i < nx && part == 0) d.segv0[so + i] = vi;
+  t = chain_run<false>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
+                       mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
+                       cs.tvec);
+  if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = t;
 }
 
-// grid (batch): segvb[P-1] = v[K]; segvb[s] = segv0[s+1] + Psi[s+1]' segvb[s+1]
-__global__ void solve_back_scan_kernel(LqDev d) {
+// ---- hierarchy scans -----------------------------------------------------------
+// phase 0 (up)  : CTA g composes the children of element g of level lev+1:
+//                 from t = 0, t <- v0[e] + Psi[e]^(T) t; result -> v0 of (lev+1, g)
+// phase 1 (top) : one CTA per instance walks all elements of level lev from the
+//                 boundary value (v[K] backward / x_0 forward), recording the
+//                 value at every element's far side -> vb / xa
+// phase 2 (down): CTA g walks the children of (lev+1, g) from that element's
+//                 vb / xa, recording the children's values
+// backward (BACK = true): children visited last -> first with Psi'.
+template <bool BACK>
+__global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__restrict__ r2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *t = reinterpret_cast<double *>(smem_raw);
-  const int nx = d.nx, b = blockIdx.x;
+  const int nx = d.nx;
+  ChainSmem cs = chain_smem_init(nx, smem_raw);
+  const int g = blockIdx.x, b = blockIdx.y;
   const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
-  double vi = 0.0;
-  if (i < nx) vi = d.v[((size_t)b * (d.K + 1) + d.K) * nx + i];
-  for (int s = d.P - 1; s >= 0; s--) {
-    const size_t so = ((size_t)b * d.P + s) * nx;
-    if (i < nx && part == 0) {
-      d.segvb[so + i] = vi;
-      t[i] = vi;
+  const size_t eb = (size_t)b * d.st.nel + d.st.off[lev];           // first element of level
+  const size_t pb = (size_t)b * d.st.nel + (phase == 1 ? 0 : d.st.off[lev + 1]);
+  double *in0 = BACK ? d.segv0 : d.segx0;   // zero-boundary solutions
+  double *bnd = BACK ? d.segvb : d.segxa;   // boundary values
+  int c0, c1;
+  double t = 0.0;
+  if (phase == 1) {
+    c0 = 0;
+    c1 = d.st.cnt[lev];
+    if (BACK) {
+      if (i < nx) t = d.v[((size_t)b * (d.K + 1) + d.K) * nx + i];
+    } else if (d.fixed_x0) {
+      // x_0 = -a_0 (hqp/Hqp_IpLQDOCP.C:2099-2100)
+      if (i < nx) t = -r2[(size_t)b * d.me + (size_t)d.K * nx + i];
+    } else {
+      // x_0 = -Vxx[0]^{-1} v[0] (:2111-2117)
+      if (threadIdx.x < nx) cs.tvec[threadIdx.x] = -d.v[(size_t)b * (d.K + 1) * nx + threadIdx.x];
+      __syncthreads();
+      if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * nx * nx, nx, nx, cs.tvec, 1);
+      __syncthreads();
+      if (i < nx) t = cs.tvec[i];
+      __syncthreads();
     }
-    __syncthreads();
-    const double a = quad_matvec<true>(d.segPsi + so * nx, t, nx, i, part);
-    if (i < nx) vi = d.segv0[so + i] + a;
-    __syncthreads();
+  } else {
+    c0 = g * d.st.R;
+    c1 = min(d.st.cnt[lev], c0 + d.st.R);
+    if (phase == 2 && i < nx) t = bnd[(pb + g) * nx + i];
   }
+  const int first = BACK ? c1 - 1 : c0, dir = BACK ? -1 : +1;
+  t = chain_run<BACK>(nx, d.use_tma, d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
+                      phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir, c1 - c0, t,
+                      cs.ring, cs.bars, cs.tvec);
+  if (phase == 0 && i < nx && part == 0) in0[(pb + g) * nx + i] = t;
 }
 
 // ---- mid -------------------------------------------------------------------
@@ -141,87 +269,31 @@ __global__ void solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   double *t = reinterpret_cast<double *>(smem_raw);  // nx
   double *Gu = t + nx;                               // nu
+  double *LDs = Gu + nu;                             // nu*nu
+  double *fus = LDs + nu * nu;                       // nx*nu
   const int k = blockIdx.x, b = blockIdx.y;
   const size_t ks = (size_t)b * d.K + k;
   const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
   const double *fu = d.fu + ks * nx * nu;
+  const double *LD = d.LD + ks * nu * nu;
   const double *g = d.g + (size_t)b * d.N + (size_t)k * nm;
+  for (int i = threadIdx.x; i < nx * nu; i += blockDim.x) fus[i] = fu[i];
+  for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) LDs[i] = LD[i];
   for (int i = threadIdx.x; i < nx; i += blockDim.x) t[i] = vp[i] + d.q[ks * nx + i];
   __syncthreads();
   for (int j = threadIdx.x; j < nu; j += blockDim.x) {
     double s = g[nx + j];
-    for (int l = 0; l < nx; l++) s = fma(fu[l * nu + j], t[l], s);
+    for (int l = 0; l < nx; l++) s = fma(fus[l * nu + j], t[l], s);
     Gu[j] = s;
   }
   __syncthreads();
-  if (threadIdx.x == 0) thread_ldlt_solve(d.LD + ks * nu * nu, nu, nu, Gu, 1);
+  if (threadIdx.x == 0) thread_ldlt_solve(LDs, nu, nu, Gu, 1);
   __syncthreads();
   for (int j = threadIdx.x; j < nu; j += blockDim.x) d.Ru[ks * nu + j] = Gu[j];
   for (int i = threadIdx.x; i < nx; i += blockDim.x) {
     double s = r2[(size_t)b * d.me + (size_t)k * nx + i];
-    for (int l = 0; l < nu; l++) s = fma(-fu[i * nu + l], Gu[l], s);
+    for (int l = 0; l < nu; l++) s = fma(-fus[i * nu + l], Gu[l], s);
     d.c[ks * nx + i] = s;
-  }
-}
-
-// ---- forward chains ---------------------------------------------------------
-// mode 0: from x_a = 0, write segx0[s] (= x at segment end);
-// mode 1: from segxa[s], store x[k], k = a..b
-__global__ void solve_fwd_kernel(LqDev d, int mode) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *t = reinterpret_cast<double *>(smem_raw);
-  const int nx = d.nx;
-  const int s = blockIdx.x, b = blockIdx.y;
-  const int ka = s * d.L, kb = min(d.K, ka + d.L);
-  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
-  const size_t so = ((size_t)b * d.P + s) * nx;
-  double xi = 0.0;
-  if (mode == 1 && i < nx) {
-    xi = d.segxa[so + i];
-    if (part == 0) d.x[((size_t)b * (d.K + 1) + ka) * nx + i] = xi;
-  }
-  for (int k = ka; k < kb; k++) {
-    const size_t ks = (size_t)b * d.K + k;
-    if (i < nx && part == 0) t[i] = xi;
-    __syncthreads();
-    const double a = quad_matvec<false>(d.Phi + ks * nx * nx, t, nx, i, part);
-    if (i < nx) {
-      xi = d.c[ks * nx + i] + a;
-      if (mode == 1 && part == 0) d.x[((size_t)b * (d.K + 1) + k + 1) * nx + i] = xi;
-    }
-    __syncthreads();
-  }
-  if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = xi;
-}
-
-// grid (batch): x_0 (fixed: -a_0, hqp/Hqp_IpLQDOCP.C:2099-2100; free:
-// -Vxx[0]^{-1} v[0], :2111-2117), then segxa[s+1] = Psi[s] segxa[s] + segx0[s]
-__global__ void solve_fwd_scan_kernel(LqDev d, const double *__restrict__ r2) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *t = reinterpret_cast<double *>(smem_raw);
-  const int nx = d.nx, b = blockIdx.x;
-  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
-  double xi = 0.0;
-  if (d.fixed_x0) {
-    if (i < nx) xi = -r2[(size_t)b * d.me + (size_t)d.K * nx + i];
-  } else {
-    if (threadIdx.x < nx) t[threadIdx.x] = -d.v[(size_t)b * (d.K + 1) * nx + threadIdx.x];
-    __syncthreads();
-    if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * nx * nx, nx, nx, t, 1);
-    __syncthreads();
-    if (i < nx) xi = t[i];
-    __syncthreads();
-  }
-  for (int s = 0; s < d.P; s++) {
-    const size_t so = ((size_t)b * d.P + s) * nx;
-    if (i < nx && part == 0) {
-      d.segxa[so + i] = xi;
-      t[i] = xi;
-    }
-    __syncthreads();
-    const double a = quad_matvec<false>(d.segPsi + so * nx, t, nx, i, part);
-    if (i < nx) xi = d.segx0[so + i] + a;
-    __syncthreads();
   }
 }
 
@@ -235,18 +307,21 @@ __global__ void solve_post_kernel(LqDev d, const double *__restrict__ r3,
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   double *xs = reinterpret_cast<double *>(smem_raw);  // nm : dx of this stage
   double *xn = xs + nm;                                // nx : x[k+1]
+  double *Rs = xn + nx;                                // nu*nx : Rux of this stage
   const int k = blockIdx.x, b = blockIdx.y;
   const double *xk = d.x + ((size_t)b * (d.K + 1) + k) * nx;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = xk[i];
-  if (k < d.K)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) xn[i] = xk[nx + i];
-  __syncthreads();
   const size_t ks = (size_t)b * d.K + k;
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = xk[i];
   if (k < d.K) {
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) xn[i] = xk[nx + i];
     const double *Rux = d.Rux + ks * nu * nx;
+    for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) Rs[i] = Rux[i];
+  }
+  __syncthreads();
+  if (k < d.K) {
     for (int j = threadIdx.x; j < nu; j += blockDim.x) {
       double s = d.Ru[ks * nu + j];
-      for (int l = 0; l < nx; l++) s = fma(Rux[j * nx + l], xs[l], s);
+      for (int l = 0; l < nx; l++) s = fma(Rs[j * nx + l], xs[l], s);
       xs[nx + j] = -s;  // u_k
     }
     // p_k = Vxx[k+1] x[k+1] + v[k+1]   (:2169-2171)

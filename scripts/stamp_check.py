@@ -1,0 +1,14 @@
+import sys, os, ctypes
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from hqp_b200 import ipcuda
+ipcuda.LIB_PATH = os.path.join(os.path.dirname(ipcuda.LIB_PATH), "libhqpcuda_timing.so")
+from hqp_b200.problem import synth_lqdocp, synth_rhs
+p = synth_lqdocp(20, 10, 10000)
+z, w, r1, r2, r3, r4 = synth_rhs(p)
+e = ipcuda.IpCuda(p); e.update()
+for _ in range(3): e.factor(z, w)
+out = (ctypes.c_longlong * 16)()
+ipcuda.lib().hqpcu_debug_stamps(e.h, out)
+st = list(out)
+print("stamps (cycles, last compose launch = top group):", [st[i+1]-st[i] for i in range(6)], "total", st[6]-st[0])
