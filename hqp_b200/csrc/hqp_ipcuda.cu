@@ -22,6 +22,7 @@
 #include "lq_device.cuh"
 #include "lq_factor.cuh"
 #include "lq_solve.cuh"
+#include "lq_eq.cuh"
 
 static thread_local std::string g_err;
 
@@ -71,6 +72,9 @@ struct hqpcu_handle {
   double *res_host = nullptr;  // pinned
   int *status_host = nullptr;  // pinned
   bool factored = false;
+  // general stage equality rows (block elimination on top of the factor)
+  LqEq q;
+  double *eqval = nullptr, *eq_r1 = nullptr;
   // optional per-kernel CUDA-event timing (bench.py roofline section)
   bool profiling = false;
   struct Span { const char *name; cudaEvent_t e0, e1; };
@@ -184,10 +188,15 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     g_err = "hqpcu_create: nx > 64 needs the tiled large-block kernels (not built yet)";
     return HQPCU_E_UNSUPPORTED;
   }
-  if (dims->n_eq > 0) {
-    g_err = "hqpcu_create: general stage equality rows are not supported yet";
+  if (dims->n_eq > 0 && dims->batch != 1) {
+    g_err = "hqpcu_create: general stage equality rows need batch == 1";
     return HQPCU_E_UNSUPPORTED;
   }
+  if (dims->n_eq > 64) {
+    g_err = "hqpcu_create: more than 64 general stage equality rows";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  if (dims->n_eq > 0 && (!dims->eq_stage || !dims->eq_ptr || !dims->eq_lcol)) return HQPCU_E_NULL;
   if (dims->n_ineq > 0 && (!dims->ineq_stage || !dims->ineq_ptr || !dims->ineq_lcol))
     return HQPCU_E_NULL;
   int ndev = 0;
@@ -211,7 +220,10 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   d.m = m;
   d.nnz = m ? dims->ineq_ptr[m] : 0;
   d.N = K * nm + nx;
-  d.me = K * nx + (d.fixed_x0 ? nx : 0);
+  d.me = K * nx + (d.fixed_x0 ? nx : 0) + dims->n_eq;
+  memset(&h->q, 0, sizeof h->q);
+  h->q.n_eq = dims->n_eq;
+  h->q.nnz = dims->n_eq ? dims->eq_ptr[dims->n_eq] : 0;
   choose_segments(h, dims->nseg);
 
   // ---- index maps -------------------------------------------------------
@@ -274,6 +286,36 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_upload(h, &d.vcol_ptr, vcol_ptr));
   TRY(dev_upload(h, &d.vcol_row, vcol_row));
   TRY(dev_upload(h, &d.vcol_nz, vcol_nz));
+
+  if (dims->n_eq) {
+    const int ne = dims->n_eq;
+    std::vector<int> es(dims->eq_stage, dims->eq_stage + ne), ep(dims->eq_ptr, dims->eq_ptr + ne + 1),
+        ec(dims->eq_lcol, dims->eq_lcol + h->q.nnz);
+    for (int r = 0; r < ne; r++) {
+      const int k = es[r];
+      bool ok = k >= 0 && k <= K && ep[r + 1] >= ep[r];
+      for (int e = ep[r]; ok && e < ep[r + 1]; e++) ok = ec[e] >= 0 && ec[e] < (k < K ? nm : nx);
+      if (!ok) {
+        g_err = "hqpcu_create: equality row outside its stage block";
+        hqpcu_destroy(h);
+        return HQPCU_E_SIZES;
+      }
+    }
+    TRY(dev_upload(h, &h->q.stage, es));
+    TRY(dev_upload(h, &h->q.ptr, ep));
+    TRY(dev_upload(h, &h->q.lcol, ec));
+    TRY(dev_alloc(h, &h->eqval, (size_t)h->q.nnz));
+    h->q.val = h->eqval;
+    TRY(dev_alloc(h, &h->q.DX, (size_t)ne * d.N));
+    TRY(dev_alloc(h, &h->q.DY, (size_t)ne * d.me));
+    TRY(dev_alloc(h, &h->q.DZ, (size_t)ne * std::max(m, 1)));
+    TRY(dev_alloc(h, &h->q.DW, (size_t)ne * std::max(m, 1)));
+    TRY(dev_alloc(h, &h->q.S, (size_t)ne * ne));
+    TRY(dev_alloc(h, &h->q.Sinv, (size_t)ne * ne));
+    TRY(dev_alloc(h, &h->q.y, (size_t)ne));
+    TRY(dev_alloc(h, &h->q.ety, (size_t)d.N));
+    TRY(dev_alloc(h, &h->eq_r1, (size_t)d.N));
+  }
 
   // ---- slabs --------------------------------------------------------------
   const size_t SB = (size_t)B;
@@ -402,8 +444,8 @@ int hqpcu_nseg(const hqpcu_handle *h) { return h ? h->d.P : 0; }
 
 // ------------------------------------------------------------------ update --
 static int update_impl(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
-                       const double *cv, cudaMemcpyKind kind) {
-  if (!h || !Q || !fx || !fu || (h->d.nnz && !cv)) return HQPCU_E_NULL;
+                       const double *cv, const double *ev, cudaMemcpyKind kind) {
+  if (!h || !Q || !fx || !fu || (h->d.nnz && !cv) || (h->q.nnz && !ev)) return HQPCU_E_NULL;
   const LqDev &d = h->d;
   const size_t B = d.batch;
   CU(cudaSetDevice(h->device));
@@ -412,24 +454,56 @@ static int update_impl(hqpcu_handle *h, const double *Q, const double *fx, const
   CU(cudaMemcpyAsync(h->fu, fu, B * d.K * d.nx * d.nu * sizeof(double), kind, h->stream));
   if (d.nnz)
     CU(cudaMemcpyAsync(h->cval, cv, B * d.nnz * sizeof(double), kind, h->stream));
+  if (h->q.nnz)
+    CU(cudaMemcpyAsync(h->eqval, ev, (size_t)h->q.nnz * sizeof(double), kind, h->stream));
   h->factored = false;
   return HQPCU_OK;
 }
 
 int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
-                 const double *ineq_val, const double *) {
-  int rc = update_impl(h, Q, fx, fu, ineq_val, cudaMemcpyHostToDevice);
+                 const double *ineq_val, const double *eq_val) {
+  int rc = update_impl(h, Q, fx, fu, ineq_val, eq_val, cudaMemcpyHostToDevice);
   if (rc) return rc;
   CU(cudaStreamSynchronize(h->stream));
   return HQPCU_OK;
 }
 
 int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
-                     const double *ineq_val, const double *) {
-  return update_impl(h, Q, fx, fu, ineq_val, cudaMemcpyDeviceToDevice);
+                     const double *ineq_val, const double *eq_val) {
+  return update_impl(h, Q, fx, fu, ineq_val, eq_val, cudaMemcpyDeviceToDevice);
 }
 
 // ------------------------------------------------------------------ factor --
+static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
+                            const double *r3, const double *r4, double *dx, double *dy,
+                            double *dz, double *dw);
+
+// extra solves + Schur complement of the general equality rows (lq_eq.cuh)
+static int launch_eq_factor(hqpcu_handle *h) {
+  const LqDev &d = h->d;
+  const LqEq &q = h->q;
+  cudaStream_t s = h->stream;
+  const int ne = q.n_eq;
+  // zero right-hand sides: t2..t4 double as scratch (overwritten by every residuum)
+  CU(cudaMemsetAsync(h->t2, 0, (size_t)d.me * sizeof(double), s));
+  if (d.m) {
+    CU(cudaMemsetAsync(h->t3, 0, (size_t)d.m * sizeof(double), s));
+    CU(cudaMemsetAsync(h->t4, 0, (size_t)d.m * sizeof(double), s));
+  }
+  for (int j = 0; j < ne; j++) {
+    CU(cudaMemsetAsync(h->eq_r1, 0, (size_t)d.N * sizeof(double), s));
+    LAUNCH(h, eq_unit_rhs_kernel, <<<1, 64, 0, s>>>(d, q, j, h->eq_r1));
+    int rc = launch_step_base(h, h->eq_r1, h->t2, h->t3, h->t4, q.DX + (size_t)j * d.N,
+                              q.DY + (size_t)j * d.me, q.DZ + (size_t)j * std::max(d.m, 1),
+                              q.DW + (size_t)j * std::max(d.m, 1));
+    if (rc) return rc;
+  }
+  LAUNCH(h, eq_schur_kernel, <<<(ne * ne + 127) / 128, 128, 0, s>>>(d, q));
+  LAUNCH(h, eq_invert_kernel, <<<1, 128, (size_t)3 * ne * ne * sizeof(double), s>>>(d, q));
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
 static int launch_factor(hqpcu_handle *h) {
   const LqDev &d = h->d;
   cudaStream_t s = h->stream;
@@ -474,6 +548,7 @@ static int launch_factor(hqpcu_handle *h) {
            <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
   CU(cudaGetLastError());
   h->factored = true;
+  if (h->q.n_eq) return launch_eq_factor(h);
   return HQPCU_OK;
 }
 
@@ -541,8 +616,9 @@ int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
 }
 
 // -------------------------------------------------------------------- step --
-static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
-                       const double *r4, double *dx, double *dy, double *dz, double *dw) {
+static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
+                            const double *r3, const double *r4, double *dx, double *dy,
+                            double *dz, double *dw) {
   const LqDev &d = h->d;
   if (!h->factored) {
     g_err = "step before factor";
@@ -572,6 +648,19 @@ static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, cons
     LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_post_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                       const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  int rc = launch_step_base(h, r1, r2, r3, r4, dx, dy, dz, dw);
+  if (rc || !h->q.n_eq) return rc;
+  const LqDev &d = h->d;
+  cudaStream_t s = h->stream;
+  LAUNCH(h, eq_multiplier_kernel, <<<1, 64, (size_t)(h->q.n_eq + 2) * sizeof(double), s>>>(d, h->q, r2, dx));
+  const int blocks = (int)std::min<size_t>(((size_t)d.N + 255) / 256, 148 * 8);
+  LAUNCH(h, eq_combine_kernel, <<<blocks, 256, 0, s>>>(d, h->q, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -630,9 +719,13 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
   CU(cudaMemsetAsync(h->res_dev, 0, sizeof(double), h->stream));
   const dim3 gall(d.K + 1, d.batch);
   const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
+  if (h->q.n_eq)
+    LAUNCH(h, eq_residuum_kernel, <<<1, 256, 0, h->stream>>>(d, h->q, r2, dx, dy,
+                                                              keep ? h->t2 : nullptr, h->res_dev));
   LAUNCH(h, residuum_kernel, <<<gall, h->thr_stage, sv, h->stream>>>(
       d, r1, r2, r3, r4, dx, dy, dz, dw, keep ? h->t1 : nullptr, keep ? h->t2 : nullptr,
-      keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev));
+      keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev,
+      h->q.n_eq ? h->q.ety : nullptr));
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));

@@ -373,7 +373,8 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
                                 const double *__restrict__ r4, const double *__restrict__ dx,
                                 const double *__restrict__ dy, const double *__restrict__ dz,
                                 const double *__restrict__ dw, double *t1, double *t2,
-                                double *t3, double *t4, double *res) {
+                                double *t3, double *t4, double *res,
+                                const double *__restrict__ ety) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   double *xs = reinterpret_cast<double *>(smem_raw);  // nm: dx stage k
@@ -412,6 +413,7 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
     const int gv = k * nm + i;
     for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++)
       s = fma(-cv[d.vcol_nz[e]], dz[(size_t)b * d.m + d.vcol_row[e]], s);
+    if (ety) s -= ety[xo + i];  // general equality rows (batch == 1)
     if (t1) t1[xo + i] = s;
     mx = fmax(mx, fabs(s));
     bad |= (s != s);

@@ -136,11 +136,12 @@ class IpCuda:
         return json.loads(buf.value.decode())
 
     # -- host-pointer API (what the plugin calls) --------------------------
-    def update(self, Q=None, fx=None, fu=None, ineq_val=None):
+    def update(self, Q=None, fx=None, fu=None, ineq_val=None, eq_val=None):
         p = self.prob
         arrs = [np.ascontiguousarray(a if a is not None else d, np.float64)
-                for a, d in ((Q, p.Q), (fx, p.fx), (fu, p.fu), (ineq_val, p.ineq_val))]
-        _check(lib().hqpcu_update(self.h, *[_hp(a) for a in arrs], None), "hqpcu_update")
+                for a, d in ((Q, p.Q), (fx, p.fx), (fu, p.fu), (ineq_val, p.ineq_val),
+                             (eq_val, p.eq_val))]
+        _check(lib().hqpcu_update(self.h, *[_hp(a) for a in arrs]), "hqpcu_update")
 
     def factor(self, z, w):
         z = np.ascontiguousarray(z, np.float64)

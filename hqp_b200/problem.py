@@ -260,3 +260,28 @@ def rhs_for(prob: LQProblem, seed=4321):
     m = prob.m
     return (rng.uniform(0.5, 1.5, m), rng.uniform(0.5, 1.5, m), rng.uniform(-1, 1, prob.N),
             rng.uniform(-1, 1, prob.me), rng.uniform(-1, 1, m), rng.uniform(-1, 1, m))
+
+
+def add_stage_equalities(prob: LQProblem, stages, rows_per_stage=1, nnz_per_row=None, seed=21):
+    """Append general stage-local equality rows  e'[x_k;u_k] + b = 0  (e.g. a
+    terminal state constraint like Prg_DID's x_K = (-1, 0), hqp_docp/Prg_DID.C)
+    after the dynamics / x0 rows of A.  Rows of one stage are linearly
+    independent with probability one."""
+    rng = np.random.default_rng(seed)
+    ptr, col, val = list(prob.eq_ptr), list(prob.eq_col), list(prob.eq_val)
+    b = list(prob.b)
+    nm = prob.nm
+    for k in stages:
+        dk = nm if k < prob.K else prob.nx
+        for _ in range(rows_per_stage):
+            nz = dk if nnz_per_row is None else min(nnz_per_row, dk)
+            cols = np.sort(rng.choice(dk, size=nz, replace=False))
+            col.extend((k * nm + cols).tolist())
+            val.extend(rng.uniform(-1, 1, nz).tolist())
+            b.append(float(rng.uniform(-0.1, 0.1)))
+            ptr.append(len(col))
+    prob.eq_ptr = np.asarray(ptr, np.int32)
+    prob.eq_col = np.asarray(col, np.int32)
+    prob.eq_val = np.asarray(val, np.float64)
+    prob.b = np.asarray(b, np.float64)
+    return prob

@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 sys.path.insert(0, GOLDEN)
 
-from hqp_b200.problem import synth_lqdocp, add_random_stage_ineq, rhs_for  # noqa: E402
+from hqp_b200.problem import (synth_lqdocp, add_random_stage_ineq, rhs_for,  # noqa: E402
+                              add_stage_equalities)
 
 
 def make_problem(nx, nu, K, bounds, gen, fixed):
@@ -19,6 +20,17 @@ def make_problem(nx, nu, K, bounds, gen, fixed):
         p.fixed_x0 = False
         p.b = p.b[:K * nx].copy()
     return p
+
+
+def make_eq_problem(nx, nu, K, bounds, gen, fixed, stages, rows):
+    """must stay identical to tests/golden/make_golden.py:make_eq_problem"""
+    p = make_problem(nx, nu, K, bounds, gen, fixed)
+    return add_stage_equalities(p, stages, rows, seed=33)
+
+
+def eq_cases():
+    import make_golden
+    return make_golden.EQ_CASES
 
 
 def relerr(a, b):

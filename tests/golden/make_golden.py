@@ -20,7 +20,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
-from hqp_b200.problem import synth_lqdocp, add_random_stage_ineq, rhs_for  # noqa: E402
+from hqp_b200.problem import (synth_lqdocp, add_random_stage_ineq, rhs_for,  # noqa: E402
+                              add_stage_equalities)
 from oracle import refharness as R  # noqa: E402
 
 STEP_CASES = {
@@ -34,6 +35,22 @@ STEP_CASES = {
     "step_n6m2K30_gen": (6, 2, 30, True, 2, True),
     "step_n4m4K25_gen_free": (4, 4, 25, False, 3, False),
 }
+
+
+# general stage equality rows (terminal constraints etc.): name ->
+# (nx, nu, K, bounds, general ineq rows/stage, fixed_x0, stages with equality rows, rows per stage)
+EQ_CASES = {
+    "eqstep_terminal_n4m2K12": (4, 2, 12, True, 0, True, [12], 2),
+    "eqstep_terminal_full_n5m2K20": (5, 2, 20, True, 0, True, [20], 5),
+    "eqstep_mid_and_terminal_n3m2K16": (3, 2, 16, True, 1, True, [16, 7], 1),
+    "eqstep_free_x0_n4m3K9": (4, 3, 9, False, 0, False, [9, 0], 2),
+    "eqstep_n20m10K60": (20, 10, 60, True, 0, True, [60], 6),
+}
+
+
+def make_eq_problem(nx, nu, K, bounds, gen, fixed, stages, rows):
+    p = make_problem(nx, nu, K, bounds, gen, fixed)
+    return add_stage_equalities(p, stages, rows, seed=33)
 
 
 def make_problem(nx, nu, K, bounds, gen, fixed):
@@ -58,6 +75,18 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), cfg=np.array(cfg, dtype=np.int64),
                             z=z, w=w, r1=r1, r2=r2, r3=r3, r4=r4, dx=dx, dy=dy, dz=dz, dw=dw,
                             sx=sx, sy=sy, sz=sz, sw=sw, res=res)
+        print(name, "res", res)
+        M.close()
+        qp.close()
+    for name, cfg in EQ_CASES.items():
+        p = make_eq_problem(*cfg)
+        z, w, r1, r2, r3, r4 = rhs_for(p, seed=77)
+        qp = R.RefQP(p)
+        M = R.RefMatrix("LQDOCP", qp)
+        M.factor(z, w)
+        sx, sy, sz, sw, res = M.solve(z, w, r1, r2, r3, r4)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), z=z, w=w, r1=r1, r2=r2, r3=r3,
+                            r4=r4, sx=sx, sy=sy, sz=sz, sw=sw, res=res)
         print(name, "res", res)
         M.close()
         qp.close()

@@ -196,3 +196,40 @@ def test_c2_prefix_matches_oracle_on_truncated_horizon():
     for a, b in zip(mine, ref):
         assert relerr(a, b) < TOL
     e.close(); o.close()
+
+
+# ---- general stage equality rows (terminal constraints) ------------------------
+from common import dense_kkt_solve, eq_cases, make_eq_problem  # noqa: E402
+import os  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(eq_cases()))
+@pytest.mark.parametrize("nseg", [1, 0])
+def test_equality_rows_match_reference_golden(name, nseg, golden_dir):
+    """The reference eliminates stage equalities with its GE_QP null-space step
+    (hqp/Hqp_IpLQDOCP.C:1883-1938); the block-elimination path must give the
+    same KKT solution."""
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    p = make_eq_problem(*eq_cases()[name])
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    e.factor(g["z"], g["w"])
+    dx, dy, dz, dw, res, nsteps = e.solve(g["r1"], g["r2"], g["r3"], g["r4"])
+    for mine, key in ((dx, "sx"), (dy, "sy"), (dz, "sz"), (dw, "sw")):
+        assert relerr(mine, g[key]) < 1e-9, (key, relerr(mine, g[key]))
+    assert res <= 1e-10
+    e.close()
+
+
+def test_equality_rows_match_dense_kkt():
+    p = make_eq_problem(4, 2, 7, True, 1, True, [7, 3], 2)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=12)
+    ref = dense_kkt_solve(p, z, w, r1, r2, r3, r4)
+    e = IpCuda(p)
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < 1e-9
+    assert e.residuum(r1, r2, r3, r4, *mine) < 1e-10
+    e.close()
