@@ -1,0 +1,69 @@
+/*
+ * Hqp_IpCuda.h --
+ *   - matrix module for HQP's interior-point QP solvers that factors and
+ *     solves the stage-structured KKT system on an NVIDIA B200 through the
+ *     C ABI of libhqpcuda.so (include/hqp_ipcuda.h)
+ *   - implements the plugin interface Hqp_IpMatrix (hqp/Hqp_IpMatrix.h:42-89)
+ *     and is selected like every other module:  qp_mat_solver Cuda
+ *   - same layering as Hqp_IpPARDISO + pardiso_wrapper
+ *     (hqp/Hqp_IpPARDISO.C:161-166, hqp/pardiso_wrapper.h:32-48): a thin C++
+ *     class that owns no numerics
+ *
+ * This file is new code; it only includes the reference's public headers.
+ */
+#ifndef Hqp_IpCuda_H
+#define Hqp_IpCuda_H
+
+#include <vector>
+
+#include "Hqp_IpMatrix.h"
+
+struct hqpcu_handle;
+
+class Hqp_IpCuda : public Hqp_IpMatrix {
+ protected:
+  hqpcu_handle *_h;
+  // interface options
+  int _nseg;      ///< mat_nseg: horizon segments (0 = automatic, 1 = sequential)
+  int _device;    ///< mat_device: CUDA device ordinal
+  int _dev_solve; ///< mat_dev_solve: run the refinement loop of solve() on the device
+
+  // stage structure derived from the sparsity of A and C (cf. Hqp_IpLQDOCP
+  // Get_Dim / Get_Constr_Dim / Check_Structure)
+  int _K, _nx, _nu, _n, _me, _m;
+  int _fixed_x0;
+  int _n_eq;
+  std::vector<int> _rowmap;   ///< ABI equality row -> row of qp->A
+  std::vector<int> _ineq_ptr; ///< CSR pattern of qp->C as passed to the ABI
+  std::vector<int> _eq_ptr;
+  // packed host slabs (reused between updates)
+  std::vector<double> _Q, _fx, _fu, _cval, _eval;
+  std::vector<double> _r2p, _dyp; ///< permuted copies when _rowmap is not the identity
+  bool _identity_rows;
+
+  void free_handle();
+  void check(int status, const char *where);
+  const double *pack_r2(const VEC *r2);
+  void unpack_dy(VEC *dy);
+
+ public:
+  Hqp_IpCuda();
+  ~Hqp_IpCuda();
+
+  void init(const Hqp_Program *);
+  void update(const Hqp_Program *);
+  void factor(const Hqp_Program *, const VEC *z, const VEC *w);
+  void step(const Hqp_Program *, const VEC *z, const VEC *w,
+            const VEC *r1, const VEC *r2, const VEC *r3, const VEC *r4,
+            VEC *dx, VEC *dy, VEC *dz, VEC *dw);
+  Real solve(const Hqp_Program *, const VEC *z, const VEC *w,
+             const VEC *r1, const VEC *r2, const VEC *r3, const VEC *r4,
+             VEC *dx, VEC *dy, VEC *dz, VEC *dw);
+  Real residuum(const Hqp_Program *, const VEC *z, const VEC *w,
+                const VEC *r1, const VEC *r2, const VEC *r3, const VEC *r4,
+                VEC *dx, VEC *dy, VEC *dz, VEC *dw);
+
+  const char *name() { return "Cuda"; }
+};
+
+#endif

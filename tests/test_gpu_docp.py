@@ -1,0 +1,54 @@
+"""Full-stack drop-in test: the reference's own host code (Hqp_Docp,
+Hqp_SqpPowell, Hqp_IpsMehrotra/Franke, iftcl; all unmodified, oracle/_ref) drives
+the Hqp_IpCuda module selected with  qp_mat_solver Cuda  on the hqp_docp example
+(hqp_docp/Docp_Main.C), and must reproduce the LQDOCP runs recorded in
+tests/golden/docp.json: identical SQP / IP iteration counts, objective within
+1e-8 relative (BASELINE.json north star)."""
+import json
+import os
+
+import pytest
+
+from oracle import refharness
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN = os.path.join(ROOT, "hqp_b200", "lib", "libhqp_ipcuda_plugin.so")
+
+needs_ref = pytest.mark.skipif(
+    not (refharness.available() and os.path.exists(PLUGIN)),
+    reason="oracle/_ref or the Hqp_IpCuda plugin were not built (needs /root/reference at build time)")
+
+
+def gold():
+    with open(os.path.join(ROOT, "tests", "golden", "docp.json")) as f:
+        return json.load(f)
+
+
+@needs_ref
+@pytest.mark.parametrize("key,kmax,qps", [
+    ("K60_Mehrotra_LQDOCP", 60, "Mehrotra"),
+    ("K200_Mehrotra_LQDOCP", 200, "Mehrotra"),
+    ("K1000_Mehrotra_LQDOCP", 1000, "Mehrotra"),
+])
+def test_docp_mehrotra_cuda_matches_lqdocp(key, kmax, qps):
+    g = gold()[key]
+    r = refharness.docp_did(kmax, qps, "Cuda", plugin=PLUGIN)
+    assert r["result"] == "optimal"
+    assert r["sqp_iters"] == g["sqp_iters"]
+    assert r["qp_iters"] == g["qp_iters"]
+    assert abs(r["objective"] - g["objective"]) <= 1e-8 * abs(g["objective"])
+
+
+@needs_ref
+def test_docp_as_shipped_franke_cuda():
+    """as shipped: Powell + Franke (hqp_docp/Docp_Main.C:42); Franke's stop test
+    consumes the refinement residual, so only the objective and optimality are
+    required to match exactly; the IP iteration count may differ by rounding."""
+    g = gold()["K60_asShipped_Franke_LQDOCP"]
+    r = refharness.docp_did(60, "", "Cuda", plugin=PLUGIN)
+    assert r["result"] == "optimal"
+    assert r["sqp_iters"] == g["sqp_iters"]
+    assert abs(r["objective"] - g["objective"]) <= 1e-8 * abs(g["objective"])
+    assert abs(r["qp_iters"] - g["qp_iters"]) <= 3
