@@ -23,6 +23,7 @@
 #include "lq_factor.cuh"
 #include "lq_solve.cuh"
 #include "lq_eq.cuh"
+#include "lq_ips.cuh"
 
 static thread_local std::string g_err;
 
@@ -53,8 +54,13 @@ static thread_local std::string g_err;
     }                                                                         \
   } while (0)
 
+struct IpsState;
+
 struct hqpcu_handle {
   LqDev d;
+  IpsState *ips = nullptr;           // device-resident IP solver state (lazy)
+  std::vector<double> eq_rowsum;     // row sums |E| of the general equality rows
+  std::vector<int> dims_eq_ptr;      // host copy of the equality CSR pointers
   hqpcu_dims dims;
   cudaStream_t stream = nullptr;
   long long launches = 0;
@@ -167,6 +173,8 @@ static int set_smem(const void *fn, size_t bytes) {
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return HQPCU_OK;
 }
+
+static void ips_free(hqpcu_handle *h);
 
 extern "C" {
 
@@ -301,6 +309,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
         return HQPCU_E_SIZES;
       }
     }
+    h->dims_eq_ptr = ep;
     TRY(dev_upload(h, &h->q.stage, es));
     TRY(dev_upload(h, &h->q.ptr, ep));
     TRY(dev_upload(h, &h->q.lcol, ec));
@@ -427,6 +436,7 @@ int hqpcu_destroy(hqpcu_handle *h) {
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (void *p : h->allocs) cudaFree(p);
+  ips_free(h);
   if (h->res_host) cudaFreeHost(h->res_host);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
@@ -464,6 +474,9 @@ int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx, const doubl
                  const double *ineq_val, const double *eq_val) {
   int rc = update_impl(h, Q, fx, fu, ineq_val, eq_val, cudaMemcpyHostToDevice);
   if (rc) return rc;
+  h->eq_rowsum.assign(h->q.n_eq, 0.0);
+  for (int i = 0; i < h->q.n_eq; i++)
+    for (int e = h->dims_eq_ptr[i]; e < h->dims_eq_ptr[i + 1]; e++) h->eq_rowsum[i] += fabs(eq_val[e]);
   CU(cudaStreamSynchronize(h->stream));
   return HQPCU_OK;
 }
@@ -885,3 +898,5 @@ int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {
 }
 
 }  // extern "C"
+
+#include "hqp_ips_host.inc"

@@ -178,6 +178,23 @@ class IpCuda:
                "hqpcu_residuum")
         return res.value
 
+    def mehrotra_solve(self, c=None, b=None, d=None, eps=1e-9, max_iters=0):
+        """Hqp_IpsMehrotra cold_start + solve on the device (hqpcu_mehrotra_solve)."""
+        p = self.prob
+        c = np.ascontiguousarray(p.c if c is None else c, np.float64)
+        b = np.ascontiguousarray(p.b if b is None else b, np.float64)
+        d = np.ascontiguousarray(p.d if d is None else d, np.float64)
+        x, y = np.zeros(self.N), np.zeros(self.me)
+        z, w = np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        it, res, gap = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
+        _check(lib().hqpcu_mehrotra_solve(self.h, _hp(c), _hp(b), _hp(d), ctypes.c_double(eps),
+                                          max_iters, _hp(x), _hp(y), _hp(z), _hp(w),
+                                          ctypes.byref(it), ctypes.byref(res), ctypes.byref(gap)),
+               "hqpcu_mehrotra_solve")
+        names = ["optimal", "feasible", "infeasible", "suboptimal", "degenerate"]
+        return dict(x=x, y=y, z=z[:self.m], w=w[:self.m], iters=it.value,
+                    result=names[res.value], gap=gap.value)
+
     def get_factor(self):
         p, B = self.prob, self.batch
         V = np.zeros((B, p.K + 1, p.nx, p.nx))

@@ -135,6 +135,21 @@ int hqpcu_solve_dev(hqpcu_handle *h, double eps, const double *r1,
                     double *dx, double *dy, double *dz, double *dw,
                     double *res /* host */, int *nsteps);
 
+/* --- device-resident interior-point solve: Hqp_IpsMehrotra::cold_start + ::solve
+ *     (hqp/Hqp_IpsMehrotra.C:209-327, 355-733; predictor-corrector with Terlaky's
+ *     safeguard, qp_init_method 0) of
+ *         min 1/2 x'Qx + c'x   s.t.  A x + b = 0,  C x + d >= 0
+ *     for the Q, A, C given to hqpcu_update.  The residual / complementarity /
+ *     step-length vector passes run as fused kernels on vectors that stay in
+ *     HBM; only scalars return to the host between iterations.  batch == 1.
+ *     result: Hqp_Result (hqp/Hqp_impl.h:37-43) 0 optimal, 3 suboptimal,
+ *     4 degenerate.  max_iters <= 0: the reference default (200).  w, gap may
+ *     be NULL.                                                                 */
+int hqpcu_mehrotra_solve(hqpcu_handle *h, const double *c, const double *b,
+                         const double *d, double eps, int max_iters, double *x,
+                         double *y, double *z, double *w, int *iters, int *result,
+                         double *gap);
+
 /* --- per-kernel timing with CUDA events on the launching stream (bench.py's
  *     roofline section).  hqpcu_profile_read synchronises and writes a JSON
  *     object {"kernel": {"ms": total, "n": launches}, ...} for everything

@@ -104,6 +104,14 @@ def main():
                             iters_redspbkp=out["RedSpBKP"]["iters"],
                             result=np.array(r["result"]))
         qp.close()
+    # Mehrotra on a problem with general inequality rows and a terminal equality
+    p = make_eq_problem(6, 2, 30, True, 1, True, [30], 3)
+    qp = R.RefQP(p)
+    r = R.ips_solve(qp, "Mehrotra", "LQDOCP", 1e-9)
+    print("ips_eq_n6m2K30", r["iters"], r["result"], np.linalg.norm(r["x"]))
+    np.savez_compressed(os.path.join(HERE, "ips_eq_n6m2K30.npz"), x=r["x"], y=r["y"], z=r["z"],
+                        iters=r["iters"], result=np.array(r["result"]))
+    qp.close()
     docp = {}
     for key, (kmax, qps, mat) in {
             # "" keeps the as-shipped Hqp_IpsFranke instance (qp_eps 1e-9 set by
