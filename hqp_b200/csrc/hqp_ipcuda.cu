@@ -24,6 +24,7 @@
 #include "lq_solve.cuh"
 #include "lq_eq.cuh"
 #include "lq_ips.cuh"
+#include "lq_range.cuh"
 
 static thread_local std::string g_err;
 
@@ -88,6 +89,13 @@ struct hqpcu_handle {
   size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0, smem_cmp = 0, smem_psi = 0, smem_chain = 0;
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
   int max_el = 0;  // elements per instance the seg* arrays were sized for
+  // horizon split: right-hand sides remembered between the three step phases
+  const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
+  bool ranged() const { return d.has_prev || d.has_next; }
+  // level scanned sequentially by the "top" kernels: the single root when the
+  // range is part of a longer horizon, else the level below it
+  int ftop() const { return (ranged() || d.ft.nlev < 2) ? d.ft.nlev - 1 : d.ft.nlev - 2; }
+  int stop() const { return (ranged() || d.st.nlev < 2) ? d.st.nlev - 1 : d.st.nlev - 2; }
 };
 
 // launch wrapper: counts the launch and, when profiling, brackets it with
@@ -139,7 +147,7 @@ static void build_tree(LqTree &t, int P, int R) {
     t.off[t.nlev] = off;
     off += cnt;
     t.nlev++;
-    if (cnt <= R || t.nlev == LQ_MAXLEV) break;
+    if (cnt == 1 || t.nlev == LQ_MAXLEV) break;
     cnt = (cnt + R - 1) / R;
   }
   t.nel = off;
@@ -354,6 +362,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_alloc(h, &d.segPsi, SB * PM * nx * nx));
   TRY(dev_alloc(h, &d.segVb, SB * PF * nx * nx));
   TRY(dev_alloc(h, &d.V0f, SB * nx * nx));
+  TRY(dev_alloc(h, &d.Vext, (size_t)nx * nx));
+  TRY(dev_alloc(h, &d.xstart, (size_t)nx));
   TRY(dev_alloc(h, &d.status, 1));
   TRY(dev_alloc(h, &d.dbg, 16));
   TRY(dev_alloc(h, &d.g, SB * d.N));
@@ -410,6 +420,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_>, h->smem_k3));
 #define SET_B(NX_)                                                             \
   TRY(set_smem((const void *)elem_scan_kernel<NX_>, h->smem_k2));             \
+  TRY(set_smem((const void *)range_scan_factor_kernel<NX_>, h->smem_k2));     \
   TRY(set_smem((const void *)elem_compose_kernel<NX_>, h->smem_cmp));         \
   TRY(set_smem((const void *)psi_compose_kernel<NX_>, h->smem_psi));
   LQ_DISPATCH_NXNU(nx, nu, SET_A);
@@ -517,7 +528,15 @@ static int launch_eq_factor(hqpcu_handle *h) {
   return HQPCU_OK;
 }
 
-static int launch_factor(hqpcu_handle *h) {
+#define L_K1(NX_, NU_) LAUNCH(h, (seg_element_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k1, s>>>(d))
+#define L_K3(NX_, NU_) LAUNCH(h, (seg_riccati_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k3, s>>>(d))
+#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, 128, h->smem_cmp, s>>>(d, l))
+#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), 128, h->smem_k2, s>>>(d, h->ftop(), 1))
+#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, 128, h->smem_k2, s>>>(d, l, 0))
+#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, 128, h->smem_psi, s>>>(d, l))
+
+// factor, part 1: bound diagonal, segment elements, tree up-sweep
+static int launch_factor_up(hqpcu_handle *h) {
   const LqDev &d = h->d;
   cudaStream_t s = h->stream;
   CU(cudaMemsetAsync(d.status, 0, sizeof(int), s));
@@ -527,40 +546,55 @@ static int launch_factor(hqpcu_handle *h) {
     const int blocks = (int)std::min<size_t>((tot + 255) / 256, 148 * 8);
     LAUNCH(h, hdiag_kernel, <<<blocks, 256, 0, s>>>(d));
   }
-#define L_K1(NX_, NU_) LAUNCH(h, (seg_element_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k1, s>>>(d))
-#define L_K3(NX_, NU_) LAUNCH(h, (seg_riccati_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k3, s>>>(d))
-#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, 128, h->smem_cmp, s>>>(d, l))
-#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), 128, h->smem_k2, s>>>(d, d.ft.nlev - 1, 1))
-#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, 128, h->smem_k2, s>>>(d, l, 0))
-#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, 128, h->smem_psi, s>>>(d, l))
-  if (d.P > 1) {
+  if (d.P > 1 || h->ranged()) {
     LQ_DISPATCH_NXNU(d.nx, d.nu, L_K1);
-    for (int l = 0; l + 1 < d.ft.nlev; l++) {
+    for (int l = 0; l < h->ftop(); l++) {
       const dim3 gl(d.ft.cnt[l + 1], d.batch);
       LQ_DISPATCH_NX(d.nx, d.nu, L_CMP);
     }
   }
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+// factor, part 2: value Hessians back down the tree, Riccati inside segments
+static int launch_factor_down(hqpcu_handle *h) {
+  const LqDev &d = h->d;
+  cudaStream_t s = h->stream;
+  const dim3 gseg(d.P, d.batch);
   LQ_DISPATCH_NX(d.nx, d.nu, L_TOP);
-  for (int l = d.ft.nlev - 2; l >= 0; l--) {
+  for (int l = h->ftop() - 1; l >= 0; l--) {
     const dim3 gl(d.ft.cnt[l + 1], d.batch);
     LQ_DISPATCH_NX(d.nx, d.nu, L_DWN);
   }
   LQ_DISPATCH_NXNU(d.nx, d.nu, L_K3);
-  for (int l = 0; l + 1 < d.st.nlev; l++) {
+  for (int l = 0; l < h->stop(); l++) {
     const dim3 gl(d.st.cnt[l + 1], d.batch);
     LQ_DISPATCH_NX(d.nx, d.nu, L_PSI);
   }
+  if (!d.fixed_x0 && !d.has_prev)
+    LAUNCH(h, x0_factor_kernel,
+           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
+  CU(cudaGetLastError());
+  h->factored = true;
+  return HQPCU_OK;
+}
 #undef L_K1
 #undef L_K3
 #undef L_CMP
 #undef L_TOP
 #undef L_DWN
 #undef L_PSI
-  if (!d.fixed_x0)
-    LAUNCH(h, x0_factor_kernel,
-           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
-  CU(cudaGetLastError());
-  h->factored = true;
+
+static int launch_factor(hqpcu_handle *h) {
+  if (h->ranged()) {
+    g_err = "this handle is a stage range of a split horizon: use hqpcu_range_*";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  int rc = launch_factor_up(h);
+  if (rc) return rc;
+  rc = launch_factor_down(h);
+  if (rc) return rc;
   if (h->q.n_eq) return launch_eq_factor(h);
   return HQPCU_OK;
 }
@@ -629,40 +663,78 @@ int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
 }
 
 // -------------------------------------------------------------------- step --
-static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
-                            const double *r3, const double *r4, double *dx, double *dy,
-                            double *dz, double *dw) {
+// solve, part 1: stage-parallel prologue, zero-boundary backward chains, up-sweep
+static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                         const double *r4) {
   const LqDev &d = h->d;
   if (!h->factored) {
     g_err = "step before factor";
     return HQPCU_E_NULL;
   }
-  const dim3 gall(d.K + 1, d.batch), gk(d.K, d.batch), gseg(d.P, d.batch);
+  const dim3 gall(d.K + 1, d.batch), gseg(d.P, d.batch);
   const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
   LAUNCH(h, solve_pre_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4));
-  // backward: segment chains, hierarchy up / top / down, segment chains again
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 0));
-  for (int l = 0; l + 1 < d.st.nlev; l++)
+  for (int l = 0; l < h->stop(); l++)
     LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
-  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, sc, s>>>(d, d.st.nlev - 1, 1, r2));
-  for (int l = d.st.nlev - 2; l >= 0; l--)
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+// solve, part 2: backward boundary values down the tree, true backward chains,
+// stage-parallel middle pass, zero-boundary forward chains, up-sweep
+static int launch_step_b(hqpcu_handle *h, const double *r2) {
+  const LqDev &d = h->d;
+  const dim3 gk(d.K, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const size_t sc = h->smem_chain;
+  const int tc = h->thr_chain;
+  cudaStream_t s = h->stream;
+  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, sc, s>>>(d, h->stop(), 1, r2));
+  for (int l = h->stop() - 1; l >= 0; l--)
     LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_mid_kernel, <<<gk, h->thr_stage, sv, s>>>(d, r2));
-  // forward
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 0));
-  for (int l = 0; l + 1 < d.st.nlev; l++)
+  for (int l = 0; l < h->stop(); l++)
     LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
-  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, sc, s>>>(d, d.st.nlev - 1, 1, r2));
-  for (int l = d.st.nlev - 2; l >= 0; l--)
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+// solve, part 3: forward boundary values down the tree, true forward chains,
+// stage-parallel epilogue
+static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, const double *r4,
+                         double *dx, double *dy, double *dz, double *dw) {
+  const LqDev &d = h->d;
+  const dim3 gall(d.K + 1, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const size_t sc = h->smem_chain;
+  const int tc = h->thr_chain;
+  cudaStream_t s = h->stream;
+  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, sc, s>>>(d, h->stop(), 1, r2));
+  for (int l = h->stop() - 1; l >= 0; l--)
     LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_post_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
+}
+
+static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
+                            const double *r3, const double *r4, double *dx, double *dy,
+                            double *dz, double *dw) {
+  if (h->ranged()) {
+    g_err = "this handle is a stage range of a split horizon: use hqpcu_range_*";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  int rc = launch_step_a(h, r1, r2, r3, r4);
+  if (!rc) rc = launch_step_b(h, r2);
+  if (!rc) rc = launch_step_c(h, r2, r3, r4, dx, dy, dz, dw);
+  return rc;
 }
 
 static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
@@ -832,6 +904,94 @@ int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
                   h->u_dw, res, nsteps);
   if (rc) return rc;
   return d2h_sol(h, dx, dy, dz, dw);
+}
+
+// ------------------------------------------------------ horizon split (8e) --
+int hqpcu_range_config(hqpcu_handle *h, int has_prev, int has_next) {
+  if (!h) return HQPCU_E_NULL;
+  if (h->d.batch != 1 || h->q.n_eq) {
+    g_err = "hqpcu_range_config: batch == 1 and no general equality rows";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  if (has_prev && h->d.fixed_x0) {
+    g_err = "hqpcu_range_config: only the first range may fix x0";
+    return HQPCU_E_SIZES;
+  }
+  h->d.has_prev = has_prev ? 1 : 0;
+  h->d.has_next = has_next ? 1 : 0;
+  h->factored = false;
+  return HQPCU_OK;
+}
+
+int hqpcu_range_factor_begin(hqpcu_handle *h, const double *z, const double *w, double *xf) {
+  if (!h || !xf) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  CU(cudaSetDevice(h->device));
+  if (d.m) {
+    const size_t bytes = (size_t)d.m * sizeof(double);
+    CU(cudaMemcpyAsync(h->z, z, bytes, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->w, w, bytes, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  int rc = launch_factor_up(h);
+  if (rc) return rc;
+  LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(d, xf));
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank, int world,
+                              double *xpsi) {
+  if (!h || !gathered || !xpsi) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+#define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, 128, h->smem_k2, s>>>(d, gathered, rank, world))
+  LQ_DISPATCH_NX(d.nx, d.nu, L_RS);
+#undef L_RS
+  int rc = launch_factor_down(h);
+  if (rc) return rc;
+  const size_t n2 = (size_t)d.nx * d.nx;
+  CU(cudaMemcpyAsync(xpsi, d.segPsi + (size_t)d.st.off[d.st.nlev - 1] * n2, n2 * sizeof(double),
+                     cudaMemcpyDeviceToDevice, s));
+  return HQPCU_OK;
+}
+
+int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
+                           const double *r3, const double *r4, double *xv) {
+  if (!h || !r1 || !r2 || !xv) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  h->rg_r1 = r1; h->rg_r2 = r2; h->rg_r3 = r3; h->rg_r4 = r4;
+  int rc = launch_step_a(h, r1, r2, r3, r4);
+  if (rc) return rc;
+  LAUNCH(h, range_export_vec_kernel<true>,
+         <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, r2, xv));
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, int rank,
+                         int world, double *xx) {
+  if (!h || !gv || !gpsi || !xx) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
+  const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
+  LAUNCH(h, range_scan_vec_kernel<true>, <<<1, thr, sm, h->stream>>>(h->d, gv, gpsi, rank, world));
+  int rc = launch_step_b(h, h->rg_r2);
+  if (rc) return rc;
+  LAUNCH(h, range_export_vec_kernel<false>,
+         <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, h->rg_r2, xx));
+  CU(cudaGetLastError());
+  return HQPCU_OK;
+}
+
+int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gpsi, int rank,
+                            int world, double *dx, double *dy, double *dz, double *dw) {
+  if (!h || !gx || !gpsi || !dx || !dy) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
+  const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
+  LAUNCH(h, range_scan_vec_kernel<false>, <<<1, thr, sm, h->stream>>>(h->d, gx, gpsi, rank, world));
+  return launch_step_c(h, h->rg_r2, h->rg_r3, h->rg_r4, dx, dy, dz, dw);
 }
 
 int hqpcu_profile(hqpcu_handle *h, int on) {

@@ -32,6 +32,12 @@ struct LqDev {
   int m, nnz;         // inequality rows / nonzeros per instance
   int N, me;          // per-instance vector lengths
   int use_tma;        // per-stage slabs are 16-byte multiples: bulk-copy path
+  // horizon split across ranks (lq_range.cuh): this handle owns a contiguous
+  // stage range of a longer horizon
+  int has_prev;       // a rank before this one supplies the state at stage 0
+  int has_next;       // a rank behind this one supplies the terminal value
+  double *Vext;       // [nx*nx] value Hessian handed over from the ranks behind
+  double *xstart;     // [nx]    state at stage 0 handed over from the ranks before
   // inequality structure (shared by all instances)
   const int *ineq_stage, *ineq_ptr, *ineq_lcol;
   const int *srow_ptr;  // [K+2] rows sorted by stage

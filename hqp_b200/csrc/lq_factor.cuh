@@ -404,6 +404,9 @@ __global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int to
       }
     }
     __syncthreads();
+    if (d.has_next)  // horizon split: value of everything behind this range
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) S[i] += d.Vext[i];
+    __syncthreads();
     double *VK = d.V + ((size_t)b * (d.K + 1) + d.K) * n2;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) VK[i] = S[i];
   } else {

@@ -238,6 +238,9 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
     c1 = d.st.cnt[lev];
     if (BACK) {
       if (i < nx) t = d.v[((size_t)b * (d.K + 1) + d.K) * nx + i];
+    } else if (d.has_prev) {
+      // horizon split: the state at stage 0 comes from the ranks before
+      if (i < nx) t = d.xstart[i];
     } else if (d.fixed_x0) {
       // x_0 = -a_0 (hqp/Hqp_IpLQDOCP.C:2099-2100)
       if (i < nx) t = -r2[(size_t)b * d.me + (size_t)d.K * nx + i];

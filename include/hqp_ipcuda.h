@@ -135,6 +135,32 @@ int hqpcu_solve_dev(hqpcu_handle *h, double eps, const double *r1,
                     double *dx, double *dy, double *dz, double *dw,
                     double *res /* host */, int *nsteps);
 
+/* --- horizon split across GPUs.  The handle owns a contiguous
+ *     stage range of a longer horizon (created with the LOCAL K; a range that is
+ *     followed by another passes a zero terminal block and no rows at stage K;
+ *     a range that is preceded by another has fixed_x0 = 0 and no x0 rows).
+ *     All pointers are DEVICE pointers; the caller performs the all-gathers
+ *     (NCCL) between the phases:
+ *       factor_begin  -> xf [4*nx*nx]  : (A, C, J) of the range, terminal block
+ *         all-gather xf  -> gathered [world][4*nx*nx]
+ *       factor_finish -> xpsi [nx*nx]  : transition of the range
+ *         all-gather xpsi -> gpsi [world][nx*nx]          (once per factor)
+ *       step_begin    -> xv [2*nx]     : (v0, v_term)
+ *         all-gather xv  -> gv [world][2*nx]
+ *       step_mid      -> xx [2*nx]     : (x0, x_start)
+ *         all-gather xx  -> gx [world][2*nx]
+ *       step_finish   -> dx, dy, dz, dw of the range                          */
+int hqpcu_range_config(hqpcu_handle *h, int has_prev, int has_next);
+int hqpcu_range_factor_begin(hqpcu_handle *h, const double *z, const double *w, double *xf);
+int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank, int world,
+                              double *xpsi);
+int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
+                           const double *r3, const double *r4, double *xv);
+int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, int rank,
+                         int world, double *xx);
+int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gpsi, int rank,
+                            int world, double *dx, double *dy, double *dz, double *dw);
+
 /* --- device-resident interior-point solve: Hqp_IpsMehrotra::cold_start + ::solve
  *     (hqp/Hqp_IpsMehrotra.C:209-327, 355-733; predictor-corrector with Terlaky's
  *     safeguard, qp_init_method 0) of
