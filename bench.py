@@ -190,48 +190,92 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=dev)
     nx, nu, K, batch = wl["nx"], wl["nu"], wl["K"], wl["batch"]
 
-    # one horizon (or one batch of instances) per GPU: weak scaling
-    p = synth_lqdocp(nx, nu, K, seed=1234 + rank)
-    z, w, r1, r2, r3, r4 = synth_rhs(p, seed=4321 + rank)
-    eng = IpCuda(p, batch=batch, device=local, nseg=args.nseg)
-    stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
+    N1 = 0  # bytes bookkeeping below
+    if world == 1:
+        # one horizon (or one batch of instances) on the GPU
+        p = synth_lqdocp(nx, nu, K, seed=1234)
+        z, w, r1, r2, r3, r4 = synth_rhs(p, seed=4321)
+        eng = IpCuda(p, batch=batch, device=local, nseg=args.nseg)
+        stream = torch.cuda.current_stream()
+        eng.set_stream(stream.cuda_stream)
 
-    def rep(a):
-        return np.ascontiguousarray(np.tile(a, batch)) if batch > 1 else a
+        def rep(a):
+            return np.ascontiguousarray(np.tile(a, batch)) if batch > 1 else a
 
-    if batch > 1:
-        eng.update(Q=np.broadcast_to(p.Q, (batch,) + p.Q.shape),
-                   fx=np.broadcast_to(p.fx, (batch,) + p.fx.shape),
-                   fu=np.broadcast_to(p.fu, (batch,) + p.fu.shape),
-                   ineq_val=np.broadcast_to(p.ineq_val, (batch,) + p.ineq_val.shape))
+        if batch > 1:
+            eng.update(Q=np.broadcast_to(p.Q, (batch,) + p.Q.shape),
+                       fx=np.broadcast_to(p.fx, (batch,) + p.fx.shape),
+                       fu=np.broadcast_to(p.fu, (batch,) + p.fu.shape),
+                       ineq_val=np.broadcast_to(p.ineq_val, (batch,) + p.ineq_val.shape))
+            update_ms = None
+        else:
+            t0 = time.perf_counter()
+            eng.update()
+            update_ms = 1e3 * (time.perf_counter() - t0)
+        host = [rep(a) for a in (z, w, r1, r2, r3, r4)]
+        lp = p
+        parallelism = "single"
     else:
+        # horizon split: ONE horizon of world*K stages, contiguous
+        # stage ranges per rank, boundary elements exchanged with all-gathers
+        if batch != 1:
+            raise RuntimeError("--gpus N > 1 is the horizon split of a single instance")
+        from hqp_b200.dist import CudaRangeEngine, RangeSolver, local_vectors, split_problem
+        pg = synth_lqdocp(nx, nu, K * world, seed=1234)
+        gvec = synth_rhs(pg, seed=4321)
+        lp, rm = split_problem(pg, world)[rank]
+        host = [np.ascontiguousarray(a) for a in local_vectors(pg, rm, *gvec)]
+        del pg, gvec
+        stream = torch.cuda.current_stream()
         t0 = time.perf_counter()
-        eng.update()
+        reng = CudaRangeEngine(lp, rm, device=local, nseg=args.nseg)
         update_ms = 1e3 * (time.perf_counter() - t0)
-    host = [rep(a) for a in (z, w, r1, r2, r3, r4)]
-    pinned = [torch.from_numpy(a).pin_memory() for a in host]
+        eng = reng.eng
+        solver = RangeSolver(reng, rank, world)
+        p = lp
+        parallelism = f"horizon split, {world} contiguous stage ranges, 2 all-gathers per factor + 2 per step"
+    pinned = [torch.from_numpy(np.array(a)).pin_memory() for a in host]
     dvec = [t.to(dev) for t in pinned]
-    N, me, m = p.N * batch, p.me * batch, p.m * batch
+    N, me, m = lp.N * batch, lp.me * batch, lp.m * batch
     outs = [torch.empty(n, dtype=torch.float64, device=dev) for n in (N, me, max(m, 1), max(m, 1))]
     hout = [torch.empty(n, dtype=torch.float64).pin_memory() for n in (N, me, max(m, 1), max(m, 1))]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    def unit_dev():
-        eng.factor_dev(dvec[0].data_ptr(), dvec[1].data_ptr())
-        for _ in range(2):
-            eng.step_dev(*[t.data_ptr() for t in dvec[2:]], *[t.data_ptr() for t in outs])
 
     hp = [t.numpy() for t in pinned]
     ho = [t.numpy() for t in hout]
     from hqp_b200 import ipcuda as _ic
     L = _ic.lib()
 
-    def unit_host():
-        _ic._check(L.hqpcu_factor(eng.h, _ic._hp(hp[0]), _ic._hp(hp[1])), "factor")
-        for _ in range(2):
-            _ic._check(L.hqpcu_step(eng.h, *[_ic._hp(a) for a in hp[2:]],
-                                    *[_ic._hp(a) for a in ho]), "step")
+    if world == 1:
+        def unit_dev():
+            eng.factor_dev(dvec[0].data_ptr(), dvec[1].data_ptr())
+            for _ in range(2):
+                eng.step_dev(*[t.data_ptr() for t in dvec[2:]], *[t.data_ptr() for t in outs])
+
+        def unit_host():
+            _ic._check(L.hqpcu_factor(eng.h, _ic._hp(hp[0]), _ic._hp(hp[1])), "factor")
+            for _ in range(2):
+                _ic._check(L.hqpcu_step(eng.h, *[_ic._hp(a) for a in hp[2:]],
+                                        *[_ic._hp(a) for a in ho]), "step")
+    else:
+        def unit_dev():
+            solver.factor(dvec[0], dvec[1])
+            for _ in range(2):
+                solver.step(*dvec[2:])
+
+        def unit_host():
+            # host buffers in, host buffers out: pinned H2D of (z,w), then per step
+            # H2D of r1..r4 and D2H of dx..dw around the same range calls
+            dvec[0].copy_(pinned[0], non_blocking=True)
+            dvec[1].copy_(pinned[1], non_blocking=True)
+            solver.factor(dvec[0], dvec[1])
+            for _ in range(2):
+                for dt, ht in zip(dvec[2:], pinned[2:]):
+                    dt.copy_(ht, non_blocking=True)
+                res = solver.step(*dvec[2:])
+                for ht, dt in zip(hout, res):
+                    ht[:dt.numel()].copy_(dt, non_blocking=True)
+            torch.cuda.synchronize()
 
     def barrier():
         if world > 1:
@@ -288,6 +332,9 @@ def run_ours(args, wl):
     ms_step, e2e_s = float(tmax[0]), float(tmax[1])
     stages = K * batch * world
     value = stages / (ms_step * 1e-3)
+    bytes_in = 8 * sum(int(np.prod(a.shape)) for a in host[:2]) + \
+        2 * 8 * sum(int(np.prod(a.shape)) for a in host[2:])
+    bytes_out = 2 * 8 * (N + me + 2 * m)
 
     if rank == 0:
         mc = p.m / K
@@ -311,23 +358,24 @@ def run_ours(args, wl):
                     "factor_frac_of_hbm": K * batch * bf / (t_factor * 1e-3) / 1e9 / peak,
                     "step_frac_of_hbm": K * batch * bs / (t_solve * 1e-3) / 1e9 / peak}
         cap = 10000 if batch == 1 else K
-        cb = time_reference(wl, 3, 1, max_stages=cap)
-        h2d = 8 * (2 * m + 2 * (N + me + 2 * m))
-        d2h = 8 * 2 * (N + me + 2 * m)
+        # reference CPU path on the host cores: rank 0, N = 1 only
+        cb = time_reference(wl, 3, 1, max_stages=cap) if world == 1 else None
+        h2d, d2h = bytes_in * world, bytes_out * world  # whole job
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": wl["name"], "unit_of_work": "1 factor + 2 step",
                            "stages_per_gpu": K * batch, "segments_per_instance": eng.nseg,
-                           "parallelism": "replicas" if world > 1 else "single",
+                           "parallelism": parallelism,
                            "l2": "flushed (256 MiB write) between timed iterations"},
                 "roofline": roofline,
-                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                                 if cb else None),
                 "e2e": {"value": stages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
                 "gpu_launches": int(gpu_launches), "clocks": clocks}
-        if batch == 1:
+        if update_ms is not None:
             line["config"]["update_ms_once_per_sqp_iteration"] = update_ms
         print(json.dumps(line), flush=True)
     eng.close()
