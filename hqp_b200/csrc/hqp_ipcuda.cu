@@ -671,12 +671,12 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
     g_err = "step before factor";
     return HQPCU_E_NULL;
   }
-  const dim3 gall(d.K + 1, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const dim3 gall((d.K + 1 + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_pre_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r1, r2, r3, r4));
+  LAUNCH(h, solve_pre_kernel, <<<gall, 128, sv, s>>>(d, r1, r2, r3, r4));
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 0));
   for (int l = 0; l < h->stop(); l++)
     LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
@@ -688,8 +688,8 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
 // stage-parallel middle pass, zero-boundary forward chains, up-sweep
 static int launch_step_b(hqpcu_handle *h, const double *r2) {
   const LqDev &d = h->d;
-  const dim3 gk(d.K, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const dim3 gk((d.K + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)LQ_WPB * (d.nx + d.nu) * sizeof(double);
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
@@ -697,7 +697,7 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   for (int l = h->stop() - 1; l >= 0; l--)
     LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 1));
-  LAUNCH(h, solve_mid_kernel, <<<gk, h->thr_stage, sv, s>>>(d, r2));
+  LAUNCH(h, solve_mid_kernel, <<<gk, 128, sv, s>>>(d, r2));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 0));
   for (int l = 0; l < h->stop(); l++)
     LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
@@ -710,8 +710,8 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
 static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, const double *r4,
                          double *dx, double *dy, double *dz, double *dw) {
   const LqDev &d = h->d;
-  const dim3 gall(d.K + 1, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)(d.nm + d.nx + 2 + d.nu * d.nu + d.nx * d.nu + 2) * sizeof(double);
+  const dim3 gall((d.K + 1 + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
+  const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
@@ -719,7 +719,7 @@ static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, co
   for (int l = h->stop() - 1; l >= 0; l--)
     LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
-  LAUNCH(h, solve_post_kernel, <<<gall, h->thr_stage, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
+  LAUNCH(h, solve_post_kernel, <<<gall, 128, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
 }

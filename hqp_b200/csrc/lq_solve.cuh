@@ -121,50 +121,67 @@ __device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw) {
   return cs;
 }
 
+// Stage-parallel passes run one WARP per stage (no CTA barriers, coalesced
+// column-wise reads of the stage blocks) and several stages per warp, so that a
+// pass is a few hundred fat CTAs instead of K tiny ones (CTA launch rate, not
+// bandwidth, limited the one-CTA-per-stage version).
+#define LQ_SPW 1                       // stages per warp
+#define LQ_WPB 4                       // warps per CTA
+#define LQ_SPB (LQ_SPW * LQ_WPB)       // stages per CTA
+
+__device__ __forceinline__ int stage_pass_blocks(int nstages) {
+  return (nstages + LQ_SPB - 1) / LQ_SPB;
+}
+
 // ---- pre ------------------------------------------------------------------
-// grid (K+1, batch), block >= nm threads
-__global__ void solve_pre_kernel(LqDev d, const double *__restrict__ r1,
-                                 const double *__restrict__ r2, const double *__restrict__ r3,
-                                 const double *__restrict__ r4) {
+// grid (ceil((K+1)/LQ_SPB), batch), block 128; smem: LQ_WPB * (nm + nx) doubles
+__global__ void __launch_bounds__(128) solve_pre_kernel(
+    LqDev d, const double *__restrict__ r1, const double *__restrict__ r2,
+    const double *__restrict__ r3, const double *__restrict__ r4) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *gk = reinterpret_cast<double *>(smem_raw);  // nm
-  double *fk = gk + d.nm;                              // nx
   const int nx = d.nx, nu = d.nu, nm = d.nm;
-  const int k = blockIdx.x, b = blockIdx.y;
-  const int dk = (k < d.K) ? nm : nx;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *gk = reinterpret_cast<double *>(smem_raw) + warp * (nm + nx);  // nm
+  double *fk = gk + nm;                                                   // nx
+  const int b = blockIdx.y;
   const double *z = d.z + (size_t)b * d.m, *w = d.w + (size_t)b * d.m;
   const double *cv = d.cval + (size_t)b * d.nnz;
   const double *r3b = r3 + (size_t)b * d.m, *r4b = r4 + (size_t)b * d.m;
-  const size_t xo = (size_t)b * d.N + (size_t)k * nm;
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) {
-    double s = -r1[xo + i];
-    const int gv = k * nm + i;
-    for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++) {
-      const int r = d.vcol_row[e];
-      s = fma(cv[d.vcol_nz[e]], (z[r] * r3b[r] + r4b[r]) / w[r], s);
+  for (int s = 0; s < LQ_SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+    if (k > d.K) break;
+    const int dk = (k < d.K) ? nm : nx;
+    const size_t xo = (size_t)b * d.N + (size_t)k * nm;
+    for (int i = lane; i < dk; i += 32) {
+      double a = -r1[xo + i];
+      const int gv = k * nm + i;
+      for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++) {
+        const int r = d.vcol_row[e];
+        a = fma(cv[d.vcol_nz[e]], (z[r] * r3b[r] + r4b[r]) / w[r], a);
+      }
+      gk[i] = a;
+      d.g[xo + i] = a;
     }
-    gk[i] = s;
-    d.g[xo + i] = s;
-  }
-  if (k < d.K)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x)
-      fk[i] = r2[(size_t)b * d.me + (size_t)k * nx + i];
-  __syncthreads();
-  if (k == d.K) {
-    for (int i = threadIdx.x; i < nx; i += blockDim.x)
-      d.v[((size_t)b * (d.K + 1) + k) * nx + i] = gk[i];
-    return;
-  }
-  const size_t ks = (size_t)b * d.K + k;
-  const double *Rux = d.Rux + ks * nu * nx;
-  const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-    double s = gk[i];
-    for (int l = 0; l < nu; l++) s = fma(-Rux[l * nx + i], gk[nx + l], s);
-    d.wv[ks * nx + i] = s;
-    double t = 0.0;
-    for (int l = 0; l < nx; l++) t = fma(Vp[l * nx + i], fk[l], t);  // Vxx symmetric
-    d.q[ks * nx + i] = t;
+    if (k < d.K)
+      for (int i = lane; i < nx; i += 32) fk[i] = r2[(size_t)b * d.me + (size_t)k * nx + i];
+    __syncwarp();
+    if (k == d.K) {
+      for (int i = lane; i < nx; i += 32) d.v[((size_t)b * (d.K + 1) + k) * nx + i] = gk[i];
+    } else {
+      const size_t ks = (size_t)b * d.K + k;
+      const double *Rux = d.Rux + ks * nu * nx;
+      const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
+      for (int i = lane; i < nx; i += 32) {
+        double a0 = gk[i], a1 = 0.0;
+#pragma unroll 10
+        for (int l = 0; l < nu; l++) a0 = fma(-Rux[l * nx + i], gk[nx + l], a0);
+#pragma unroll 10
+        for (int l = 0; l < nx; l++) a1 = fma(Vp[l * nx + i], fk[l], a1);  // Vxx symmetric
+        d.wv[ks * nx + i] = a0;
+        d.q[ks * nx + i] = a1;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -265,105 +282,136 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
   if (phase == 0 && i < nx && part == 0) in0[(pb + g) * nx + i] = t;
 }
 
+// warp-cooperative solve of (L D L') y = b, y in shared memory (m <= 32 per pass
+// of 32 lanes; larger m loops).  LD row-major in GLOBAL memory (ld = m): the
+// column sweeps read it once, coalesced per column pair.
+__device__ __forceinline__ void warp_ldlt_solve_g(const double *__restrict__ LD, int m,
+                                                  double *y, int lane) {
+  // forward: for each column l, rows i > l subtract L[i][l] y[l]
+  for (int l = 0; l < m; l++) {
+    const double yl = y[l];
+    for (int i = l + 1 + lane; i < m; i += 32) y[i] = fma(-LD[i * m + l], yl, y[i]);
+    __syncwarp();
+  }
+  for (int i = lane; i < m; i += 32) y[i] *= LD[i * m + i];
+  __syncwarp();
+  // backward: for each row l (descending), entries i < l subtract L[l][i] y[l]
+  for (int l = m - 1; l > 0; l--) {
+    const double yl = y[l];
+    for (int i = lane; i < l; i += 32) y[i] = fma(-LD[l * m + i], yl, y[i]);
+    __syncwarp();
+  }
+}
+
 // ---- mid -------------------------------------------------------------------
-// grid (K, batch), block >= max(nx,nu) threads
-__global__ void solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
+// grid (ceil(K/LQ_SPB), batch), block 128; smem: LQ_WPB * (nx + nu) doubles
+__global__ void __launch_bounds__(128) solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
-  double *t = reinterpret_cast<double *>(smem_raw);  // nx
-  double *Gu = t + nx;                               // nu
-  double *LDs = Gu + nu;                             // nu*nu
-  double *fus = LDs + nu * nu;                       // nx*nu
-  const int k = blockIdx.x, b = blockIdx.y;
-  const size_t ks = (size_t)b * d.K + k;
-  const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
-  const double *fu = d.fu + ks * nx * nu;
-  const double *LD = d.LD + ks * nu * nu;
-  const double *g = d.g + (size_t)b * d.N + (size_t)k * nm;
-  for (int i = threadIdx.x; i < nx * nu; i += blockDim.x) fus[i] = fu[i];
-  for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) LDs[i] = LD[i];
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) t[i] = vp[i] + d.q[ks * nx + i];
-  __syncthreads();
-  for (int j = threadIdx.x; j < nu; j += blockDim.x) {
-    double s = g[nx + j];
-    for (int l = 0; l < nx; l++) s = fma(fus[l * nu + j], t[l], s);
-    Gu[j] = s;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) thread_ldlt_solve(LDs, nu, nu, Gu, 1);
-  __syncthreads();
-  for (int j = threadIdx.x; j < nu; j += blockDim.x) d.Ru[ks * nu + j] = Gu[j];
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-    double s = r2[(size_t)b * d.me + (size_t)k * nx + i];
-    for (int l = 0; l < nu; l++) s = fma(-fus[i * nu + l], Gu[l], s);
-    d.c[ks * nx + i] = s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *t = reinterpret_cast<double *>(smem_raw) + warp * (nx + nu);  // nx
+  double *Gu = t + nx;                                                   // nu
+  const int b = blockIdx.y;
+  for (int s = 0; s < LQ_SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+    if (k >= d.K) break;
+    const size_t ks = (size_t)b * d.K + k;
+    const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
+    const double *fu = d.fu + ks * nx * nu;
+    const double *g = d.g + (size_t)b * d.N + (size_t)k * nm;
+    for (int i = lane; i < nx; i += 32) t[i] = vp[i] + d.q[ks * nx + i];
+    __syncwarp();
+    for (int j = lane; j < nu; j += 32) {
+      double a = g[nx + j];
+#pragma unroll 10
+      for (int l = 0; l < nx; l++) a = fma(fu[l * nu + j], t[l], a);
+      Gu[j] = a;
+    }
+    __syncwarp();
+    warp_ldlt_solve_g(d.LD + ks * nu * nu, nu, Gu, lane);
+    for (int j = lane; j < nu; j += 32) d.Ru[ks * nu + j] = Gu[j];
+    for (int i = lane; i < nx; i += 32) {
+      double a = r2[(size_t)b * d.me + (size_t)k * nx + i];
+#pragma unroll 10
+      for (int l = 0; l < nu; l++) a = fma(-fu[i * nu + l], Gu[l], a);
+      d.c[ks * nx + i] = a;
+    }
+    __syncwarp();
   }
 }
 
 // ---- post -------------------------------------------------------------------
-// grid (K+1, batch), block >= nm threads
-__global__ void solve_post_kernel(LqDev d, const double *__restrict__ r3,
-                                  const double *__restrict__ r4, double *__restrict__ dx,
-                                  double *__restrict__ dy, double *__restrict__ dz,
-                                  double *__restrict__ dw) {
+// grid (ceil((K+1)/LQ_SPB), batch), block 128; smem: LQ_WPB * (nm + nx) doubles
+__global__ void __launch_bounds__(128) solve_post_kernel(
+    LqDev d, const double *__restrict__ r3, const double *__restrict__ r4,
+    double *__restrict__ dx, double *__restrict__ dy, double *__restrict__ dz,
+    double *__restrict__ dw) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
-  double *xs = reinterpret_cast<double *>(smem_raw);  // nm : dx of this stage
-  double *xn = xs + nm;                                // nx : x[k+1]
-  double *Rs = xn + nx;                                // nu*nx : Rux of this stage
-  const int k = blockIdx.x, b = blockIdx.y;
-  const double *xk = d.x + ((size_t)b * (d.K + 1) + k) * nx;
-  const size_t ks = (size_t)b * d.K + k;
-  for (int i = threadIdx.x; i < nx; i += blockDim.x) xs[i] = xk[i];
-  if (k < d.K) {
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) xn[i] = xk[nx + i];
-    const double *Rux = d.Rux + ks * nu * nx;
-    for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) Rs[i] = Rux[i];
-  }
-  __syncthreads();
-  if (k < d.K) {
-    for (int j = threadIdx.x; j < nu; j += blockDim.x) {
-      double s = d.Ru[ks * nu + j];
-      for (int l = 0; l < nx; l++) s = fma(Rs[j * nx + l], xs[l], s);
-      xs[nx + j] = -s;  // u_k
-    }
-    // p_k = Vxx[k+1] x[k+1] + v[k+1]   (:2169-2171)
-    const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
-    const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = vp[i];
-      for (int l = 0; l < nx; l++) s = fma(Vp[l * nx + i], xn[l], s);
-      dy[(size_t)b * d.me + (size_t)k * nx + i] = s;
-    }
-  }
-  if (k == 0 && d.fixed_x0) {  // y_0 = -(Vx[0] + Vxx[0] x_0)   (:2153-2159)
-    const double *V0 = d.V + (size_t)b * (d.K + 1) * nx * nx;
-    const double *v0 = d.v + (size_t)b * (d.K + 1) * nx;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = v0[i];
-      for (int l = 0; l < nx; l++) s = fma(V0[l * nx + i], xs[l], s);
-      dy[(size_t)b * d.me + (size_t)d.K * nx + i] = -s;
-    }
-  }
-  __syncthreads();
-  const int dk = (k < d.K) ? nm : nx;
-  // dx = -[x;u]   (:952)
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) {
-    xs[i] = -xs[i];
-    dx[(size_t)b * d.N + (size_t)k * nm + i] = xs[i];
-  }
-  __syncthreads();
-  // dw = C dx - r3 ; dz = (r4 - z dw)/w   (:955-960)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *xs = reinterpret_cast<double *>(smem_raw) + warp * (nm + nx);  // nm: [x_k ; u_k] -> dx
+  double *xn = xs + nm;                                                   // nx: x_{k+1}
+  const int b = blockIdx.y;
   const double *cv = d.cval + (size_t)b * d.nnz;
-  for (int rr = d.srow_ptr[k] + threadIdx.x; rr < d.srow_ptr[k + 1]; rr += blockDim.x) {
-    const int r = d.srow[rr];
-    double s = 0.0;
-    for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
-      s = fma(cv[e], xs[d.ineq_lcol[e]], s);
-    const size_t ro = (size_t)b * d.m + r;
-    const double dwr = s - r3[ro];
-    dw[ro] = dwr;
-    dz[ro] = (r4[ro] - d.z[ro] * dwr) / d.w[ro];
+  for (int s = 0; s < LQ_SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+    if (k > d.K) break;
+    const double *xk = d.x + ((size_t)b * (d.K + 1) + k) * nx;
+    const size_t ks = (size_t)b * d.K + k;
+    for (int i = lane; i < nx; i += 32) {
+      xs[i] = xk[i];
+      if (k < d.K) xn[i] = xk[nx + i];
+    }
+    __syncwarp();
+    if (k < d.K) {
+      const double *Rux = d.Rux + ks * nu * nx;
+      for (int j = lane; j < nu; j += 32) {
+        double a = d.Ru[ks * nu + j];
+#pragma unroll 10
+        for (int l = 0; l < nx; l++) a = fma(Rux[j * nx + l], xs[l], a);
+        xs[nx + j] = -a;  // u_k
+      }
+      // p_k = Vxx[k+1] x[k+1] + v[k+1]   (:2169-2171)
+      const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
+      const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
+      for (int i = lane; i < nx; i += 32) {
+        double a = vp[i];
+#pragma unroll 10
+        for (int l = 0; l < nx; l++) a = fma(Vp[l * nx + i], xn[l], a);
+        dy[(size_t)b * d.me + (size_t)k * nx + i] = a;
+      }
+    }
+    if (k == 0 && d.fixed_x0) {  // y_0 = -(Vx[0] + Vxx[0] x_0)   (:2153-2159)
+      const double *V0 = d.V + (size_t)b * (d.K + 1) * nx * nx;
+      const double *v0 = d.v + (size_t)b * (d.K + 1) * nx;
+      for (int i = lane; i < nx; i += 32) {
+        double a = v0[i];
+#pragma unroll 10
+        for (int l = 0; l < nx; l++) a = fma(V0[l * nx + i], xs[l], a);
+        dy[(size_t)b * d.me + (size_t)d.K * nx + i] = -a;
+      }
+    }
+    __syncwarp();
+    const int dk = (k < d.K) ? nm : nx;
+    // dx = -[x;u]   (:952)
+    for (int i = lane; i < dk; i += 32) {
+      const double a = -xs[i];
+      xs[i] = a;
+      dx[(size_t)b * d.N + (size_t)k * nm + i] = a;
+    }
+    __syncwarp();
+    // dw = C dx - r3 ; dz = (r4 - z dw)/w   (:955-960)
+    for (int rr = d.srow_ptr[k] + lane; rr < d.srow_ptr[k + 1]; rr += 32) {
+      const int r = d.srow[rr];
+      double a = 0.0;
+      for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
+        a = fma(cv[e], xs[d.ineq_lcol[e]], a);
+      const size_t ro = (size_t)b * d.m + r;
+      const double dwr = a - r3[ro];
+      dw[ro] = dwr;
+      dz[ro] = (r4[ro] - d.z[ro] * dwr) / d.w[ro];
+    }
+    __syncwarp();
   }
 }
 
