@@ -178,6 +178,100 @@ __device__ __forceinline__ void cta_mm(double *C, int ldc, const double *C0, int
          blockDim.x);
 }
 
+// ---------------------------------------------------------------------------
+// Same product on the FP64 tensor cores: mma.sync.m8n8k4.f64 (SASS: DMMA).
+// One warp owns 8x8 output tiles; per k-step of 4 every lane loads ONE element
+// of A and ONE of B (fragment layout of the PTX ISA: A row = lane/4, col =
+// lane%4; B row = lane%4, col = lane/4; C row = lane/4, cols = 2*(lane%4)+{0,1}),
+// i.e. 2 shared-memory loads per 256 multiply-adds instead of 8 loads per 128
+// with the 2x2 FMA tiles.  ncu showed the FMA version bound by shared-memory
+// wavefronts (74 % LSU) with the FP64 pipe at 14 %, which is the case where the
+// tensor-core path pays even for 20 x 20 blocks (padded to 24): see
+// profiles/r01_ncu_full_factor_v2.md.  Used by the <NX,NU>-templated kernels;
+// sizes/strides are compile-time constants there and the k-loop fully unrolls.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+  asm volatile(
+      "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
+                                          double beta, double alpha, const double *A, int ar,
+                                          int ac, const double *B, int br, int bc, int M, int N,
+                                          int Kd) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = LQ_NT / 32;
+  const int g = lane >> 2, t = lane & 3;
+  const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
+  const int ntiles = TI * TJ;
+  // two tiles in flight per warp: independent accumulator chains
+  for (int tile = warp; tile < ntiles; tile += 2 * nwarps) {
+    const int tile2 = tile + nwarps;
+    const bool has2 = tile2 < ntiles;
+    const int i0 = (tile / TJ) << 3, j0 = (tile % TJ) << 3;
+    const int i1 = has2 ? (tile2 / TJ) << 3 : i0, j1 = has2 ? (tile2 % TJ) << 3 : j0;
+    const bool va0 = i0 + g < M, vb0 = j0 + g < N;
+    const bool va1 = has2 && i1 + g < M, vb1 = has2 && j1 + g < N;
+    const double *a0p = A + (i0 + g) * ar, *b0p = B + (j0 + g) * bc;
+    const double *a1p = A + (i1 + g) * ar, *b1p = B + (j1 + g) * bc;
+    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+    for (int k0 = 0; k0 < Kd; k0 += 4) {
+      const int k = k0 + t;
+      const bool vk = k < Kd;
+      const double a0 = (va0 && vk) ? a0p[k * ac] : 0.0;
+      const double b0 = (vb0 && vk) ? b0p[k * br] : 0.0;
+      const double a1 = (va1 && vk) ? a1p[k * ac] : 0.0;
+      const double b1 = (vb1 && vk) ? b1p[k * br] : 0.0;
+      dmma_m8n8k4(c00, c01, a0, b0);
+      dmma_m8n8k4(c10, c11, a1, b1);
+    }
+    {
+      const int ic = i0 + g, jc = j0 + 2 * t;
+      if (ic < M) {
+        if (jc < N) {
+          double r = alpha * c00;
+          if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
+          C[ic * ldc + jc] = r;
+        }
+        if (jc + 1 < N) {
+          double r = alpha * c01;
+          if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
+          C[ic * ldc + jc + 1] = r;
+        }
+      }
+    }
+    if (has2) {
+      const int ic = i1 + g, jc = j1 + 2 * t;
+      if (ic < M) {
+        if (jc < N) {
+          double r = alpha * c10;
+          if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
+          C[ic * ldc + jc] = r;
+        }
+        if (jc + 1 < N) {
+          double r = alpha * c11;
+          if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
+          C[ic * ldc + jc + 1] = r;
+        }
+      }
+    }
+  }
+}
+
+// compile-time choice between the tensor-core and the FMA product
+template <bool TC>
+__device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
+                                        double beta, double alpha, const double *A, int ar,
+                                        int ac, const double *B, int br, int bc, int M, int N,
+                                        int Kd) {
+  if constexpr (TC)
+    cta_mm_tc(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+  else
+    cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+}
+
 // A <- 0.5 (A + A')  (n x n, lda); one thread per (i<j) pair
 __device__ __forceinline__ void cta_symmetrize(double *A, int lda, int n) {
   const int total = n * n;

@@ -33,6 +33,10 @@
 
 #include "lq_device.cuh"
 
+#ifndef LQ_USE_DMMA
+#define LQ_USE_DMMA 1  // FP64 tensor-core block products in the templated kernels
+#endif
+
 // ---------------------------------------------------------------------------
 // hdiag[b][j] = sum over single-entry rows r of C in column j of (z_r/w_r) c_r^2
 // (the bound rows of Hqp_Docp, hqp/Hqp_Docp.C:658-666).  grid-stride over
@@ -169,7 +173,7 @@ struct ElemAcc {
   double *A, *W, *Y, *Cg;
 };
 
-template <int NU>
+template <int NU, bool TC>
 __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, double *V,
                                               const double *fx, const double *fu, double *G,
                                               double *T, double *Rux, double *Phi, int *st_s,
@@ -178,17 +182,17 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   const int tid = threadIdx.x, nthr = blockDim.x;
   if (!zero_V) {
     // T = V [fx fu]
-    cta_mm(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fx, nx, 1, nx, nx, nx);
-    cta_mm(T + nx, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fu, nu, 1, nx, nu, nx);
+    cta_mmx<TC>(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fx, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(T + nx, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fu, nu, 1, nx, nu, nx);
   }
   if (el)  // W = A fu
-    cta_mm(el->W, nu, nullptr, 0, 0.0, 1.0, el->A, nx, 1, fu, nu, 1, nx, nu, nx);
+    cta_mmx<TC>(el->W, nu, nullptr, 0, 0.0, 1.0, el->A, nx, 1, fu, nu, 1, nx, nu, nx);
   if (!zero_V || el) __syncthreads();
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
-    cta_mm(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, nm, 1, nx, nx, nx);
-    cta_mm(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, nu, T, nm, 1, nu, nx, nx);
-    cta_mm(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, nu, T + nx, nm, 1, nu,
+    cta_mmx<TC>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, nm, 1, nx, nx, nx);
+    cta_mmx<TC>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, nu, T, nm, 1, nu, nx, nx);
+    cta_mmx<TC>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, nu, T + nx, nm, 1, nu,
            nu, nx);
     __syncthreads();
   }
@@ -212,9 +216,9 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   }
   __syncthreads();
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W'
-  cta_mm(V, nx, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, nx, 1, nx, nx, nu);
-  cta_mm(Phi, nx, fx, nx, 1.0, -1.0, fu, nu, 1, Rux, nx, 1, nx, nx, nu);
-  if (el) cta_mm(el->Cg, nx, el->Cg, nx, 1.0, 1.0, el->Y, nu, 1, el->W, 1, nu, nx, nx, nu);
+  cta_mmx<TC>(V, nx, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, nx, 1, nx, nx, nu);
+  cta_mmx<TC>(Phi, nx, fx, nx, 1.0, -1.0, fu, nu, 1, Rux, nx, 1, nx, nx, nu);
+  if (el) cta_mmx<TC>(el->Cg, nx, el->Cg, nx, 1.0, 1.0, el->Y, nu, 1, el->W, 1, nu, nx, nx, nu);
   __syncthreads();
 }
 
@@ -225,6 +229,7 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   SmemCarver sm(smem_raw);
@@ -256,11 +261,11 @@ __global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
     }
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
     ElemAcc el{A, W, Y, Cg};
-    riccati_stage<NU>(nx, nu, k == kb - 1, J, sp.fx(buf), sp.fu(buf), sp.G(buf), T, Rux, Phi,
+    riccati_stage<NU, TC>(nx, nu, k == kb - 1, J, sp.fx(buf), sp.fu(buf), sp.G(buf), T, Rux, Phi,
                   &st_s, &el);
     // J symmetrised ; A <- A Phi
     cta_symmetrize(J, nx, nx);
-    cta_mm(An, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, Phi, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(An, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, Phi, nx, 1, nx, nx, nx);
     double *t = A; A = An; An = t;
     __syncthreads();
   }
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LQ_STAMP(0);
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
   SmemCarver sm(smem_raw);
@@ -326,22 +332,22 @@ __global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
     }
     __syncthreads();
     LQ_STAMP(2);
-    cta_mm(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
     __syncthreads();
     LQ_STAMP(3);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * n3 + i] += 1.0;
     cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
     // T1 = A_j X_C ; T2 = J_j X_A
-    cta_mm(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
-    cta_mm(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
     __syncthreads();
     // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
-    cta_mm(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
-    cta_mm(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+    cta_mmx<TC>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
     __syncthreads();
     // A = A_j X_A (into T1, then copy)
-    cta_mm(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
     cta_symmetrize(Cj, nx, nx);
     cta_symmetrize(Jj, nx, nx);
     __syncthreads();
@@ -373,6 +379,7 @@ template <int NX>
 __global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int top) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   SmemCarver sm(smem_raw);
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
@@ -430,13 +437,13 @@ __global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int to
     }
     __syncthreads();
     // M = [I + S C | S A]
-    cta_mm(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mm(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
     cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised
-    cta_mm(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);
     __syncthreads();
@@ -451,6 +458,7 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu, n2 = nx * nx;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   SmemCarver sm(smem_raw);
@@ -485,7 +493,7 @@ __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
     }
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
     double *G = sp.G(buf);
-    riccati_stage<NU>(nx, nu, false, V, sp.fx(buf), sp.fu(buf), G, T, Rux, Phi, &st_s, nullptr);
+    riccati_stage<NU, TC>(nx, nu, false, V, sp.fx(buf), sp.fu(buf), G, T, Rux, Phi, &st_s, nullptr);
     const size_t ks = (size_t)b * d.K + k;
     double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * n2;
     cta_symmetrize(V, nx, nx);
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
     }
     for (int i = threadIdx.x; i < n2; i += blockDim.x) Pk[i] = Phi[i];
     // Psi <- Psi Phi
-    cta_mm(Psin, nx, nullptr, 0, 0.0, 1.0, Psi, nx, 1, Phi, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(Psin, nx, nullptr, 0, 0.0, 1.0, Psi, nx, 1, Phi, nx, 1, nx, nx, nx);
     double *t = Psi; Psi = Psin; Psin = t;
     __syncthreads();
     // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
@@ -517,6 +525,7 @@ template <int NX>
 __global__ void __launch_bounds__(128) psi_compose_kernel(LqDev d, int lev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
   SmemCarver sm(smem_raw);
@@ -528,7 +537,7 @@ __global__ void __launch_bounds__(128) psi_compose_kernel(LqDev d, int lev) {
   for (int c = c1 - 2; c >= c0; c--) {
     for (int i = threadIdx.x; i < n2; i += blockDim.x) Pc[i] = d.segPsi[base + (size_t)c * n2 + i];
     __syncthreads();
-    cta_mm(Pn, nx, nullptr, 0, 0.0, 1.0, P, nx, 1, Pc, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(Pn, nx, nullptr, 0, 0.0, 1.0, P, nx, 1, Pc, nx, 1, nx, nx, nx);
     double *t = P; P = Pn; Pn = t;
     __syncthreads();
   }
