@@ -1040,6 +1040,9 @@ int hqpcu_debug_stamps(hqpcu_handle *h, long long *out16) {
   CU(cudaSetDevice(h->device));
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(out16, h->d.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+#ifdef LQ_TIMING
+  CU(cudaMemcpyFromSymbol(out16, g_dbg, 16 * sizeof(long long)));
+#endif
   return HQPCU_OK;
 }
 

@@ -76,6 +76,13 @@ struct LqDev {
   double *segv0, *segvb, *segx0, *segxa;  // [batch][st.nel][nx]
 };
 
+#ifdef LQ_TIMING
+__device__ long long g_dbg[32];  // clock64 stamps of one CTA (timing builds only)
+#define LQ_STAMP2(i) do { if (threadIdx.x == 0 && blockIdx.x == 7) g_dbg[i] = clock64(); } while (0)
+#else
+#define LQ_STAMP2(i) do { } while (0)
+#endif
+
 // status word bits (device) -> HQPCU_E_SING / HQPCU_E_NOTPD (host)
 #define LQ_FLAG_SING 1
 #define LQ_FLAG_NOTPD 2
@@ -317,6 +324,60 @@ __device__ __forceinline__ int warp_ldlt(double *A, int lda, int m) {
     __syncwarp();
   }
   return st;
+}
+
+// fast FP64 reciprocal: hardware seed (MUFU.RCP64H) + two Newton steps; full
+// double precision for normal, finite, non-zero x (pivots are checked by the
+// callers), without the slow path of a generic IEEE division
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// Register-resident LDL^T for compile-time M <= 32: lane i keeps row i of the
+// block; per pivot the pivot column is broadcast with warp shuffles (no shared
+// memory traffic, no integer division, no barriers inside the sweep).
+template <int M>
+__device__ __forceinline__ int warp_ldlt_reg(double *A, int lda) {
+  const int lane = threadIdx.x & 31;
+  const int row = lane < M ? lane : M - 1;
+  double a[M];
+#pragma unroll
+  for (int j = 0; j < M; j++) a[j] = A[row * lda + j];
+  int st = 0;
+#pragma unroll
+  for (int p = 0; p < M; p++) {
+    const double dp = __shfl_sync(0xffffffffu, a[p], p);
+    if (!(dp > 0.0)) st |= (dp == 0.0 || dp != dp) ? LQ_FLAG_SING : LQ_FLAG_NOTPD;
+    const double inv = fast_rcp(dp);
+    const double li = a[p] * inv;  // multiplier L[row][p] (meaningful for row > p)
+#pragma unroll
+    for (int j = p + 1; j < M; j++) {
+      const double ajp = __shfl_sync(0xffffffffu, a[p], j);  // A[j][p] before scaling
+      a[j] = fma(-li, ajp, a[j]);
+    }
+    a[p] = (lane == p) ? inv : li;
+  }
+  if (lane < M) {
+#pragma unroll
+    for (int j = 0; j < M; j++)
+      if (j <= lane) A[lane * lda + j] = a[j];
+  }
+  __syncwarp();
+  return st;
+}
+
+template <int M>
+__device__ __forceinline__ int warp_ldlt_any(double *A, int lda, int m) {
+  if constexpr (M > 0 && M <= 32)
+    return warp_ldlt_reg<M>(A, lda);
+  else
+    return warp_ldlt(A, lda, m);
 }
 
 // Solve (L D L') y = b in place for one right-hand side held at y[i*ys],

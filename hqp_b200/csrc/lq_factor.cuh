@@ -33,6 +33,12 @@
 
 #include "lq_device.cuh"
 
+#ifdef LQ_TIMING
+#define LQ_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) d.dbg[i] = clock64(); } while (0)
+#else
+#define LQ_STAMP(i) do { } while (0)
+#endif
+
 #ifndef LQ_USE_DMMA
 #define LQ_USE_DMMA 1  // FP64 tensor-core block products in the templated kernels
 #endif
@@ -180,6 +186,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
                                               const ElemAcc *el) {
   const int nm = nx + nu;
   const int tid = threadIdx.x, nthr = blockDim.x;
+  LQ_STAMP2(1);
   if (!zero_V) {
     // T = V [fx fu]
     cta_mmx<TC>(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fx, nx, 1, nx, nx, nx);
@@ -188,6 +195,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   if (el)  // W = A fu
     cta_mmx<TC>(el->W, nu, nullptr, 0, 0.0, 1.0, el->A, nx, 1, fu, nu, 1, nx, nu, nx);
   if (!zero_V || el) __syncthreads();
+  LQ_STAMP2(2);
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
     cta_mmx<TC>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, nm, 1, nx, nx, nx);
@@ -197,11 +205,13 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
+  LQ_STAMP2(3);
   if (tid < 32) {
-    const int st = warp_ldlt(Guu, nm, nu);
+    const int st = warp_ldlt_any<NU>(Guu, nm, nu);
     if (st && tid == 0) atomicOr(st_s, st);
   }
   __syncthreads();
+  LQ_STAMP2(4);
   // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
   // K1: rows of Y = W Guu^{-1} on the next nx threads
   for (int j = tid; j < (el ? 2 * nx : nx); j += nthr) {
@@ -215,6 +225,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
     }
   }
   __syncthreads();
+  LQ_STAMP2(5);
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W'
   cta_mmx<TC>(V, nx, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, nx, 1, nx, nx, nu);
   cta_mmx<TC>(Phi, nx, fx, nx, 1.0, -1.0, fu, nu, 1, Rux, nx, 1, nx, nx, nu);
@@ -285,11 +296,6 @@ __global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
 // K2a: compose the children [g*R, min((g+1)*R, cnt)) of level `lev` into
 // element g of level lev+1.  grid (cnt_{lev+1}, batch).
 // ---------------------------------------------------------------------------
-#ifdef LQ_TIMING
-#define LQ_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) d.dbg[i] = clock64(); } while (0)
-#else
-#define LQ_STAMP(i) do { } while (0)
-#endif
 
 template <int NX>
 __global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
@@ -491,9 +497,11 @@ __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
       fence_proxy_async();
       stage_issue(d, nx, nu, sp, b, k - 1, buf ^ 1);
     }
+    LQ_STAMP2(0);
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
     double *G = sp.G(buf);
     riccati_stage<NU, TC>(nx, nu, false, V, sp.fx(buf), sp.fu(buf), G, T, Rux, Phi, &st_s, nullptr);
+    LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;
     double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * n2;
     cta_symmetrize(V, nx, nx);
@@ -507,6 +515,7 @@ __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
     cta_mmx<TC>(Psin, nx, nullptr, 0, 0.0, 1.0, Psi, nx, 1, Phi, nx, 1, nx, nx, nx);
     double *t = Psi; Psi = Psin; Psin = t;
     __syncthreads();
+    LQ_STAMP2(7);
     // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
     // s-1 and is written there
     if (k > ka || s == 0) {

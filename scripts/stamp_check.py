@@ -6,9 +6,12 @@ ipcuda.LIB_PATH = os.path.join(os.path.dirname(ipcuda.LIB_PATH), "libhqpcuda_tim
 from hqp_b200.problem import synth_lqdocp, synth_rhs
 p = synth_lqdocp(20, 10, 10000)
 z, w, r1, r2, r3, r4 = synth_rhs(p)
-e = ipcuda.IpCuda(p); e.update()
-for _ in range(3): e.factor(z, w)
-out = (ctypes.c_longlong * 16)()
-ipcuda.lib().hqpcu_debug_stamps(e.h, out)
-st = list(out)
-print("stamps (cycles, last compose launch = top group):", [st[i+1]-st[i] for i in range(6)], "total", st[6]-st[0])
+for nseg in (0, 148):
+    e = ipcuda.IpCuda(p, nseg=nseg); e.update()
+    for _ in range(3): e.factor(z, w)
+    out = (ctypes.c_longlong * 16)()
+    ipcuda.lib().hqpcu_debug_stamps(e.h, out)
+    st = list(out)
+    names = ["acquire", "T=V F (+W)", "G+=F'T", "LDL", "Rux solve", "V,Phi", "sym/store/Psi"]
+    print("nseg", e.nseg, "K3 last stage of CTA 7 (cycles):", {n: st[i+1]-st[i] for i, n in enumerate(names)}, "stage total", st[7]-st[0])
+    e.close()
