@@ -179,6 +179,10 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
 static int set_smem(const void *fn, size_t bytes) {
   if (bytes > 48 * 1024)
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  // all of the L1/shared array as shared memory: these kernels live in shared
+  // memory and their occupancy is bounded by it (ncu: occupancy_limit_shared_mem)
+  CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
+                          cudaSharedmemCarveoutMaxShared));
   return HQPCU_OK;
 }
 

@@ -204,65 +204,89 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
       : "d"(a), "d"(b));
 }
 
+// one 8x8 tile pair (tiles ta, tb; tb < 0: none) of the product, all indices
+// compile-time after unrolling: interior tiles carry no bounds predicates
+__device__ __forceinline__ void mm_tc_tile_pair(double *C, int ldc, const double *C0, int ldc0,
+                                                double beta, double alpha, const double *A,
+                                                int ar, int ac, const double *B, int br, int bc,
+                                                int M, int N, int Kd, int TJ, int ta, int tb,
+                                                int g, int t) {
+  const bool has2 = tb >= 0;
+  const int i0 = (ta / TJ) << 3, j0 = (ta % TJ) << 3;
+  const int i1 = has2 ? (tb / TJ) << 3 : 0, j1 = has2 ? (tb % TJ) << 3 : 0;
+  // bounds checks only where the tile crosses the matrix edge (compile-time test)
+  const bool va0 = (i0 + 8 <= M) || (i0 + g < M), vb0 = (j0 + 8 <= N) || (j0 + g < N);
+  const bool va1 = has2 && ((i1 + 8 <= M) || (i1 + g < M));
+  const bool vb1 = has2 && ((j1 + 8 <= N) || (j1 + g < N));
+  const double *a0p = A + (i0 + g) * ar + t * ac, *b0p = B + (j0 + g) * bc + t * br;
+  const double *a1p = A + (i1 + g) * ar + t * ac, *b1p = B + (j1 + g) * bc + t * br;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+#pragma unroll
+  for (int k0 = 0; k0 < Kd; k0 += 4) {
+    const bool vk = (k0 + 4 <= Kd) || (k0 + t < Kd);
+    const double a0 = (va0 && vk) ? a0p[k0 * ac] : 0.0;
+    const double b0 = (vb0 && vk) ? b0p[k0 * br] : 0.0;
+    dmma_m8n8k4(c00, c01, a0, b0);
+    if (has2) {
+      const double a1 = (va1 && vk) ? a1p[k0 * ac] : 0.0;
+      const double b1 = (vb1 && vk) ? b1p[k0 * br] : 0.0;
+      dmma_m8n8k4(c10, c11, a1, b1);
+    }
+  }
+  {
+    const int ic = i0 + g, jc = j0 + 2 * t;
+    const bool vr = (i0 + 8 <= M) || (ic < M);
+    const bool v0 = vr && ((j0 + 8 <= N) || (jc < N));
+    const bool v1 = vr && ((j0 + 8 <= N) || (jc + 1 < N));
+    if (v0) {
+      double r = alpha * c00;
+      if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
+      C[ic * ldc + jc] = r;
+    }
+    if (v1) {
+      double r = alpha * c01;
+      if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
+      C[ic * ldc + jc + 1] = r;
+    }
+  }
+  if (has2) {
+    const int ic = i1 + g, jc = j1 + 2 * t;
+    const bool vr = (i1 + 8 <= M) || (ic < M);
+    const bool v0 = vr && ((j1 + 8 <= N) || (jc < N));
+    const bool v1 = vr && ((j1 + 8 <= N) || (jc + 1 < N));
+    if (v0) {
+      double r = alpha * c10;
+      if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
+      C[ic * ldc + jc] = r;
+    }
+    if (v1) {
+      double r = alpha * c11;
+      if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
+      C[ic * ldc + jc + 1] = r;
+    }
+  }
+}
+
 __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
                                           double beta, double alpha, const double *A, int ar,
                                           int ac, const double *B, int br, int bc, int M, int N,
                                           int Kd) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = LQ_NT / 32;
+  constexpr int NW = LQ_NT / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
   const int ntiles = TI * TJ;
-  // two tiles in flight per warp: independent accumulator chains
-  for (int tile = warp; tile < ntiles; tile += 2 * nwarps) {
-    const int tile2 = tile + nwarps;
-    const bool has2 = tile2 < ntiles;
-    const int i0 = (tile / TJ) << 3, j0 = (tile % TJ) << 3;
-    const int i1 = has2 ? (tile2 / TJ) << 3 : i0, j1 = has2 ? (tile2 % TJ) << 3 : j0;
-    const bool va0 = i0 + g < M, vb0 = j0 + g < N;
-    const bool va1 = has2 && i1 + g < M, vb1 = has2 && j1 + g < N;
-    const double *a0p = A + (i0 + g) * ar, *b0p = B + (j0 + g) * bc;
-    const double *a1p = A + (i1 + g) * ar, *b1p = B + (j1 + g) * bc;
-    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+  // tiles are dealt to the warps in pairs (two accumulator chains in flight);
+  // the tile loop is unrolled with compile-time tile indices, the warp test is
+  // uniform
 #pragma unroll
-    for (int k0 = 0; k0 < Kd; k0 += 4) {
-      const int k = k0 + t;
-      const bool vk = k < Kd;
-      const double a0 = (va0 && vk) ? a0p[k * ac] : 0.0;
-      const double b0 = (vb0 && vk) ? b0p[k * br] : 0.0;
-      const double a1 = (va1 && vk) ? a1p[k * ac] : 0.0;
-      const double b1 = (vb1 && vk) ? b1p[k * br] : 0.0;
-      dmma_m8n8k4(c00, c01, a0, b0);
-      dmma_m8n8k4(c10, c11, a1, b1);
-    }
-    {
-      const int ic = i0 + g, jc = j0 + 2 * t;
-      if (ic < M) {
-        if (jc < N) {
-          double r = alpha * c00;
-          if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
-          C[ic * ldc + jc] = r;
-        }
-        if (jc + 1 < N) {
-          double r = alpha * c01;
-          if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
-          C[ic * ldc + jc + 1] = r;
-        }
-      }
-    }
-    if (has2) {
-      const int ic = i1 + g, jc = j1 + 2 * t;
-      if (ic < M) {
-        if (jc < N) {
-          double r = alpha * c10;
-          if (C0) r = fma(beta, C0[ic * ldc0 + jc], r);
-          C[ic * ldc + jc] = r;
-        }
-        if (jc + 1 < N) {
-          double r = alpha * c11;
-          if (C0) r = fma(beta, C0[ic * ldc0 + jc + 1], r);
-          C[ic * ldc + jc + 1] = r;
-        }
-      }
+  for (int t0 = 0; t0 < ntiles; t0 += 2 * NW) {
+#pragma unroll
+    for (int q = 0; q < NW; q++) {
+      const int ta = t0 + q, tb = t0 + NW + q;
+      if (ta < ntiles && warp == q)
+        mm_tc_tile_pair(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, TJ, ta,
+                        tb < ntiles ? tb : -1, g, t);
     }
   }
 }
