@@ -31,6 +31,7 @@ static thread_local std::string g_err;
 // Compile-time specialisations of the factor kernels for the stage shapes named
 // in BASELINE.json; any other shape runs the <0,0> (runtime-dimension) build of
 // the same code.
+#define LQ_SCAN_R 32  // radix of the solve hierarchy
 #define LQ_DISPATCH_NXNU(nx_, nu_, CALL)                                       \
   do {                                                                        \
     if ((nx_) == 20 && (nu_) == 10) { CALL(20, 10); }                         \
@@ -89,6 +90,9 @@ struct hqpcu_handle {
   size_t smem_k1 = 0, smem_k2 = 0, smem_k3 = 0, smem_cmp = 0, smem_psi = 0, smem_chain = 0;
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
   int max_el = 0;  // elements per instance the seg* arrays were sized for
+  int n_sm = 148, k1_ctas_per_sm = 3;
+  int ring_scan = 8;
+  size_t smem_scan = 0;
   // horizon split: right-hand sides remembered between the three step phases
   const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
   bool ranged() const { return d.has_prev || d.has_next; }
@@ -162,8 +166,13 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
     // enough independent instances already fill the machine: sequential sweep
     if (h->dims.batch >= 64 || K < 32)
       P = 1;
-    else
-      P = std::max(2, K / 12);  // ~12 stages per segment
+    else {
+      // one wave of segment CTAs: (SMs x resident CTAs per SM of the K1 kernel),
+      // but never fewer than 8 stages per segment
+      const int wave = std::max(1, h->n_sm * std::max(1, h->k1_ctas_per_sm));
+      const int per_inst = std::max(1, wave / std::max(1, h->dims.batch));
+      P = std::max(2, std::min(per_inst, K / 8));
+    }
   }
   P = std::max(1, std::min(P, std::max(1, K / 2)));
   P = std::min(P, 16384);
@@ -173,7 +182,7 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   d.P = P;
   d.L = L;
   build_tree(d.ft, P, 2);
-  build_tree(d.st, P, 32);
+  build_tree(d.st, P, LQ_SCAN_R);
 }
 
 static int set_smem(const void *fn, size_t bytes) {
@@ -244,6 +253,16 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   memset(&h->q, 0, sizeof h->q);
   h->q.n_eq = dims->n_eq;
   h->q.nnz = dims->n_eq ? dims->eq_ptr[dims->n_eq] : 0;
+  {
+    // resident K1 CTAs per SM (shared-memory bound) -> one wave of segments
+    const size_t p2 = 2 * (pad2((size_t)nm * nm) + pad2((size_t)nx * nx) + pad2((size_t)nx * nu) +
+                           pad2((size_t)nm)) * sizeof(double);
+    const size_t k1 = p2 + (5 * pad2((size_t)nx * nx) + pad2((size_t)nx * nm) +
+                            pad2((size_t)nu * nx) + 2 * pad2((size_t)nx * nu)) * sizeof(double);
+    cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dims->device);
+    // 3 was the measured optimum at nx=20 (4 fit by size but run in two waves)
+    h->k1_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (k1 + 1024)));
+  }
   choose_segments(h, dims->nseg);
 
   // ---- index maps -------------------------------------------------------
@@ -410,8 +429,12 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   h->smem_cmp = (5 * nn + pad2((size_t)3 * nx * nx) + 2 * nn + pad2((size_t)2 * nx * nx)) *
                 sizeof(double);
   h->smem_psi = 3 * nn * sizeof(double);
-  h->smem_chain = (pad2((size_t)LQ_RING * (nx * nx + 2 * nx)) + pad2((size_t)nx)) * sizeof(double) +
-                  LQ_RING * sizeof(uint64_t);
+  h->smem_chain = (pad2((size_t)2 * LQ_RING * (nx * nx + 2 * nx)) + pad2((size_t)3 * nx)) * sizeof(double) +
+                  2 * sizeof(uint64_t) + 16;
+  // the hierarchy scans run few CTAs: stage every matrix of a group up front
+  h->ring_scan = std::max(1, std::min(LQ_SCAN_R, (int)((100 * 1024) / ((nx * nx + 2 * nx) * sizeof(double)))));
+  h->smem_scan = (pad2((size_t)2 * h->ring_scan * (nx * nx + 2 * nx)) + pad2((size_t)3 * nx)) * sizeof(double) +
+                 2 * sizeof(uint64_t) + 16;
   const size_t smem_max = 227 * 1024;
   if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max ||
       h->smem_cmp > smem_max) {
@@ -439,8 +462,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   }
   TRY(set_smem((const void *)solve_back_kernel, h->smem_chain));
   TRY(set_smem((const void *)solve_fwd_kernel, h->smem_chain));
-  TRY(set_smem((const void *)solve_scan_kernel<true>, h->smem_chain));
-  TRY(set_smem((const void *)solve_scan_kernel<false>, h->smem_chain));
+  TRY(set_smem((const void *)solve_scan_kernel<true>, h->smem_scan));
+  TRY(set_smem((const void *)solve_scan_kernel<false>, h->smem_scan));
 #undef TRY
   *out = h;
   return HQPCU_OK;
@@ -683,7 +706,7 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
   LAUNCH(h, solve_pre_kernel, <<<gall, 128, sv, s>>>(d, r1, r2, r3, r4));
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 0));
   for (int l = 0; l < h->stop(); l++)
-    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
+    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 0, r2, h->ring_scan));
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -697,14 +720,14 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, sc, s>>>(d, h->stop(), 1, r2));
+  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, h->smem_scan, s>>>(d, h->stop(), 1, r2, h->ring_scan));
   for (int l = h->stop() - 1; l >= 0; l--)
-    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
+    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 2, r2, h->ring_scan));
   LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_mid_kernel, <<<gk, 128, sv, s>>>(d, r2));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 0));
   for (int l = 0; l < h->stop(); l++)
-    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 0, r2));
+    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 0, r2, h->ring_scan));
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -719,9 +742,9 @@ static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, co
   const size_t sc = h->smem_chain;
   const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, sc, s>>>(d, h->stop(), 1, r2));
+  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, h->smem_scan, s>>>(d, h->stop(), 1, r2, h->ring_scan));
   for (int l = h->stop() - 1; l >= 0; l--)
-    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, sc, s>>>(d, l, 2, r2));
+    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 2, r2, h->ring_scan));
   LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
   LAUNCH(h, solve_post_kernel, <<<gall, 128, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
@@ -1045,7 +1068,7 @@ int hqpcu_debug_stamps(hqpcu_handle *h, long long *out16) {
   CU(cudaStreamSynchronize(h->stream));
   CU(cudaMemcpy(out16, h->d.dbg, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
 #ifdef LQ_TIMING
-  CU(cudaMemcpyFromSymbol(out16, g_dbg, 16 * sizeof(long long)));
+  CU(cudaMemcpyFromSymbol(out16 + 16, g_dbg, 16 * sizeof(long long)));  // caller passes 32
 #endif
   return HQPCU_OK;
 }

@@ -206,14 +206,17 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   }
   double *Guu = G + nx * nm + nx;
   LQ_STAMP2(3);
+#ifndef LQ_SKIP_LDL  // (timing experiments only)
   if (tid < 32) {
     const int st = warp_ldlt_any<NU>(Guu, nm, nu);
     if (st && tid == 0) atomicOr(st_s, st);
   }
+#endif
   __syncthreads();
   LQ_STAMP2(4);
   // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
   // K1: rows of Y = W Guu^{-1} on the next nx threads
+#ifndef LQ_SKIP_SOLVE  // (timing experiments only)
   for (int j = tid; j < (el ? 2 * nx : nx); j += nthr) {
     if (j < nx) {
       for (int i = 0; i < nu; i++) Rux[i * nx + j] = G[(nx + i) * nm + j];
@@ -224,6 +227,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
       ldlt_solve_any<NU>(Guu, nm, nu, el->Y + i * nu, 1);
     }
   }
+#endif
   __syncthreads();
   LQ_STAMP2(5);
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W'

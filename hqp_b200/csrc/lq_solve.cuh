@@ -25,7 +25,7 @@
 
 #include "lq_device.cuh"
 
-#define LQ_RING 8  // stages in flight per chain (TMA ring depth)
+#define LQ_RING 4  // stages per staged chunk of a segment chain (two chunk buffers)
 
 // One sequential affine chain executed by a whole CTA (4 lanes per row):
 //     for j = 0..cnt-1, e = first + j*dir:
@@ -34,69 +34,86 @@
 //         if post: post[e + post_shift] = t
 // M: n x n row-major blocks (stride n*n), a/b/pre/post: n-vectors (stride n).
 // t lives in registers (valid for part == 0 lanes and replicated in the quad).
-// ring: LQ_RING slots of (n*n + 2n) doubles + LQ_RING mbarriers; tvec: n doubles.
+// The operands of CH consecutive steps are contiguous in memory, so each chunk
+// is staged with THREE bulk copies (M, a, b) on one mbarrier -- issuing one
+// small copy per step from a single thread costs more than the step itself --
+// and the next chunk is in flight while the current one is consumed (two chunk
+// buffers).  buf: 2 * CH * (n*n + 2n) doubles, bars: 2, tvec: 2n doubles.
 template <bool TRANS>
 __device__ __forceinline__ double chain_run(int n, bool use_tma, const double *M,
                                             const double *a, const double *b, double *pre,
                                             double *post, int post_shift, int first, int dir,
-                                            int cnt, double t, double *ring, uint64_t *bars,
-                                            double *tvec) {
+                                            int cnt, double t, double *buf, uint64_t *bars,
+                                            double *tvec, int CH) {
   const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
-  const int slot_sz = n * n + 2 * n;
-  const uint32_t bm = n * n * 8, bv = n * 8;
+  const int n2 = n * n;
+  const size_t chunk_sz = (size_t)CH * (n2 + 2 * n);
+  const int nchunk = (cnt + CH - 1) / CH;
+  // chunk c covers steps [c*CH, c*CH + len): elements e_lo .. e_lo + len - 1
+  auto issue = [&](int c) {
+    const int j0 = c * CH, len = min(CH, cnt - j0);
+    const int e_first = first + j0 * dir;
+    const int e_lo = dir > 0 ? e_first : e_first - (len - 1);
+    double *cb = buf + (size_t)(c & 1) * chunk_sz;
+    uint64_t *bar = &bars[c & 1];
+    const uint32_t bm = (uint32_t)len * n2 * 8, bv = (uint32_t)len * n * 8;
+    mbar_expect_tx(bar, bm + bv + (b ? bv : 0));
+    tma_load_1d(cb, M + (size_t)e_lo * n2, bm, bar);
+    tma_load_1d(cb + (size_t)CH * n2, a + (size_t)e_lo * n, bv, bar);
+    if (b) tma_load_1d(cb + (size_t)CH * (n2 + n), b + (size_t)e_lo * n, bv, bar);
+  };
   if (use_tma && threadIdx.x == 0) {
-    for (int j = 0; j < LQ_RING && j < cnt; j++) {
-      const int e = first + j * dir;
-      double *sl = ring + (size_t)j * slot_sz;
-      mbar_expect_tx(&bars[j], bm + bv + (b ? bv : 0));
-      tma_load_1d(sl, M + (size_t)e * n * n, bm, &bars[j]);
-      tma_load_1d(sl + n * n, a + (size_t)e * n, bv, &bars[j]);
-      if (b) tma_load_1d(sl + n * n + n, b + (size_t)e * n, bv, &bars[j]);
-    }
+    issue(0);
+    if (nchunk > 1) issue(1);
   }
-  for (int j = 0; j < cnt; j++) {
-    const int e = first + j * dir;
-    const int slot = j % LQ_RING;
-    const double *Ms, *as, *bs;
-    if (use_tma) {
-      const double *sl = ring + (size_t)slot * slot_sz;
-      mbar_wait(&bars[slot], (j / LQ_RING) & 1);
-      Ms = sl;
-      as = sl + n * n;
-      bs = b ? sl + n * n + n : nullptr;
-    } else {
-      Ms = M + (size_t)e * n * n;
-      as = a + (size_t)e * n;
-      bs = b ? b + (size_t)e * n : nullptr;
-    }
-    if (i < n && part == 0) {
-      if (pre) pre[(size_t)e * n + i] = t;
-      tvec[i] = bs ? t + bs[i] : t;
-    }
-    __syncthreads();
-    double s = 0.0;
-    if (i < n) {
-      if (TRANS) {
-        for (int l = part; l < n; l += 4) s = fma(Ms[l * n + i], tvec[l], s);
+  for (int c = 0; c < nchunk; c++) {
+    const int j0 = c * CH, len = min(CH, cnt - j0);
+    const int e_first = first + j0 * dir;
+    const int e_lo = dir > 0 ? e_first : e_first - (len - 1);
+    const double *cb = buf + (size_t)(c & 1) * chunk_sz;
+    if (use_tma) mbar_wait(&bars[c & 1], (c >> 1) & 1);
+    for (int jj = 0; jj < len; jj++) {
+      const int j = j0 + jj;
+      const int e = e_first + jj * dir;
+      const double *Ms, *as, *bs;
+      if (use_tma) {
+        const int o = e - e_lo;
+        Ms = cb + (size_t)o * n2;
+        as = cb + (size_t)CH * n2 + (size_t)o * n;
+        bs = b ? cb + (size_t)CH * (n2 + n) + (size_t)o * n : nullptr;
       } else {
-        for (int l = part; l < n; l += 4) s = fma(Ms[i * n + l], tvec[l], s);
+        Ms = M + (size_t)e * n2;
+        as = a + (size_t)e * n;
+        bs = b ? b + (size_t)e * n : nullptr;
+      }
+      double *tv = tvec + (j & 1) * n;  // double buffer: one barrier per step
+      if (i < n && part == 0) {
+        if (pre) pre[(size_t)e * n + i] = t;
+        tv[i] = bs ? t + bs[i] : t;
+      }
+      __syncthreads();
+      double s = 0.0;
+      if (i < n) {
+        if (TRANS) {
+          for (int l = part; l < n; l += 4) s = fma(Ms[l * n + i], tv[l], s);
+        } else {
+          for (int l = part; l < n; l += 4) s = fma(Ms[i * n + l], tv[l], s);
+        }
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (i < n) {
+        t = as[i] + s;
+        if (post && part == 0) post[(size_t)(e + post_shift) * n + i] = t;
       }
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (i < n) {
-      t = as[i] + s;
-      if (post && part == 0) post[(size_t)(e + post_shift) * n + i] = t;
-    }
-    __syncthreads();
-    if (use_tma && threadIdx.x == 0 && j + LQ_RING < cnt) {
-      const int e2 = first + (j + LQ_RING) * dir;
-      double *sl = ring + (size_t)slot * slot_sz;
-      fence_proxy_async();
-      mbar_expect_tx(&bars[slot], bm + bv + (b ? bv : 0));
-      tma_load_1d(sl, M + (size_t)e2 * n * n, bm, &bars[slot]);
-      tma_load_1d(sl + n * n, a + (size_t)e2 * n, bv, &bars[slot]);
-      if (b) tma_load_1d(sl + n * n + n, b + (size_t)e2 * n, bv, &bars[slot]);
+    if (use_tma && c + 2 < nchunk) {
+      // this chunk buffer is refilled only after every thread has read it
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        issue(c + 2);
+      }
     }
   }
   return t;
@@ -107,14 +124,15 @@ struct ChainSmem {
   uint64_t *bars;
 };
 
-__device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw) {
+__device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH) {
   SmemCarver sm(raw);
   ChainSmem cs;
-  cs.ring = sm.take(LQ_RING * (n * n + 2 * n));
-  cs.tvec = sm.take(n);
-  cs.bars = sm.take_bars(LQ_RING);
+  cs.ring = sm.take(2 * CH * (n * n + 2 * n));
+  cs.tvec = sm.take(3 * n);
+  cs.bars = sm.take_bars(2);
   if (threadIdx.x == 0) {
-    for (int j = 0; j < LQ_RING; j++) mbar_init(&cs.bars[j], 1);
+    mbar_init(&cs.bars[0], 1);
+    mbar_init(&cs.bars[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -191,7 +209,7 @@ __global__ void __launch_bounds__(128) solve_pre_kernel(
 __global__ void solve_back_kernel(LqDev d, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int i = threadIdx.x >> 2;
@@ -201,7 +219,7 @@ __global__ void solve_back_kernel(LqDev d, int mode) {
   if (mode == 1 && i < nx) t = d.segvb[so + i];
   t = chain_run<true>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx,
                       nullptr, mode == 1 ? d.v + (size_t)b * (d.K + 1) * nx : nullptr, 0,
-                      kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec);
+                      kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec, LQ_RING);
   if (mode == 0 && i < nx && (threadIdx.x & 3) == 0) d.segv0[so + i] = t;
 }
 
@@ -210,7 +228,7 @@ __global__ void solve_back_kernel(LqDev d, int mode) {
 __global__ void solve_fwd_kernel(LqDev d, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
@@ -224,7 +242,7 @@ __global__ void solve_fwd_kernel(LqDev d, int mode) {
   }
   t = chain_run<false>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
                        mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
-                       cs.tvec);
+                       cs.tvec, LQ_RING);
   if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = t;
 }
 
@@ -238,10 +256,11 @@ __global__ void solve_fwd_kernel(LqDev d, int mode) {
 //                 vb / xa, recording the children's values
 // backward (BACK = true): children visited last -> first with Psi'.
 template <bool BACK>
-__global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__restrict__ r2) {
+__global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__restrict__ r2,
+                                  int ring_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
   const int g = blockIdx.x, b = blockIdx.y;
   const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
   const size_t eb = (size_t)b * d.st.nel + d.st.off[lev];           // first element of level
@@ -263,11 +282,12 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
       if (i < nx) t = -r2[(size_t)b * d.me + (size_t)d.K * nx + i];
     } else {
       // x_0 = -Vxx[0]^{-1} v[0] (:2111-2117)
-      if (threadIdx.x < nx) cs.tvec[threadIdx.x] = -d.v[(size_t)b * (d.K + 1) * nx + threadIdx.x];
+      double *scr = cs.tvec + 2 * nx;
+      if (threadIdx.x < nx) scr[threadIdx.x] = -d.v[(size_t)b * (d.K + 1) * nx + threadIdx.x];
       __syncthreads();
-      if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * nx * nx, nx, nx, cs.tvec, 1);
+      if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * nx * nx, nx, nx, scr, 1);
       __syncthreads();
-      if (i < nx) t = cs.tvec[i];
+      if (i < nx) t = scr[i];
       __syncthreads();
     }
   } else {
@@ -278,7 +298,7 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
   const int first = BACK ? c1 - 1 : c0, dir = BACK ? -1 : +1;
   t = chain_run<BACK>(nx, d.use_tma, d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
                       phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir, c1 - c0, t,
-                      cs.ring, cs.bars, cs.tvec);
+                      cs.ring, cs.bars, cs.tvec, ring_n);
   if (phase == 0 && i < nx && part == 0) in0[(pb + g) * nx + i] = t;
 }
 
