@@ -557,9 +557,9 @@ static int launch_eq_factor(hqpcu_handle *h) {
 
 #define L_K1(NX_, NU_) LAUNCH(h, (seg_element_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k1, s>>>(d))
 #define L_K3(NX_, NU_) LAUNCH(h, (seg_riccati_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k3, s>>>(d))
-#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, 128, h->smem_cmp, s>>>(d, l))
-#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), 128, h->smem_k2, s>>>(d, h->ftop(), 1))
-#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, 128, h->smem_k2, s>>>(d, l, 0))
+#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_cmp, s>>>(d, l))
+#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), LQ_NT2, h->smem_k2, s>>>(d, h->ftop(), 1))
+#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, LQ_NT2, h->smem_k2, s>>>(d, l, 0))
 #define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, 128, h->smem_psi, s>>>(d, l))
 
 // factor, part 1: bound diagonal, segment elements, tree up-sweep
@@ -972,7 +972,7 @@ int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank,
   const LqDev &d = h->d;
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
-#define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, 128, h->smem_k2, s>>>(d, gathered, rank, world))
+#define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, LQ_NT2, h->smem_k2, s>>>(d, gathered, rank, world))
   LQ_DISPATCH_NX(d.nx, d.nu, L_RS);
 #undef L_RS
   int rc = launch_factor_down(h);

@@ -10,7 +10,8 @@
 #include <stdint.h>
 
 #define LQ_MAXLEV 16
-#define LQ_NT 128  // threads per CTA of the factor kernels (compile-time)
+#define LQ_NT 128  // threads per CTA of the segment kernels K1/K3 (compile-time)
+#define LQ_NT2 256 // threads per CTA of the tree kernels (compose / scan): quads x columns
 
 // R-ary hierarchy over the P level-0 segments of one instance
 struct LqTree {
@@ -267,11 +268,11 @@ __device__ __forceinline__ void mm_tc_tile_pair(double *C, int ldc, const double
   }
 }
 
+template <int NW>
 __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
                                           double beta, double alpha, const double *A, int ar,
                                           int ac, const double *B, int br, int bc, int M, int N,
                                           int Kd) {
-  constexpr int NW = LQ_NT / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
@@ -292,13 +293,13 @@ __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, 
 }
 
 // compile-time choice between the tensor-core and the FMA product
-template <bool TC>
+template <bool TC, int NW = LQ_NT / 32>
 __device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
                                         double beta, double alpha, const double *A, int ar,
                                         int ac, const double *B, int br, int bc, int M, int N,
                                         int Kd) {
   if constexpr (TC)
-    cta_mm_tc(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
   else
     cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
 }
@@ -465,10 +466,12 @@ __device__ __forceinline__ void ldlt_solve_any(const double *LD, int lda, int m,
 // M (ldm), nc > n.  Rows are never swapped: column p is eliminated with the
 // not-yet-used row of largest modulus, the row permutation is kept in piv_s and
 // undone when the solution A^{-1} B is copied to X (n x (nc-n), ldx = nc-n).
-// Whole CTA cooperates; ONE barrier per pivot: every thread owns whole columns
-// j > p (column p itself is only read), and the owner of column p+1 picks the
-// next pivot row and its reciprocal while it updates that column.
+// Whole CTA cooperates; ONE barrier per pivot.  A quad of lanes owns a column
+// j > p (lane q of the quad the rows i = q mod 4), so the per-thread work of a
+// pivot is n/4 FMAs; the quad that owns column p+1 also picks the next pivot
+// row (quad shuffle reduction) and its reciprocal while it updates that column.
 // piv_s: >= n ints, inv_s: 2 doubles (shared).  Status is OR-ed into *st_s.
+// NX > 0: n is a compile-time constant (unrolled row loops).
 // ---------------------------------------------------------------------------
 template <int NX>
 __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int nc, double *X,
@@ -492,45 +495,68 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
       if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
     }
   }
+#ifdef LQ_SKIP_GJ  // (timing experiments only)
+  if (threadIdx.x < n) piv_s[threadIdx.x] = threadIdx.x;
+#endif
   __syncthreads();
   unsigned long long used = 0ull;  // rows already consumed as pivot rows
+  const int q = threadIdx.x & 3, jl = threadIdx.x >> 2, ncol = blockDim.x >> 2;
+#ifdef LQ_SKIP_GJ
+  for (int p = 0; p < 0; p++) {
+#else
   for (int p = 0; p < n; p++) {
+#endif
     const int r = piv_s[p];
     const double inv = inv_s[p & 1];
     used |= 1ull << r;
-    for (int j = p + 1 + threadIdx.x; j < nc; j += blockDim.x) {
-      const double prj = M[r * ldm + j] * inv;
+    for (int j0 = p + 1; j0 < nc; j0 += ncol) {  // uniform trip count: shuffles below
+      const int j = j0 + jl;
+      const bool act = j < nc;
       const bool next = (j == p + 1) && (p + 1 < n);
+      const double prj = act ? M[r * ldm + j] * inv : 0.0;
       double best = -1.0, bv = 0.0;
       int bi = 0;
-      if constexpr (NX > 0) {
-        double f[NX], c[NX];
+      if (act) {
+        constexpr int NR = NX > 0 ? (NX + 3) / 4 : 1;
+        if constexpr (NX > 0) {
+          double f[NR], c[NR];
 #pragma unroll
-        for (int i = 0; i < NX; i++) {
-          f[i] = M[i * ldm + p];
-          c[i] = M[i * ldm + j];
-        }
+          for (int k = 0; k < NR; k++) {
+            const int i = q + 4 * k;
+            f[k] = i < NX ? M[i * ldm + p] : 0.0;
+            c[k] = i < NX ? M[i * ldm + j] : 0.0;
+          }
 #pragma unroll
-        for (int i = 0; i < NX; i++) {
-          c[i] = fma(-f[i], prj, c[i]);
-          M[i * ldm + j] = c[i];
-        }
-        if (next) {
-#pragma unroll
-          for (int i = 0; i < NX; i++)
-            if (!((used >> i) & 1ull) && fabs(c[i]) > best) { best = fabs(c[i]); bv = c[i]; bi = i; }
-        }
-      } else {
-        for (int i = 0; i < n; i++) {
-          const double v = fma(-M[i * ldm + p], prj, M[i * ldm + j]);
-          M[i * ldm + j] = v;
-          if (next && !((used >> i) & 1ull) && fabs(v) > best) { best = fabs(v); bv = v; bi = i; }
+          for (int k = 0; k < NR; k++) {
+            const int i = q + 4 * k;
+            c[k] = fma(-f[k], prj, c[k]);
+            if (i < NX && i != r) M[i * ldm + j] = c[k];
+            if (i < NX && !((used >> i) & 1ull) && fabs(c[k]) > best) {
+              best = fabs(c[k]); bv = c[k]; bi = i;
+            }
+          }
+        } else {
+          for (int i = q; i < n; i += 4) {
+            const double v = fma(-M[i * ldm + p], prj, M[i * ldm + j]);
+            if (i != r) M[i * ldm + j] = v;
+            if (!((used >> i) & 1ull) && fabs(v) > best) { best = fabs(v); bv = v; bi = i; }
+          }
         }
       }
-      M[r * ldm + j] = prj;  // pivot row: scaled, not eliminated
-      if (next) {
+      __syncwarp();  // every lane of the quad has read M[r][j] before it is overwritten
+      if (act && q == (r & 3)) M[r * ldm + j] = prj;  // pivot row: scaled, not eliminated
+      // next pivot: reduce (best, bi, bv) over the quad that owns column p+1;
+      // ties go to the smaller row index
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bv = ov; bi = oi; }
+      }
+      if (next && q == 0) {
         piv_s[p + 1] = bi;
-        inv_s[(p + 1) & 1] = 1.0 / bv;
+        inv_s[(p + 1) & 1] = fast_rcp(bv);
         if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
       }
     }

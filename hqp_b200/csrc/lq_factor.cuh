@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
 // ---------------------------------------------------------------------------
 
 template <int NX>
-__global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
+__global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LQ_STAMP(0);
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
@@ -342,22 +342,22 @@ __global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
     }
     __syncthreads();
     LQ_STAMP(2);
-    cta_mmx<TC>(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
     __syncthreads();
     LQ_STAMP(3);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * n3 + i] += 1.0;
     cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
     // T1 = A_j X_C ; T2 = J_j X_A
-    cta_mmx<TC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
-    cta_mmx<TC>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
     __syncthreads();
     // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
-    cta_mmx<TC>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
-    cta_mmx<TC>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
     __syncthreads();
     // A = A_j X_A (into T1, then copy)
-    cta_mmx<TC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
     cta_symmetrize(Cj, nx, nx);
     cta_symmetrize(Jj, nx, nx);
     __syncthreads();
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(128) elem_compose_kernel(LqDev d, int lev) {
 //   S <- J + A' (I + S C)^{-1} S A.
 // ---------------------------------------------------------------------------
 template <int NX>
-__global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int top) {
+__global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int top) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -447,13 +447,13 @@ __global__ void __launch_bounds__(128) elem_scan_kernel(LqDev d, int lev, int to
     }
     __syncthreads();
     // M = [I + S C | S A]
-    cta_mmx<TC>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
     cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised
-    cta_mmx<TC>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);
     __syncthreads();

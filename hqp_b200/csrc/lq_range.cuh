@@ -43,7 +43,7 @@ __global__ void range_export_factor_kernel(LqDev d, double *xf) {
 // of the last rank and apply the elements of the ranks world-1 .. rank+1
 // (V_start = J + A'(I + S C)^{-1} S A).  gathered: [world][4][nx*nx].  One CTA.
 template <int NX>
-__global__ void __launch_bounds__(128) range_scan_factor_kernel(LqDev d, const double *gathered,
+__global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, const double *gathered,
                                                                 int rank, int world) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
@@ -64,12 +64,12 @@ __global__ void __launch_bounds__(128) range_scan_factor_kernel(LqDev d, const d
       Cg[i] = E[n2 + i];
     }
     __syncthreads();
-    cta_mmx<TC>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
     cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
-    cta_mmx<TC>(S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);
     __syncthreads();
