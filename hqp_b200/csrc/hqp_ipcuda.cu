@@ -91,7 +91,7 @@ struct hqpcu_handle {
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
   int max_el = 0;  // elements per instance the seg* arrays were sized for
   int n_sm = 148, k1_ctas_per_sm = 3;
-  int ring_scan = 8;
+  int ring_scan = 8, psi_chunk = 2;
   size_t smem_scan = 0;
   // horizon split: right-hand sides remembered between the three step phases
   const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
@@ -425,10 +425,14 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   const size_t pipe = 2 * (gg + nn + xu + hd) * sizeof(double) + 2 * sizeof(uint64_t);
   h->smem_k1 = pipe + (4 * nn + nf + ru + nn + 2 * xu) * sizeof(double);
   h->smem_k3 = pipe + (nn + nf + ru + 3 * nn) * sizeof(double);
-  h->smem_k2 = (4 * nn + pad2((size_t)2 * nx * nx)) * sizeof(double);
-  h->smem_cmp = (5 * nn + pad2((size_t)3 * nx * nx) + 2 * nn + pad2((size_t)2 * nx * nx)) *
+  // (+ odd-stride augmented matrix and the scratch of the warp inverse)
+  const size_t invs = pad2((size_t)nx * (nx + 1) + 2 * (nx + 2));
+  h->smem_k2 = (4 * nn + pad2((size_t)nx * (2 * nx + 1)) + invs) * sizeof(double);
+  h->smem_cmp = (5 * nn + pad2((size_t)nx * (3 * nx + 1)) + 2 * nn + pad2((size_t)2 * nx * nx) + invs) *
                 sizeof(double);
-  h->smem_psi = 3 * nn * sizeof(double);
+  // children of one group multiplied as a tree in shared memory, in chunks that fit
+  h->psi_chunk = std::max(2, std::min(LQ_SCAN_R, (int)((192 * 1024) / (nn * sizeof(double)) * 2 / 3)));
+  h->smem_psi = (size_t)(h->psi_chunk + (h->psi_chunk + 1) / 2) * nn * sizeof(double);
   h->smem_chain = (pad2((size_t)2 * LQ_RING * (nx * nx + 2 * nx)) + pad2((size_t)3 * nx)) * sizeof(double) +
                   2 * sizeof(uint64_t) + 16;
   // the hierarchy scans run few CTAs: stage every matrix of a group up front
@@ -437,7 +441,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
                  2 * sizeof(uint64_t) + 16;
   const size_t smem_max = 227 * 1024;
   if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max ||
-      h->smem_cmp > smem_max) {
+      h->smem_cmp > smem_max || h->smem_psi > smem_max) {
     g_err = "hqpcu_create: stage blocks too large for the shared-memory kernels";
     hqpcu_destroy(h);
     return HQPCU_E_UNSUPPORTED;
@@ -460,10 +464,13 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     hqpcu_destroy(h);
     return HQPCU_E_UNSUPPORTED;
   }
-  TRY(set_smem((const void *)solve_back_kernel, h->smem_chain));
-  TRY(set_smem((const void *)solve_fwd_kernel, h->smem_chain));
-  TRY(set_smem((const void *)solve_scan_kernel<true>, h->smem_scan));
-  TRY(set_smem((const void *)solve_scan_kernel<false>, h->smem_scan));
+#define SET_C(NX_)                                                             \
+  TRY(set_smem((const void *)solve_back_kernel<NX_>, h->smem_chain));         \
+  TRY(set_smem((const void *)solve_fwd_kernel<NX_>, h->smem_chain));          \
+  TRY(set_smem((const void *)(solve_scan_kernel<true, NX_>), h->smem_scan));  \
+  TRY(set_smem((const void *)(solve_scan_kernel<false, NX_>), h->smem_scan));
+  LQ_DISPATCH_NX(nx, nu, SET_C);
+#undef SET_C
 #undef TRY
   *out = h;
   return HQPCU_OK;
@@ -560,7 +567,7 @@ static int launch_eq_factor(hqpcu_handle *h) {
 #define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_cmp, s>>>(d, l))
 #define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), LQ_NT2, h->smem_k2, s>>>(d, h->ftop(), 1))
 #define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, LQ_NT2, h->smem_k2, s>>>(d, l, 0))
-#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, 128, h->smem_psi, s>>>(d, l))
+#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_psi, s>>>(d, l, h->psi_chunk))
 
 // factor, part 1: bound diagonal, segment elements, tree up-sweep
 static int launch_factor_up(hqpcu_handle *h) {
@@ -689,6 +696,39 @@ int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
   return HQPCU_OK;
 }
 
+// chain kernels: one warp per chain for the compiled sizes, else the CTA version
+static void launch_back(hqpcu_handle *h, int mode) {
+  const LqDev &d = h->d;
+  const dim3 gseg(d.P, d.batch);
+  cudaStream_t s = h->stream;
+#define L_(NX_) LAUNCH(h, solve_back_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode))
+  LQ_DISPATCH_NX(d.nx, d.nu, L_);
+#undef L_
+}
+static void launch_fwd(hqpcu_handle *h, int mode) {
+  const LqDev &d = h->d;
+  const dim3 gseg(d.P, d.batch);
+  cudaStream_t s = h->stream;
+#define L_(NX_) LAUNCH(h, solve_fwd_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode))
+  LQ_DISPATCH_NX(d.nx, d.nu, L_);
+#undef L_
+}
+static void launch_scan(hqpcu_handle *h, bool back, int groups, int lev, int phase,
+                        const double *r2) {
+  const LqDev &d = h->d;
+  const dim3 g(groups, d.batch);
+  cudaStream_t s = h->stream;
+#define L_(NX_)                                                                               \
+  do {                                                                                        \
+    if (back)                                                                                 \
+      LAUNCH(h, (solve_scan_kernel<true, NX_>), <<<g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s>>>(d, lev, phase, r2, h->ring_scan)); \
+    else                                                                                      \
+      LAUNCH(h, (solve_scan_kernel<false, NX_>), <<<g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s>>>(d, lev, phase, r2, h->ring_scan)); \
+  } while (0)
+  LQ_DISPATCH_NX(d.nx, d.nu, L_);
+#undef L_
+}
+
 // -------------------------------------------------------------------- step --
 // solve, part 1: stage-parallel prologue, zero-boundary backward chains, up-sweep
 static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
@@ -700,13 +740,11 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
   }
   const dim3 gall((d.K + 1 + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
   const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
-  const size_t sc = h->smem_chain;
-  const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
   LAUNCH(h, solve_pre_kernel, <<<gall, 128, sv, s>>>(d, r1, r2, r3, r4));
-  LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 0));
+  launch_back(h, 0);
   for (int l = 0; l < h->stop(); l++)
-    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 0, r2, h->ring_scan));
+    launch_scan(h, true, d.st.cnt[l + 1], l, 0, r2);
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -717,17 +755,15 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   const LqDev &d = h->d;
   const dim3 gk((d.K + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
   const size_t sv = (size_t)LQ_WPB * (d.nx + d.nu) * sizeof(double);
-  const size_t sc = h->smem_chain;
-  const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_scan_kernel<true>, <<<dim3(1, d.batch), tc, h->smem_scan, s>>>(d, h->stop(), 1, r2, h->ring_scan));
+  launch_scan(h, true, 1, h->stop(), 1, r2);
   for (int l = h->stop() - 1; l >= 0; l--)
-    LAUNCH(h, solve_scan_kernel<true>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 2, r2, h->ring_scan));
-  LAUNCH(h, solve_back_kernel, <<<gseg, tc, sc, s>>>(d, 1));
+    launch_scan(h, true, d.st.cnt[l + 1], l, 2, r2);
+  launch_back(h, 1);
   LAUNCH(h, solve_mid_kernel, <<<gk, 128, sv, s>>>(d, r2));
-  LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 0));
+  launch_fwd(h, 0);
   for (int l = 0; l < h->stop(); l++)
-    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 0, r2, h->ring_scan));
+    launch_scan(h, false, d.st.cnt[l + 1], l, 0, r2);
   CU(cudaGetLastError());
   return HQPCU_OK;
 }
@@ -739,13 +775,11 @@ static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, co
   const LqDev &d = h->d;
   const dim3 gall((d.K + 1 + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
   const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
-  const size_t sc = h->smem_chain;
-  const int tc = h->thr_chain;
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_scan_kernel<false>, <<<dim3(1, d.batch), tc, h->smem_scan, s>>>(d, h->stop(), 1, r2, h->ring_scan));
+  launch_scan(h, false, 1, h->stop(), 1, r2);
   for (int l = h->stop() - 1; l >= 0; l--)
-    LAUNCH(h, solve_scan_kernel<false>, <<<dim3(d.st.cnt[l + 1], d.batch), tc, h->smem_scan, s>>>(d, l, 2, r2, h->ring_scan));
-  LAUNCH(h, solve_fwd_kernel, <<<gseg, tc, sc, s>>>(d, 1));
+    launch_scan(h, false, d.st.cnt[l + 1], l, 2, r2);
+  launch_fwd(h, 1);
   LAUNCH(h, solve_post_kernel, <<<gall, 128, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;

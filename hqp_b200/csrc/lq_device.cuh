@@ -84,6 +84,13 @@ __device__ long long g_dbg[32];  // clock64 stamps of one CTA (timing builds onl
 #define LQ_STAMP2(i) do { } while (0)
 #endif
 
+// warp index as a value the compiler knows to be warp-uniform (a shuffle
+// result): branches on it are uniform, so the *_sync collectives inside
+// warp-specialised code are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs
+__device__ __forceinline__ int warp_id_uniform() {
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+}
+
 // status word bits (device) -> HQPCU_E_SING / HQPCU_E_NOTPD (host)
 #define LQ_FLAG_SING 1
 #define LQ_FLAG_NOTPD 2
@@ -462,6 +469,119 @@ __device__ __forceinline__ void ldlt_solve_any(const double *LD, int lda, int m,
 }
 
 // ---------------------------------------------------------------------------
+// Inverse of the N x N matrix M (shared memory, ldm) by ONE warp, register
+// resident: lane i owns rows i (and i + 32 for N > 32) -- in-place Gauss-Jordan
+// with implicit partial pivoting.  Per pivot the dependent path is a redux over
+// 32-bit magnitude keys (the high words of |a_ip|: enough to pick a pivot
+// within 2^-20 of the column maximum), the pivot lane's row and the reciprocal
+// it computed meanwhile published through a double-buffered shared row, and N
+// independent multiply-adds per lane; no CTA barrier (the CTA-wide version
+// spent ~900 cycles per pivot, measured on B200).
+// Minv (shared, ldi) <- M^{-1}; scratch in shared memory: rowbuf 2 (N + 2)
+// doubles (16-byte aligned), rowsel 65 ints.
+// Returns LQ_FLAG_SING on a zero pivot column (the sweep still completes).
+// ---------------------------------------------------------------------------
+#ifdef LQ_GJ_STAMPS
+__device__ long long g_gj_stamps[80];
+#endif
+template <int N>
+__device__ __forceinline__ int warp_gj_inverse(const double *M, int ldm, double *Minv, int ldi,
+                                               double *rowbuf, int *rowsel) {
+  constexpr int NR = (N + 31) / 32;
+  static_assert(NR <= 2 && N % 2 == 0, "warp_gj_inverse: even N <= 64");
+  const int lane = threadIdx.x & 31;
+  double a[NR][N];
+  bool used[NR];
+  int mystep[NR];
+  double dinv[NR];  // reciprocal pivot of the own row(s): rows are scaled at the end
+#pragma unroll
+  for (int rr = 0; rr < NR; rr++) {
+    const int row = lane + 32 * rr;
+    used[rr] = row >= N;  // rows past the matrix never become pivots
+    mystep[rr] = 0;
+    dinv[rr] = 1.0;
+#pragma unroll
+    for (int j = 0; j < N; j++) a[rr][j] = row < N ? M[row * ldm + j] : 0.0;
+  }
+  int flag = 0;
+#pragma unroll
+  for (int p = 0; p < N; p++) {
+    // local candidate, its key and its reciprocal
+#ifdef LQ_GJ_STAMPS
+    if (lane == 0) g_gj_stamps[p] = clock64();
+#endif
+    unsigned key = 0u;
+    int krr = 0;
+    bool cand = false;
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) {
+      if (!used[rr]) {
+        const unsigned k = (unsigned)__double2hiint(fabs(a[rr][p]));
+        if (!cand || k > key) { key = k; krr = rr; }
+        cand = true;
+      }
+    }
+    const double mine = (NR > 1 && krr) ? a[NR - 1][p] : a[0][p];
+    const double myinv = fast_rcp(mine);
+    const unsigned best = __reduce_max_sync(0xffffffffu, cand ? key : 0u);
+    const unsigned ball = __ballot_sync(0xffffffffu, cand && key == best);
+    if (best == 0u) flag |= LQ_FLAG_SING;
+    const int rl = __ffs(ball) - 1;
+    const bool me = lane == rl;
+    // the pivot lane publishes its (unscaled) row and 1/pivot through shared
+    // memory: a broadcast read costs one wavefront, N shuffles cost ~10 cycles each
+    double *rb = rowbuf + (p & 1) * (N + 2);
+    if (me) {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        double2 v;
+        v.x = (NR > 1 && krr) ? a[NR - 1][j] : a[0][j];
+        v.y = (NR > 1 && krr) ? a[NR - 1][j + 1] : a[0][j + 1];
+        *reinterpret_cast<double2 *>(rb + j) = v;
+      }
+      rb[N] = myinv;
+      if (NR > 1) rowsel[64] = krr;
+      rowsel[p] = lane + 32 * krr;
+    }
+    __syncwarp();
+    const double inv = rb[N];
+    const int rsel = NR > 1 ? rowsel[64] : 0;
+    // row_i -= (a_ip / piv) row_r for i != r; the pivot row stays unscaled, the
+    // unit column of the right-hand identity takes the place of column p
+    double m[NR];
+#pragma unroll
+    for (int rr = 0; rr < NR; rr++) {
+      const bool isr = me && rr == rsel;
+      m[rr] = isr ? 0.0 : a[rr][p] * inv;
+      a[rr][p] = isr ? 1.0 : -m[rr];
+      if (isr) { used[rr] = true; mystep[rr] = p; dinv[rr] = inv; }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j += 2) {
+      const double2 prj = *reinterpret_cast<const double2 *>(rb + j);
+#pragma unroll
+      for (int rr = 0; rr < NR; rr++) {
+        if (j != p) a[rr][j] = fma(-m[rr], prj.x, a[rr][j]);
+        if (j + 1 != p) a[rr][j + 1] = fma(-m[rr], prj.y, a[rr][j + 1]);
+      }
+    }
+  }
+  __syncwarp();
+#ifdef LQ_GJ_STAMPS
+  if (lane == 0) g_gj_stamps[N] = clock64();
+#endif
+  // register a[rr][q] / piv of the row chosen at step p is Minv[p][rowsel[q]]
+#pragma unroll
+  for (int rr = 0; rr < NR; rr++) {
+    if (lane + 32 * rr < N) {
+#pragma unroll
+      for (int q = 0; q < N; q++) Minv[mystep[rr] * ldi + rowsel[q]] = a[rr][q] * dinv[rr];
+    }
+  }
+  return flag;
+}
+
+// ---------------------------------------------------------------------------
 // Gauss-Jordan with (implicit) partial pivoting on the augmented n x nc matrix
 // M (ldm), nc > n.  Rows are never swapped: column p is eliminated with the
 // not-yet-used row of largest modulus, the row permutation is kept in piv_s and
@@ -568,6 +688,28 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
     const int p = e / nr, j = e - p * nr;
     X[e] = M[piv_s[p] * ldm + n + j];
   }
+  __syncthreads();
+}
+
+// X = M0^{-1} R for the augmented M = [M0 | R] (n x nc, ldm) of the compiled
+// sizes: warp 0 inverts M0 in registers (warp_gj_inverse), then the whole CTA
+// applies the inverse to R on the tensor cores.  Same contract as
+// cta_gauss_jordan (X: n x (nc - n), ld = nc - n; barriers on entry and exit);
+// ldm should be odd (conflict-free row-per-lane reads).
+// scratch: NX (NX + 1) + 2 (NX + 2) doubles, rowsel: 65 ints.
+template <int NX, int NW>
+__device__ __forceinline__ void cta_inverse_apply(double *M, int ldm, int nc, double *X,
+                                                  double *scratch, int *rowsel, int *st_s) {
+  static_assert(NX > 0, "compiled sizes only");
+  __syncthreads();
+  double *Minv = scratch, *rowbuf = scratch + NX * (NX + 1);
+  if (warp_id_uniform() == 0) {
+    const int fl = warp_gj_inverse<NX>(M, ldm, Minv, NX + 1, rowbuf, rowsel);
+    if (fl && (threadIdx.x & 31) == 0) *st_s |= fl;
+  }
+  __syncthreads();
+  cta_mm_tc<NW>(X, nc - NX, nullptr, 0, 0.0, 1.0, Minv, NX + 1, 1, M + NX, ldm, 1, NX, nc - NX,
+                NX);
   __syncthreads();
 }
 

@@ -207,7 +207,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   double *Guu = G + nx * nm + nx;
   LQ_STAMP2(3);
 #ifndef LQ_SKIP_LDL  // (timing experiments only)
-  if (tid < 32) {
+  if (warp_id_uniform() == 0) {  // uniform branch: no WARPSYNC around the shuffles inside
     const int st = warp_ldlt_any<NU>(Guu, nm, nu);
     if (st && tid == 0) atomicOr(st_s, st);
   }
@@ -307,14 +307,16 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   LQ_STAMP(0);
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
+  const int ldm = NX > 0 ? n3 + 1 : n3;  // odd row stride for the warp inverse
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
   SmemCarver sm(smem_raw);
   double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
   double *Ai = sm.take(n2), *Ji = sm.take(n2);
-  double *M = sm.take(nx * n3), *T1 = sm.take(n2), *T2 = sm.take(n2);
+  double *M = sm.take(nx * ldm), *T1 = sm.take(n2), *T2 = sm.take(n2);
   double *X = sm.take(2 * n2);  // [X_A | X_C], ld = 2 nx
-  __shared__ int st_s, piv_s[64];
+  double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
+  __shared__ int st_s, piv_s[65];
   __shared__ double inv_s[2];
   if (threadIdx.x == 0) st_s = 0;
   const size_t base = ((size_t)b * d.ft.nel + d.ft.off[lev]) * n2;
@@ -336,17 +338,20 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
       const double ai = d.segA[o + i], ci = d.segC[o + i];
       Ai[i] = ai;
       Ji[i] = d.segJ[o + i];
-      M[r * n3 + nx + cc] = ai;
-      M[r * n3 + 2 * nx + cc] = ci;
+      M[r * ldm + nx + cc] = ai;
+      M[r * ldm + 2 * nx + cc] = ci;
       T1[i] = ci;
     }
     __syncthreads();
     LQ_STAMP(2);
-    cta_mmx<TC, LQ_NT2 / 32>(M, n3, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
     __syncthreads();
     LQ_STAMP(3);
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * n3 + i] += 1.0;
-    cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
+    if constexpr (NX > 0)
+      cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, n3, X, inv_scr, piv_s, &st_s);
+    else
+      cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
     // T1 = A_j X_C ; T2 = J_j X_A
     cta_mmx<TC, LQ_NT2 / 32>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
@@ -391,11 +396,13 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
   const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
+  const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
   SmemCarver sm(smem_raw);
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
-  double *M = sm.take(nx * 2 * nx);
+  double *M = sm.take(nx * ldm);
   double *X = sm.take(n2);
-  __shared__ int st_s, piv_s[64];
+  double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
+  __shared__ int st_s, piv_s[65];
   __shared__ double inv_s[2];
   if (threadIdx.x == 0) st_s = 0;
   int c0, c1;
@@ -447,11 +454,14 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
     }
     __syncthreads();
     // M = [I + S C | S A]
-    cta_mmx<TC, LQ_NT2 / 32>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
-    cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
+    if constexpr (NX > 0)
+      cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
+    else
+      cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised
     cta_mmx<TC, LQ_NT2 / 32>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
@@ -533,29 +543,71 @@ __global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
 }
 
 // K4: Psi of element g of level lev+1 = Psi[c1-1] ... Psi[c0] of its children.
-// grid (cnt_{lev+1}, batch)
+// The children are loaded `chunk` at a time and multiplied as a binary tree
+// inside the CTA (log2 rounds of independent products on the tensor cores)
+// instead of R-1 dependent products; the product so far re-enters the next
+// chunk as its first (rightmost) factor.  grid (cnt_{lev+1}, batch), LQ_NT2
+// threads, smem: (chunk + ceil(chunk/2)) * nx*nx doubles.
 template <int NX>
-__global__ void __launch_bounds__(128) psi_compose_kernel(LqDev d, int lev) {
+__global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, int chunk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
-  SmemCarver sm(smem_raw);
-  double *P0 = sm.take(n2), *P1 = sm.take(n2), *Pc = sm.take(n2);
+  double *bufA = reinterpret_cast<double *>(smem_raw);  // chunk blocks
+  double *bufB = bufA + (size_t)chunk * n2;             // ceil(chunk/2) blocks
   const size_t base = ((size_t)b * d.st.nel + d.st.off[lev]) * n2;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) P0[i] = d.segPsi[base + (size_t)(c1 - 1) * n2 + i];
-  __syncthreads();
-  double *P = P0, *Pn = P1;
-  for (int c = c1 - 2; c >= c0; c--) {
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) Pc[i] = d.segPsi[base + (size_t)c * n2 + i];
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int TJ = (nx + 7) >> 3, ntiles = TJ * TJ;
+  double *src = bufA;
+  int have = 0;
+  for (int done = c0; done < c1;) {
+    const int take = min(chunk - have, c1 - done);
+    for (int i = threadIdx.x; i < take * n2; i += blockDim.x)
+      bufA[(size_t)have * n2 + i] = d.segPsi[base + (size_t)done * n2 + i];
+    done += take;
+    int cnt = have + take;
     __syncthreads();
-    cta_mmx<TC>(Pn, nx, nullptr, 0, 0.0, 1.0, P, nx, 1, Pc, nx, 1, nx, nx, nx);
-    double *t = P; P = Pn; Pn = t;
-    __syncthreads();
+    double *dst = bufB;
+    src = bufA;
+    while (cnt > 1) {
+      const int half = cnt >> 1, odd = cnt & 1;
+      // pair (2i+1, 2i) -> src[2i+1] * src[2i]; an unpaired last block is copied
+      if constexpr (TC) {
+        const int wpp = max(1, nwarp / half);  // warps per product
+        const int stride = max(1, nwarp / wpp);
+        for (int pr = warp / wpp; pr < half; pr += stride) {
+          const int wq = warp % wpp;
+          const double *A = src + (size_t)(2 * pr + 1) * n2, *B = src + (size_t)(2 * pr) * n2;
+          double *C = dst + (size_t)pr * n2;
+          for (int ta = wq; ta < ntiles; ta += 2 * wpp) {
+            const int tb = ta + wpp;
+            mm_tc_tile_pair(C, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, B, nx, 1, nx, nx, nx, TJ, ta,
+                            tb < ntiles ? tb : -1, gq, t);
+          }
+        }
+      } else {
+        for (int pr = 0; pr < half; pr++)
+          cta_mm(dst + (size_t)pr * n2, nx, nullptr, 0, 0.0, 1.0, src + (size_t)(2 * pr + 1) * n2,
+                 nx, 1, src + (size_t)(2 * pr) * n2, nx, 1, nx, nx, nx);
+      }
+      if (odd)
+        for (int i = threadIdx.x; i < n2; i += blockDim.x)
+          dst[(size_t)half * n2 + i] = src[(size_t)(cnt - 1) * n2 + i];
+      __syncthreads();
+      cnt = half + odd;
+      double *tmp = src; src = dst; dst = tmp;
+    }
+    if (done < c1 && src != bufA) {
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) bufA[i] = src[i];
+      // the loads of the next chunk touch other blocks; the barrier after them orders this copy
+    }
+    have = 1;
   }
   const size_t o = ((size_t)b * d.st.nel + d.st.off[lev + 1] + g) * n2;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segPsi[o + i] = P[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segPsi[o + i] = src[i];
 }
 
 // LDL^T of Vxx[0] for a free initial state (hqp/Hqp_IpLQDOCP.C:1971-1996 with

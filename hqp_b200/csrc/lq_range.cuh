@@ -48,10 +48,12 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
+  const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
   SmemCarver sm(smem_raw);
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
-  double *M = sm.take(nx * 2 * nx), *X = sm.take(n2);
-  __shared__ int st_s, piv_s[64];
+  double *M = sm.take(nx * ldm), *X = sm.take(n2);
+  double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
+  __shared__ int st_s, piv_s[65];
   __shared__ double inv_s[2];
   if (threadIdx.x == 0) st_s = 0;
   const double *last = gathered + (size_t)(world - 1) * 4 * n2;
@@ -64,11 +66,14 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
       Cg[i] = E[n2 + i];
     }
     __syncthreads();
-    cta_mmx<TC, LQ_NT2 / 32>(M, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(M + nx, 2 * nx, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * 2 * nx + i] += 1.0;
-    cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
+    if constexpr (NX > 0)
+      cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
+    else
+      cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     cta_mmx<TC, LQ_NT2 / 32>(S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);

@@ -139,6 +139,106 @@ __device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH) {
   return cs;
 }
 
+// The same chain run by ONE WARP with the vector in registers (lane i owns rows
+// i, i + 32, ...): every step broadcasts the vector with shuffles and each lane
+// accumulates its own rows -- no shared-memory round trip and no CTA barrier on
+// the dependent path (the CTA version spent most of a step there).  The
+// matrices are staged by the same chunked TMA ring; t[] is in/out.
+template <bool TRANS, int N>
+__device__ __forceinline__ void chain_run_warp(const double *M, const double *a, const double *b,
+                                               double *pre, double *post, int post_shift,
+                                               int first, int dir, int cnt,
+                                               double (&t)[(N + 31) / 32], double *buf,
+                                               uint64_t *bars, int CH) {
+  static_assert(N % 2 == 0, "chain_run_warp reads matrix rows as double2");
+  constexpr int NR = (N + 31) / 32, n2 = N * N;
+  const int lane = threadIdx.x & 31;
+  const size_t chunk_sz = (size_t)CH * (n2 + 2 * N);
+  const int nchunk = (cnt + CH - 1) / CH;
+  auto issue = [&](int c) {
+    const int j0 = c * CH, len = min(CH, cnt - j0);
+    const int e_first = first + j0 * dir;
+    const int e_lo = dir > 0 ? e_first : e_first - (len - 1);
+    double *cb = buf + (size_t)(c & 1) * chunk_sz;
+    uint64_t *bar = &bars[c & 1];
+    const uint32_t bm = (uint32_t)len * n2 * 8, bv = (uint32_t)len * N * 8;
+    mbar_expect_tx(bar, bm + bv + (b ? bv : 0));
+    tma_load_1d(cb, M + (size_t)e_lo * n2, bm, bar);
+    tma_load_1d(cb + (size_t)CH * n2, a + (size_t)e_lo * N, bv, bar);
+    if (b) tma_load_1d(cb + (size_t)CH * (n2 + N), b + (size_t)e_lo * N, bv, bar);
+  };
+  if (lane == 0) {
+    issue(0);
+    if (nchunk > 1) issue(1);
+  }
+  for (int c = 0; c < nchunk; c++) {
+    const int j0 = c * CH, len = min(CH, cnt - j0);
+    const int e_first = first + j0 * dir;
+    const int e_lo = dir > 0 ? e_first : e_first - (len - 1);
+    const double *cb = buf + (size_t)(c & 1) * chunk_sz;
+    mbar_wait(&bars[c & 1], (c >> 1) & 1);
+    for (int jj = 0; jj < len; jj++) {
+      const int e = e_first + jj * dir, o = e - e_lo;
+      const double *Ms = cb + (size_t)o * n2;
+      const double *as = cb + (size_t)CH * n2 + (size_t)o * N;
+      const double *bs = b ? cb + (size_t)CH * (n2 + N) + (size_t)o * N : nullptr;
+      double tb[NR], acc[NR][4];
+#pragma unroll
+      for (int r = 0; r < NR; r++) {
+        const int row = lane + 32 * r;
+        tb[r] = 0.0;
+        if (row < N) {
+          if (pre) pre[(size_t)e * N + row] = t[r];
+          tb[r] = bs ? t[r] + bs[row] : t[r];
+        }
+        acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+      }
+      if (TRANS) {
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+          const double tl = __shfl_sync(0xffffffffu, tb[l >> 5], l & 31);
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            const int row = lane + 32 * r;
+            if (row < N) acc[r][l & 3] = fma(Ms[l * N + row], tl, acc[r][l & 3]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int l = 0; l < N; l += 2) {
+          const double t0 = __shfl_sync(0xffffffffu, tb[l >> 5], l & 31);
+          const double t1 = __shfl_sync(0xffffffffu, tb[(l + 1) >> 5], (l + 1) & 31);
+#pragma unroll
+          for (int r = 0; r < NR; r++) {
+            const int row = lane + 32 * r;
+            if (row < N) {
+              const double2 m = *reinterpret_cast<const double2 *>(Ms + row * N + l);
+              acc[r][l & 2] = fma(m.x, t0, acc[r][l & 2]);
+              acc[r][(l & 2) + 1] = fma(m.y, t1, acc[r][(l & 2) + 1]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < NR; r++) {
+        const int row = lane + 32 * r;
+        if (row < N) {
+          t[r] = as[row] + ((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]));
+          if (post) post[(size_t)(e + post_shift) * N + row] = t[r];
+        }
+      }
+    }
+    if (c + 2 < nchunk) {
+      // this chunk buffer is refilled only after every lane has read it
+      __syncwarp();
+      if (lane == 0) {
+        fence_proxy_async();
+        issue(c + 2);
+      }
+    }
+  }
+}
+
 // Stage-parallel passes run one WARP per stage (no CTA barriers, coalesced
 // column-wise reads of the stage blocks) and several stages per warp, so that a
 // pass is a few hundred fat CTAs instead of K tiny ones (CTA launch rate, not
@@ -204,46 +304,89 @@ __global__ void __launch_bounds__(128) solve_pre_kernel(
 }
 
 // ---- fine chains -------------------------------------------------------------
-// grid (P, batch), block = 4 * ceil32(nx) threads.
+// grid (P, batch).  NX > 0: one warp per chain (chain_run_warp), 32 threads;
+// NX == 0: any nx, block = 4 * ceil32(nx) threads (chain_run).
 // back: mode 0 from 0, writes segv0[s]; mode 1 from segvb[s], stores v[k]
+template <int NX>
 __global__ void solve_back_kernel(LqDev d, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx;
+  const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
-  const int i = threadIdx.x >> 2;
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
   const size_t ks0 = (size_t)b * d.K;
-  double t = 0.0;
-  if (mode == 1 && i < nx) t = d.segvb[so + i];
-  t = chain_run<true>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx,
-                      nullptr, mode == 1 ? d.v + (size_t)b * (d.K + 1) * nx : nullptr, 0,
-                      kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec, LQ_RING);
-  if (mode == 0 && i < nx && (threadIdx.x & 3) == 0) d.segv0[so + i] = t;
+  double *vout = mode == 1 ? d.v + (size_t)b * (d.K + 1) * nx : nullptr;
+  if constexpr (NX > 0) {
+    constexpr int NR = (NX + 31) / 32;
+    const int lane = threadIdx.x;
+    double t[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++)
+      t[r] = (mode == 1 && lane + 32 * r < NX) ? d.segvb[so + lane + 32 * r] : 0.0;
+    chain_run_warp<true, NX>(d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx, nullptr, vout,
+                             0, kb - 1, -1, kb - ka, t, cs.ring, cs.bars, LQ_RING);
+    if (mode == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+        if (lane + 32 * r < NX) d.segv0[so + lane + 32 * r] = t[r];
+    }
+  } else {
+    const int i = threadIdx.x >> 2;
+    double t = 0.0;
+    if (mode == 1 && i < nx) t = d.segvb[so + i];
+    t = chain_run<true>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx,
+                        nullptr, vout, 0, kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec,
+                        LQ_RING);
+    if (mode == 0 && i < nx && (threadIdx.x & 3) == 0) d.segv0[so + i] = t;
+  }
 }
 
 // fwd: mode 0 from x_a = 0, writes segx0[s] (x at the segment end);
 //      mode 1 from segxa[s], stores x[k], k = a..b
+template <int NX>
 __global__ void solve_fwd_kernel(LqDev d, int mode) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx;
+  const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
-  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
   const size_t ks0 = (size_t)b * d.K;
   double *xb = d.x + (size_t)b * (d.K + 1) * nx;
-  double t = 0.0;
-  if (mode == 1 && i < nx) {
-    t = d.segxa[so + i];
-    if (part == 0) xb[(size_t)ka * nx + i] = t;
+  if constexpr (NX > 0) {
+    constexpr int NR = (NX + 31) / 32;
+    const int lane = threadIdx.x;
+    double t[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const int row = lane + 32 * r;
+      t[r] = 0.0;
+      if (mode == 1 && row < NX) {
+        t[r] = d.segxa[so + row];
+        xb[(size_t)ka * nx + row] = t[r];
+      }
+    }
+    chain_run_warp<false, NX>(d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
+                              mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
+                              LQ_RING);
+    if (mode == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+        if (lane + 32 * r < NX) d.segx0[so + lane + 32 * r] = t[r];
+    }
+  } else {
+    const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+    double t = 0.0;
+    if (mode == 1 && i < nx) {
+      t = d.segxa[so + i];
+      if (part == 0) xb[(size_t)ka * nx + i] = t;
+    }
+    t = chain_run<false>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
+                         mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
+                         cs.tvec, LQ_RING);
+    if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = t;
   }
-  t = chain_run<false>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
-                       mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
-                       cs.tvec, LQ_RING);
-  if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = t;
 }
 
 // ---- hierarchy scans -----------------------------------------------------------
@@ -255,51 +398,67 @@ __global__ void solve_fwd_kernel(LqDev d, int mode) {
 // phase 2 (down): CTA g walks the children of (lev+1, g) from that element's
 //                 vb / xa, recording the children's values
 // backward (BACK = true): children visited last -> first with Psi'.
-template <bool BACK>
+template <bool BACK, int NX>
 __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__restrict__ r2,
                                   int ring_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nx = d.nx;
+  const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
   const int g = blockIdx.x, b = blockIdx.y;
-  const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
   const size_t eb = (size_t)b * d.st.nel + d.st.off[lev];           // first element of level
   const size_t pb = (size_t)b * d.st.nel + (phase == 1 ? 0 : d.st.off[lev + 1]);
   double *in0 = BACK ? d.segv0 : d.segx0;   // zero-boundary solutions
   double *bnd = BACK ? d.segvb : d.segxa;   // boundary values
-  int c0, c1;
-  double t = 0.0;
-  if (phase == 1) {
-    c0 = 0;
-    c1 = d.st.cnt[lev];
-    if (BACK) {
-      if (i < nx) t = d.v[((size_t)b * (d.K + 1) + d.K) * nx + i];
-    } else if (d.has_prev) {
-      // horizon split: the state at stage 0 comes from the ranks before
-      if (i < nx) t = d.xstart[i];
-    } else if (d.fixed_x0) {
-      // x_0 = -a_0 (hqp/Hqp_IpLQDOCP.C:2099-2100)
-      if (i < nx) t = -r2[(size_t)b * d.me + (size_t)d.K * nx + i];
-    } else {
-      // x_0 = -Vxx[0]^{-1} v[0] (:2111-2117)
-      double *scr = cs.tvec + 2 * nx;
-      if (threadIdx.x < nx) scr[threadIdx.x] = -d.v[(size_t)b * (d.K + 1) * nx + threadIdx.x];
-      __syncthreads();
-      if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * nx * nx, nx, nx, scr, 1);
-      __syncthreads();
-      if (i < nx) t = scr[i];
-      __syncthreads();
-    }
-  } else {
+  // start value of row `row` (phase 1: the boundary condition of the horizon)
+  double *scr = cs.tvec;
+  if (phase == 1 && !BACK && !d.has_prev && !d.fixed_x0) {
+    // x_0 = -Vxx[0]^{-1} v[0] (hqp/Hqp_IpLQDOCP.C:2111-2117)
+    for (int r = threadIdx.x; r < nx; r += blockDim.x)
+      scr[r] = -d.v[(size_t)b * (d.K + 1) * nx + r];
+    __syncthreads();
+    // runtime dims on purpose: a serial one-off solve, not worth unrolling
+    if (threadIdx.x == 0) thread_ldlt_solve(d.V0f + (size_t)b * d.nx * d.nx, d.nx, d.nx, scr, 1);
+    __syncthreads();
+  }
+  auto start = [&](int row) -> double {
+    if (row >= nx) return 0.0;
+    if (phase == 0) return 0.0;
+    if (phase == 2) return bnd[(pb + g) * nx + row];
+    if (BACK) return d.v[((size_t)b * (d.K + 1) + d.K) * nx + row];
+    if (d.has_prev) return d.xstart[row];  // horizon split: state from the ranks before
+    if (d.fixed_x0)                         // x_0 = -a_0 (hqp/Hqp_IpLQDOCP.C:2099-2100)
+      return -r2[(size_t)b * d.me + (size_t)d.K * nx + row];
+    return scr[row];
+  };
+  int c0 = 0, c1 = d.st.cnt[lev];
+  if (phase != 1) {
     c0 = g * d.st.R;
     c1 = min(d.st.cnt[lev], c0 + d.st.R);
-    if (phase == 2 && i < nx) t = bnd[(pb + g) * nx + i];
   }
   const int first = BACK ? c1 - 1 : c0, dir = BACK ? -1 : +1;
-  t = chain_run<BACK>(nx, d.use_tma, d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
-                      phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir, c1 - c0, t,
-                      cs.ring, cs.bars, cs.tvec, ring_n);
-  if (phase == 0 && i < nx && part == 0) in0[(pb + g) * nx + i] = t;
+  if constexpr (NX > 0) {
+    constexpr int NR = (NX + 31) / 32;
+    const int lane = threadIdx.x;
+    double t[NR];
+#pragma unroll
+    for (int r = 0; r < NR; r++) t[r] = start(lane + 32 * r);
+    chain_run_warp<BACK, NX>(d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
+                             phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir,
+                             c1 - c0, t, cs.ring, cs.bars, ring_n);
+    if (phase == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; r++)
+        if (lane + 32 * r < NX) in0[(pb + g) * nx + lane + 32 * r] = t[r];
+    }
+  } else {
+    const int i = threadIdx.x >> 2, part = threadIdx.x & 3;
+    double t = start(i);
+    __syncthreads();  // scr (inside tvec) is reused by the chain
+    t = chain_run<BACK>(nx, d.use_tma, d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
+                        phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir, c1 - c0, t,
+                        cs.ring, cs.bars, cs.tvec, ring_n);
+    if (phase == 0 && i < nx && part == 0) in0[(pb + g) * nx + i] = t;
+  }
 }
 
 // warp-cooperative solve of (L D L') y = b, y in shared memory (m <= 32 per pass
