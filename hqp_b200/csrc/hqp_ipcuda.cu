@@ -14,7 +14,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,8 +93,14 @@ struct hqpcu_handle {
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
   int max_el = 0;  // elements per instance the seg* arrays were sized for
   int n_sm = 148, k1_ctas_per_sm = 3;
-  int ring_scan = 8, psi_chunk = 2;
+  int ring_scan = 8, psi_chunk = 2, ring_chain = LQ_RING;
   size_t smem_scan = 0;
+  // CUDA graphs of the fixed launch sequences (factor; step per pointer set):
+  // replayed with one cudaGraphLaunch instead of 13-21 dependent launches
+  struct GraphEntry { std::vector<const void *> key; cudaGraphExec_t exec; long long launches; };
+  std::vector<GraphEntry> graphs;
+  bool use_graphs = true;
+  cudaStream_t cap_stream = nullptr;  // capture happens here (the user stream may be stream 0)
   // horizon split: right-hand sides remembered between the three step phases
   const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
   bool ranged() const { return d.has_prev || d.has_next; }
@@ -119,6 +127,63 @@ struct hqpcu_handle {
       (h)->spans.push_back(sp_);                                              \
     }                                                                         \
   } while (0)
+
+static void drop_graphs(hqpcu_handle *h) {
+  for (auto &g : h->graphs) cudaGraphExecDestroy(g.exec);
+  h->graphs.clear();
+}
+
+// Run `body` (a fixed sequence of launches on h->stream that depends only on
+// `key`) through a cached CUDA graph: captured on first use, replayed afterwards.
+template <class F>
+static int run_graphed(hqpcu_handle *h, std::vector<const void *> key, F &&body) {
+  if (!h->use_graphs || h->profiling || !h->cap_stream) return body();
+  for (auto &g : h->graphs)
+    if (g.key == key) {
+      CU(cudaGraphLaunch(g.exec, h->stream));
+      h->launches += g.launches;
+      return HQPCU_OK;
+    }
+  cudaStream_t user = h->stream;
+  const long long l0 = h->launches;
+  h->stream = h->cap_stream;
+  cudaError_t e = cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) {  // capture unavailable: plain launches
+    cudaGetLastError();
+    h->stream = user;
+    h->use_graphs = false;
+    return body();
+  }
+  int rc = body();
+  cudaGraph_t graph = nullptr;
+  e = cudaStreamEndCapture(h->cap_stream, &graph);
+  h->stream = user;
+  const long long nl = h->launches - l0;
+  h->launches = l0;
+  if (rc || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    if (rc) return rc;
+    h->use_graphs = false;
+    return body();
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    h->use_graphs = false;
+    return body();
+  }
+  if (h->graphs.size() >= 16) {  // bounded cache: drop the oldest
+    cudaGraphExecDestroy(h->graphs.front().exec);
+    h->graphs.erase(h->graphs.begin());
+  }
+  h->graphs.push_back({std::move(key), exec, nl});
+  CU(cudaGraphLaunch(exec, h->stream));
+  h->launches += nl;
+  return HQPCU_OK;
+}
 
 template <typename T>
 static int dev_alloc(hqpcu_handle *h, T **p, size_t count) {
@@ -159,6 +224,7 @@ static void build_tree(LqTree &t, int P, int R) {
 
 // segments per instance, stages per segment and the hierarchies above them
 static void choose_segments(hqpcu_handle *h, int nseg) {
+  drop_graphs(h);  // the launch geometry is about to change
   const int K = h->dims.K;
   LqDev &d = h->d;
   int P = nseg;
@@ -239,6 +305,15 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   hqpcu_handle *h = new hqpcu_handle;
   h->dims = *dims;
   h->device = dims->device;
+  {
+    const char *env = getenv("HQPCU_GRAPHS");  // "0": plain launches (debugging, ncu per-kernel lists)
+    h->use_graphs = !(env && env[0] == '0');
+    if (h->use_graphs &&
+        cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      h->cap_stream = nullptr;
+    }
+  }
   h->nseg_req = dims->nseg;
   LqDev &d = h->d;
   memset(&d, 0, sizeof d);
@@ -433,7 +508,11 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   // children of one group multiplied as a tree in shared memory, in chunks that fit
   h->psi_chunk = std::max(2, std::min(LQ_SCAN_R, (int)((192 * 1024) / (nn * sizeof(double)) * 2 / 3)));
   h->smem_psi = (size_t)(h->psi_chunk + (h->psi_chunk + 1) / 2) * nn * sizeof(double);
-  h->smem_chain = (pad2((size_t)2 * LQ_RING * (nx * nx + 2 * nx)) + pad2((size_t)3 * nx)) * sizeof(double) +
+  {
+    const char *env = getenv("HQPCU_CHAIN_CHUNK");  // tuning knob: stages per TMA chunk
+    h->ring_chain = env ? std::max(1, atoi(env)) : LQ_RING;
+  }
+  h->smem_chain = (pad2((size_t)2 * h->ring_chain * (nx * nx + 2 * nx)) + pad2((size_t)3 * nx)) * sizeof(double) +
                   2 * sizeof(uint64_t) + 16;
   // the hierarchy scans run few CTAs: stage every matrix of a group up front
   h->ring_scan = std::max(1, std::min(LQ_SCAN_R, (int)((100 * 1024) / ((nx * nx + 2 * nx) * sizeof(double)))));
@@ -480,6 +559,8 @@ int hqpcu_destroy(hqpcu_handle *h) {
   if (!h) return HQPCU_OK;
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  drop_graphs(h);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (void *p : h->allocs) cudaFree(p);
   ips_free(h);
   if (h->res_host) cudaFreeHost(h->res_host);
@@ -625,12 +706,14 @@ static int launch_factor(hqpcu_handle *h) {
     g_err = "this handle is a stage range of a split horizon: use hqpcu_range_*";
     return HQPCU_E_UNSUPPORTED;
   }
-  int rc = launch_factor_up(h);
-  if (rc) return rc;
-  rc = launch_factor_down(h);
-  if (rc) return rc;
-  if (h->q.n_eq) return launch_eq_factor(h);
-  return HQPCU_OK;
+  int rc = run_graphed(h, {(const void *)(uintptr_t)1}, [&]() {
+    int r = launch_factor_up(h);
+    if (!r) r = launch_factor_down(h);
+    if (!r && h->q.n_eq) r = launch_eq_factor(h);
+    return r;
+  });
+  if (!rc) h->factored = true;
+  return rc;
 }
 
 static int read_status(hqpcu_handle *h) {
@@ -701,7 +784,7 @@ static void launch_back(hqpcu_handle *h, int mode) {
   const LqDev &d = h->d;
   const dim3 gseg(d.P, d.batch);
   cudaStream_t s = h->stream;
-#define L_(NX_) LAUNCH(h, solve_back_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode))
+#define L_(NX_) LAUNCH(h, solve_back_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode, h->ring_chain))
   LQ_DISPATCH_NX(d.nx, d.nu, L_);
 #undef L_
 }
@@ -709,7 +792,7 @@ static void launch_fwd(hqpcu_handle *h, int mode) {
   const LqDev &d = h->d;
   const dim3 gseg(d.P, d.batch);
   cudaStream_t s = h->stream;
-#define L_(NX_) LAUNCH(h, solve_fwd_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode))
+#define L_(NX_) LAUNCH(h, solve_fwd_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode, h->ring_chain))
   LQ_DISPATCH_NX(d.nx, d.nu, L_);
 #undef L_
 }
@@ -798,8 +881,9 @@ static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
   return rc;
 }
 
-static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
-                       const double *r4, double *dx, double *dy, double *dz, double *dw) {
+static int launch_step_plain(hqpcu_handle *h, const double *r1, const double *r2,
+                             const double *r3, const double *r4, double *dx, double *dy,
+                             double *dz, double *dw) {
   int rc = launch_step_base(h, r1, r2, r3, r4, dx, dy, dz, dw);
   if (rc || !h->q.n_eq) return rc;
   const LqDev &d = h->d;
@@ -809,6 +893,17 @@ static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, cons
   LAUNCH(h, eq_combine_kernel, <<<blocks, 256, 0, s>>>(d, h->q, dx, dy, dz, dw));
   CU(cudaGetLastError());
   return HQPCU_OK;
+}
+
+static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                       const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  if (!h->factored) {
+    g_err = "step before factor";
+    return HQPCU_E_NULL;
+  }
+  return run_graphed(h, {(const void *)(uintptr_t)2, r1, r2, r3, r4, dx, dy, dz, dw}, [&]() {
+    return launch_step_plain(h, r1, r2, r3, r4, dx, dy, dz, dw);
+  });
 }
 
 int hqpcu_step_dev(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,

@@ -39,6 +39,10 @@
 #define LQ_STAMP(i) do { } while (0)
 #endif
 
+#ifndef LQ_K13_MINB
+#define LQ_K13_MINB 3  // resident CTAs per SM the segment kernels are compiled for
+#endif
+
 #ifndef LQ_USE_DMMA
 #define LQ_USE_DMMA 1  // FP64 tensor-core block products in the templated kernels
 #endif
@@ -241,7 +245,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
 // K1: condense segment s of instance b with zero terminal cost.
 // ---------------------------------------------------------------------------
 template <int NX, int NU>
-__global__ void __launch_bounds__(128) seg_element_kernel(LqDev d) {
+__global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_element_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
 // K3: Riccati recursion inside segment s from its terminal Vb.
 // ---------------------------------------------------------------------------
 template <int NX, int NU>
-__global__ void __launch_bounds__(128) seg_riccati_kernel(LqDev d) {
+__global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;

@@ -25,7 +25,7 @@
 
 #include "lq_device.cuh"
 
-#define LQ_RING 4  // stages per staged chunk of a segment chain (two chunk buffers)
+#define LQ_RING 4  // default stages per staged chunk of a segment chain (two chunk buffers)
 
 // One sequential affine chain executed by a whole CTA (4 lanes per row):
 //     for j = 0..cnt-1, e = first + j*dir:
@@ -139,18 +139,39 @@ __device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH) {
   return cs;
 }
 
-// The same chain run by ONE WARP with the vector in registers (lane i owns rows
-// i, i + 32, ...): every step broadcasts the vector with shuffles and each lane
-// accumulates its own rows -- no shared-memory round trip and no CTA barrier on
-// the dependent path (the CTA version spent most of a step there).  The
-// matrices are staged by the same chunked TMA ring; t[] is in/out.
+// shared-memory loads as opaque PTX (keeps nvcc from fusing / re-vectorising the
+// prefetch and the dependent-path loads; a volatile variant that also pins the
+// order for ptxas measured 3 % slower in the full pipeline)
+__device__ __forceinline__ double lds_ordered(const double *p) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];"
+               : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+__device__ __forceinline__ double2 lds_ordered2(const double *p) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+               : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+  return v;
+}
+
+// The same chain run by ONE WARP (lane i owns rows i, i + 32, ...): no CTA
+// barrier on the dependent path.  Per step the vector goes through a
+// double-buffered shared row (one store per lane, __syncwarp, broadcast reads:
+// ~40 cycles, against ~5 per shuffled element) and each lane accumulates its own
+// rows in four independent chains.
+//   TRANS : lane i reads column i of M, M[l][i]: consecutive lanes, no conflict
+//   !TRANS: lane i reads row i in the skewed order l' = (l + i) mod N, so that
+//           the 32 simultaneous reads M[i][l'] fall into distinct banks (row
+//           stride N = 20, 12, 40 doubles would otherwise collide 2- to 8-way)
+// The matrices are staged by the chunked TMA ring; t[] is in/out.  tvec: 2 N.
 template <bool TRANS, int N>
 __device__ __forceinline__ void chain_run_warp(const double *M, const double *a, const double *b,
                                                double *pre, double *post, int post_shift,
                                                int first, int dir, int cnt,
                                                double (&t)[(N + 31) / 32], double *buf,
-                                               uint64_t *bars, int CH) {
-  static_assert(N % 2 == 0, "chain_run_warp reads matrix rows as double2");
+                                               uint64_t *bars, double *tvec, int CH) {
+  static_assert(N % 4 == 0, "chain_run_warp: four accumulator chains, double2 reads");
   constexpr int NR = (N + 31) / 32, n2 = N * N;
   const int lane = threadIdx.x & 31;
   const size_t chunk_sz = (size_t)CH * (n2 + 2 * N);
@@ -171,63 +192,102 @@ __device__ __forceinline__ void chain_run_warp(const double *M, const double *a,
     issue(0);
     if (nchunk > 1) issue(1);
   }
+  int par = 0;
+  // matrix entries of one lane for one step (row `rs`): column rs of M (TRANS) or
+  // row rs in skewed order
+  auto load_m = [&](double (&m)[N], const double *Ms, int rs) {
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+      if (TRANS) {
+        m[l] = lds_ordered(Ms + l * N + rs);
+      } else {
+        const int cidx = (l + rs < N) ? l + rs : l + rs - N;  // (l + row) mod N
+        m[l] = lds_ordered(Ms + rs * N + cidx);
+      }
+    }
+  };
+  // the vector as this lane needs it: all of it (TRANS) or in the skewed order
+  auto load_t = [&](double (&tl)[N], const double *tv, int rs) {
+    if (TRANS) {
+#pragma unroll
+      for (int l = 0; l < N; l += 2) {
+        const double2 ta = lds_ordered2(tv + l);
+        tl[l] = ta.x;
+        tl[l + 1] = ta.y;
+      }
+    } else {
+#pragma unroll
+      for (int l = 0; l < N; l++) {
+        const int cidx = (l + rs < N) ? l + rs : l + rs - N;
+        tl[l] = lds_ordered(tv + cidx);
+      }
+    }
+  };
+  auto dot = [&](const double (&m)[N], const double (&tl)[N]) -> double {
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+    for (int l = 0; l < N; l += 4) {
+      acc0 = fma(m[l], tl[l], acc0);
+      acc1 = fma(m[l + 1], tl[l + 1], acc1);
+      acc2 = fma(m[l + 2], tl[l + 2], acc2);
+      acc3 = fma(m[l + 3], tl[l + 3], acc3);
+    }
+    return (acc0 + acc1) + (acc2 + acc3);
+  };
   for (int c = 0; c < nchunk; c++) {
     const int j0 = c * CH, len = min(CH, cnt - j0);
     const int e_first = first + j0 * dir;
     const int e_lo = dir > 0 ? e_first : e_first - (len - 1);
     const double *cb = buf + (size_t)(c & 1) * chunk_sz;
     mbar_wait(&bars[c & 1], (c >> 1) & 1);
-    for (int jj = 0; jj < len; jj++) {
+    // one step; the matrix entries of the NEXT step (same chunk) are requested
+    // before this step's multiply-adds: they do not depend on the chain, and the
+    // ~30 shared-memory loads of a step otherwise sit on its dependent path
+    auto step = [&](int jj, double (&mcur)[N], double (&mnext)[N]) {
       const int e = e_first + jj * dir, o = e - e_lo;
       const double *Ms = cb + (size_t)o * n2;
       const double *as = cb + (size_t)CH * n2 + (size_t)o * N;
       const double *bs = b ? cb + (size_t)CH * (n2 + N) + (size_t)o * N : nullptr;
-      double tb[NR], acc[NR][4];
+      double *tv = tvec + par * N;
+      par ^= 1;
 #pragma unroll
       for (int r = 0; r < NR; r++) {
         const int row = lane + 32 * r;
-        tb[r] = 0.0;
         if (row < N) {
           if (pre) pre[(size_t)e * N + row] = t[r];
-          tb[r] = bs ? t[r] + bs[row] : t[r];
-        }
-        acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
-      }
-      if (TRANS) {
-#pragma unroll
-        for (int l = 0; l < N; l++) {
-          const double tl = __shfl_sync(0xffffffffu, tb[l >> 5], l & 31);
-#pragma unroll
-          for (int r = 0; r < NR; r++) {
-            const int row = lane + 32 * r;
-            if (row < N) acc[r][l & 3] = fma(Ms[l * N + row], tl, acc[r][l & 3]);
-          }
-        }
-      } else {
-#pragma unroll
-        for (int l = 0; l < N; l += 2) {
-          const double t0 = __shfl_sync(0xffffffffu, tb[l >> 5], l & 31);
-          const double t1 = __shfl_sync(0xffffffffu, tb[(l + 1) >> 5], (l + 1) & 31);
-#pragma unroll
-          for (int r = 0; r < NR; r++) {
-            const int row = lane + 32 * r;
-            if (row < N) {
-              const double2 m = *reinterpret_cast<const double2 *>(Ms + row * N + l);
-              acc[r][l & 2] = fma(m.x, t0, acc[r][l & 2]);
-              acc[r][(l & 2) + 1] = fma(m.y, t1, acc[r][(l & 2) + 1]);
-            }
-          }
+          tv[row] = bs ? t[r] + bs[row] : t[r];
         }
       }
+      __syncwarp();
 #pragma unroll
       for (int r = 0; r < NR; r++) {
         const int row = lane + 32 * r;
-        if (row < N) {
-          t[r] = as[row] + ((acc[r][0] + acc[r][1]) + (acc[r][2] + acc[r][3]));
+        const bool act = row < N;
+        const int rs = act ? row : 0;
+        double s, tl[N];
+        load_t(tl, tv, rs);  // first in the queue: these are on the dependent path
+        if (NR == 1) {
+          if (jj + 1 < len) load_m(mnext, Ms + dir * n2, rs);
+          s = dot(mcur, tl);
+        } else {
+          double m[N];
+          load_m(m, Ms, rs);
+          s = dot(m, tl);
+        }
+        if (act) {
+          t[r] = as[row] + s;
           if (post) post[(size_t)(e + post_shift) * N + row] = t[r];
         }
       }
+    };
+    double mA[N], mB[N];
+    if (NR == 1) load_m(mA, cb + (size_t)(e_first - e_lo) * n2, lane < N ? lane : 0);
+    int jj = 0;
+    for (; jj + 1 < len; jj += 2) {
+      step(jj, mA, mB);
+      step(jj + 1, mB, mA);
     }
+    if (jj < len) step(jj, mA, mB);
     if (c + 2 < nchunk) {
       // this chunk buffer is refilled only after every lane has read it
       __syncwarp();
@@ -308,10 +368,10 @@ __global__ void __launch_bounds__(128) solve_pre_kernel(
 // NX == 0: any nx, block = 4 * ceil32(nx) threads (chain_run).
 // back: mode 0 from 0, writes segv0[s]; mode 1 from segvb[s], stores v[k]
 template <int NX>
-__global__ void solve_back_kernel(LqDev d, int mode) {
+__global__ void solve_back_kernel(LqDev d, int mode, int ring_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
@@ -325,7 +385,7 @@ __global__ void solve_back_kernel(LqDev d, int mode) {
     for (int r = 0; r < NR; r++)
       t[r] = (mode == 1 && lane + 32 * r < NX) ? d.segvb[so + lane + 32 * r] : 0.0;
     chain_run_warp<true, NX>(d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx, nullptr, vout,
-                             0, kb - 1, -1, kb - ka, t, cs.ring, cs.bars, LQ_RING);
+                             0, kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec, ring_n);
     if (mode == 0) {
 #pragma unroll
       for (int r = 0; r < NR; r++)
@@ -337,7 +397,7 @@ __global__ void solve_back_kernel(LqDev d, int mode) {
     if (mode == 1 && i < nx) t = d.segvb[so + i];
     t = chain_run<true>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.wv + ks0 * nx, d.q + ks0 * nx,
                         nullptr, vout, 0, kb - 1, -1, kb - ka, t, cs.ring, cs.bars, cs.tvec,
-                        LQ_RING);
+                        ring_n);
     if (mode == 0 && i < nx && (threadIdx.x & 3) == 0) d.segv0[so + i] = t;
   }
 }
@@ -345,10 +405,10 @@ __global__ void solve_back_kernel(LqDev d, int mode) {
 // fwd: mode 0 from x_a = 0, writes segx0[s] (x at the segment end);
 //      mode 1 from segxa[s], stores x[k], k = a..b
 template <int NX>
-__global__ void solve_fwd_kernel(LqDev d, int mode) {
+__global__ void solve_fwd_kernel(LqDev d, int mode, int ring_n) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw, LQ_RING);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
@@ -369,7 +429,7 @@ __global__ void solve_fwd_kernel(LqDev d, int mode) {
     }
     chain_run_warp<false, NX>(d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
                               mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
-                              LQ_RING);
+                              cs.tvec, ring_n);
     if (mode == 0) {
 #pragma unroll
       for (int r = 0; r < NR; r++)
@@ -384,7 +444,7 @@ __global__ void solve_fwd_kernel(LqDev d, int mode) {
     }
     t = chain_run<false>(nx, d.use_tma, d.Phi + ks0 * nx * nx, d.c + ks0 * nx, nullptr, nullptr,
                          mode == 1 ? xb : nullptr, 1, ka, +1, kb - ka, t, cs.ring, cs.bars,
-                         cs.tvec, LQ_RING);
+                         cs.tvec, ring_n);
     if (mode == 0 && i < nx && part == 0) d.segx0[so + i] = t;
   }
 }
@@ -444,7 +504,7 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
     for (int r = 0; r < NR; r++) t[r] = start(lane + 32 * r);
     chain_run_warp<BACK, NX>(d.segPsi + eb * nx * nx, in0 + eb * nx, nullptr,
                              phase == 0 ? nullptr : bnd + eb * nx, nullptr, 0, first, dir,
-                             c1 - c0, t, cs.ring, cs.bars, ring_n);
+                             c1 - c0, t, cs.ring, cs.bars, cs.tvec, ring_n);
     if (phase == 0) {
 #pragma unroll
       for (int r = 0; r < NR; r++)
