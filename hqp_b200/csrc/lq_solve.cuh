@@ -139,18 +139,18 @@ __device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH) {
   return cs;
 }
 
-// shared-memory loads as opaque PTX (keeps nvcc from fusing / re-vectorising the
-// prefetch and the dependent-path loads; a volatile variant that also pins the
-// order for ptxas measured 3 % slower in the full pipeline)
+// shared-memory loads as PTX: `asm volatile` keeps nvcc from moving or merging
+// them (the prefetch and the dependent-path loads stay where they are written),
+// the plain ld.shared leaves the final schedule to ptxas
 __device__ __forceinline__ double lds_ordered(const double *p) {
   double v;
-  asm("ld.shared.f64 %0, [%1];"
+  asm volatile("ld.shared.f64 %0, [%1];"
                : "=d"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)));
   return v;
 }
 __device__ __forceinline__ double2 lds_ordered2(const double *p) {
   double2 v;
-  asm("ld.shared.v2.f64 {%0, %1}, [%2];"
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
                : "=d"(v.x), "=d"(v.y) : "r"((uint32_t)__cvta_generic_to_shared(p)));
   return v;
 }
