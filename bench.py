@@ -38,6 +38,10 @@ WORKLOADS = {
     "c5s": dict(nx=40, nu=10, K=100000, batch=1,
                 name="long-horizon LQ-DOCP nx=40 nu=10 K=100000 (slice of BASELINE configs[4])"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel
+# (seg_riccati_kernel) from the committed `ncu --set full` capture; null where no
+# capture exists.  Compare with K * algorithmic bytes per stage (C2: 160.4 MB).
+NCU_TRAFFIC = {"c2": (124.024064e6 + 51.595776e6, "profiles/r01_ncu_full_k1k3_v4.md")}
 METRIC = "LQ-DOCP KKT factor+solve stages/s"
 UNIT = "stages/s"
 
@@ -350,7 +354,10 @@ def run_ours(args, wl):
         kms = per[kname]
         ach = K * batch * bf / (kms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": how,
+                    "unit": "GB/s", "frac": ach / peak,
+                    "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
+                    "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                    "algorithmic_bytes_per_launch": K * batch * bf, "peak_source": how,
                     "algorithmic_bytes_per_stage": {"factor": bf, "step": bs},
                     "algorithmic_flops_per_stage": {"factor": ff, "step": fs},
                     "kernel_ms_per_unit": per, "dominant_kernel": dom,
