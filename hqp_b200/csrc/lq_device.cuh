@@ -275,26 +275,117 @@ __device__ __forceinline__ void mm_tc_tile_pair(double *C, int ldc, const double
   }
 }
 
+// R x S block of 8x8 tiles (tile rows ti0.., tile columns tj0..) by one warp:
+// per k-step R fragments of A and S of B feed R*S DMMAs, so a 1x2 block loads 3
+// fragments for 2 DMMAs and a 3x1 block 4 for 3 (a lone tile: 2 for 1) -- the
+// segment kernels are bound by shared-memory wavefronts, most of them these
+// fragment loads (profiles/r01_ncu_full_k1k3_v4.md).  The C tile is read and
+// written as double2 when the row strides are even (conflict-free for strides
+// = 8 mod 16 doubles, half the instructions otherwise).
+template <int R, int S>
+__device__ __forceinline__ void mm_tc_block(double *C, int ldc, const double *C0, int ldc0,
+                                            double beta, double alpha, const double *A, int ar,
+                                            int ac, const double *B, int br, int bc, int M,
+                                            int N, int Kd, int ti0, int tj0, int nr, int g,
+                                            int t) {
+  double acc[R][S][2];
+  bool va[R], vb[S];
+  const double *ap[R], *bp[S];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    const int i0 = (ti0 + r) << 3;
+    va[r] = r < nr && ((i0 + 8 <= M) || (i0 + g < M));
+    ap[r] = A + (i0 + g) * ar + t * ac;
+#pragma unroll
+    for (int s = 0; s < S; s++) acc[r][s][0] = acc[r][s][1] = 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < S; s++) {
+    const int j0 = (tj0 + s) << 3;
+    vb[s] = (j0 + 8 <= N) || (j0 + g < N);
+    bp[s] = B + (j0 + g) * bc + t * br;
+  }
+#pragma unroll
+  for (int k0 = 0; k0 < Kd; k0 += 4) {
+    const bool vk = (k0 + 4 <= Kd) || (k0 + t < Kd);
+    double af[R], bf[S];
+#pragma unroll
+    for (int r = 0; r < R; r++) af[r] = (va[r] && vk) ? ap[r][k0 * ac] : 0.0;
+#pragma unroll
+    for (int s = 0; s < S; s++) bf[s] = (vb[s] && vk) ? bp[s][k0 * br] : 0.0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      if (r < nr) {
+#pragma unroll
+        for (int s = 0; s < S; s++) dmma_m8n8k4(acc[r][s][0], acc[r][s][1], af[r], bf[s]);
+      }
+    }
+  }
+  const bool vec = (ldc % 2 == 0) && (N % 2 == 0) && (C0 == nullptr || ldc0 % 2 == 0);
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (r >= nr) continue;
+    const int i0 = (ti0 + r) << 3, ic = i0 + g;
+    const bool vr = (i0 + 8 <= M) || (ic < M);
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+      const int j0 = (tj0 + s) << 3, jc = j0 + 2 * t;
+      const bool v0 = vr && ((j0 + 8 <= N) || (jc < N));
+      const bool v1 = vr && ((j0 + 8 <= N) || (jc + 1 < N));
+      double r0 = alpha * acc[r][s][0], r1 = alpha * acc[r][s][1];
+      if (vec) {
+        if (v0) {
+          if (C0) {
+            const double2 c0 = *reinterpret_cast<const double2 *>(C0 + ic * ldc0 + jc);
+            r0 = fma(beta, c0.x, r0);
+            r1 = fma(beta, c0.y, r1);
+          }
+          *reinterpret_cast<double2 *>(C + ic * ldc + jc) = make_double2(r0, r1);
+        }
+      } else {
+        if (v0) {
+          if (C0) r0 = fma(beta, C0[ic * ldc0 + jc], r0);
+          C[ic * ldc + jc] = r0;
+        }
+        if (v1) {
+          if (C0) r1 = fma(beta, C0[ic * ldc0 + jc + 1], r1);
+          C[ic * ldc + jc + 1] = r1;
+        }
+      }
+    }
+  }
+}
+
+// Whole-CTA product on the tensor cores.  Work units: per tile row, pairs of
+// adjacent tiles (1x2 blocks, shared A fragment); if the tile-column count is
+// odd, the last column in vertical strips of up to three tiles (shared B
+// fragment).  Units are dealt round-robin to the NW warps starting at warp
+// `wofs` (lets back-to-back products without a barrier between them spread over
+// different warps).  Tile indices are compile-time after unrolling; the warp
+// test is uniform.
 template <int NW>
 __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
                                           double beta, double alpha, const double *A, int ar,
                                           int ac, const double *B, int br, int bc, int M, int N,
-                                          int Kd) {
+                                          int Kd, int wofs = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
-  const int ntiles = TI * TJ;
-  // tiles are dealt to the warps in pairs (two accumulator chains in flight);
-  // the tile loop is unrolled with compile-time tile indices, the warp test is
-  // uniform
+  const int npr = TJ >> 1;                       // 1x2 blocks per tile row
+  const int nrow_units = TI * npr;
+  const int ncol_units = (TJ & 1) ? (TI + 2) / 3 : 0;
 #pragma unroll
-  for (int t0 = 0; t0 < ntiles; t0 += 2 * NW) {
+  for (int u = 0; u < nrow_units; u++) {
+    if (warp == (u + wofs) % NW)
+      mm_tc_block<1, 2>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, u / npr,
+                        2 * (u % npr), 1, g, t);
+  }
 #pragma unroll
-    for (int q = 0; q < NW; q++) {
-      const int ta = t0 + q, tb = t0 + NW + q;
-      if (ta < ntiles && warp == q)
-        mm_tc_tile_pair(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, TJ, ta,
-                        tb < ntiles ? tb : -1, g, t);
+  for (int c = 0; c < ncol_units; c++) {
+    if (warp == (nrow_units + c + wofs) % NW) {
+      const int nr = TI - 3 * c < 3 ? TI - 3 * c : 3;
+      mm_tc_block<3, 1>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, 3 * c,
+                        TJ - 1, nr, g, t);
     }
   }
 }
@@ -304,9 +395,9 @@ template <bool TC, int NW = LQ_NT / 32>
 __device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
                                         double beta, double alpha, const double *A, int ar,
                                         int ac, const double *B, int br, int bc, int M, int N,
-                                        int Kd) {
+                                        int Kd, int wofs = 0) {
   if constexpr (TC)
-    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs);
   else
     cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
 }
