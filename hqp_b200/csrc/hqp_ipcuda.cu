@@ -498,8 +498,19 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   const size_t nn = pad2((size_t)nx * nx), nf = pad2((size_t)nx * nm), gg = pad2((size_t)nm * nm),
                ru = pad2((size_t)nu * nx), xu = pad2((size_t)nx * nu), hd = pad2((size_t)nm);
   const size_t pipe = 2 * (gg + nn + xu + hd) * sizeof(double) + 2 * sizeof(uint64_t);
-  h->smem_k1 = pipe + (4 * nn + nf + ru + nn + 2 * xu) * sizeof(double);
-  h->smem_k3 = pipe + (nn + nf + ru + 3 * nn) * sizeof(double);
+  {
+    // CTA-internal blocks of K1/K3 with the padded strides of the tensor-core
+    // instantiations (lq_pad4); the generic kernels use less
+    bool compiled = false;
+#define IS_(NX_) if ((NX_) > 0) compiled = true;
+    LQ_DISPATCH_NX(nx, nu, IS_);
+#undef IS_
+    const size_t LV = compiled ? lq_pad4(nx) : nx, LT = compiled ? lq_pad4(nm) : nm;
+    const size_t bv = pad2((size_t)nx * LV), bt = pad2((size_t)nx * LT), bu = pad2((size_t)nu * LV);
+    const size_t bf = compiled ? pad2((size_t)nx * lq_pad4(nu)) : 0;  // re-packed fu
+    h->smem_k1 = pipe + (bf + 4 * bv + bt + bu + bv + 2 * bu) * sizeof(double);
+    h->smem_k3 = pipe + (bf + bv + bt + bu + 3 * bv) * sizeof(double);
+  }
   // (+ odd-stride augmented matrix and the scratch of the warp inverse)
   const size_t invs = pad2((size_t)nx * (nx + 1) + 2 * (nx + 2));
   h->smem_k2 = (4 * nn + pad2((size_t)nx * (2 * nx + 1)) + invs) * sizeof(double);

@@ -110,9 +110,11 @@ __device__ __forceinline__ void stage_issue(const LqDev &d, int nx, int nu,
 //   G = Q_k + C_k' diag(z/w) C_k   (factor prologue hqp/Hqp_IpLQDOCP.C:805-832,
 //   CTDC :68-103),  fx, fu.  `parity` = phase of the buffer's mbarrier.
 // Ends with __syncthreads().
+// fup != nullptr: fu is also re-packed there with row stride LU.
 __device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
                                               const StagePipe &sp, int b, int k, int buf,
-                                              uint32_t parity) {
+                                              uint32_t parity, double *fup = nullptr,
+                                              int LU = 0) {
   const int nm = nx + nu;
   const int dk = k < d.K ? nm : nx;
   double *G = sp.G(buf);
@@ -132,6 +134,13 @@ __device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
     __syncthreads();
   }
   for (int i = threadIdx.x; i < dk; i += blockDim.x) G[i * nm + i] += sp.hd(buf)[i];
+  if (fup && k < d.K) {
+    const double *fu = sp.fu(buf);
+    for (int i = threadIdx.x; i < nx * nu; i += blockDim.x) {
+      const int r = i / nu, c = i - r * nu;
+      fup[r * LU + c] = fu[i];
+    }
+  }
   // general rows (more than one nonzero): dense rank-1 updates, one row at a
   // time so that the summation order is fixed
   const int r0 = d.grow_ptr[k], r1 = d.grow_ptr[k + 1];
@@ -179,33 +188,50 @@ __device__ __forceinline__ void stage_pipe_init(int nx, int nu, SmemCarver &sm, 
 // Cg += Y W' are folded into the same barrier phases.
 // Ends with __syncthreads().
 // ---------------------------------------------------------------------------
+// Row strides of the CTA-internal blocks.  A DMMA fragment load is a 64-bit
+// shared load that the hardware serves per half-warp (lanes g = 0..3, t = 0..3),
+// for both operand orientations -- element (row g, col t) at g*ld + t or at
+// t*ld + g -- conflict-free exactly when ld = 4 (mod 8) doubles (measured: stride
+// 24 doubled the wavefronts of these loads, 20 is ideal).  The tensor-core
+// kernels therefore pad the internal row strides to the next value = 4 (mod 8):
+// 20 -> 20, 30 -> 36, 10 -> 12, 12 -> 12, 16 -> 20, 40 -> 44, 50 -> 52, and the
+// K1 accumulators are kept transposed so that no operand needs another layout.
+// G and fx arrive by TMA in their dense global layout; fu (small) is re-packed.
+__host__ __device__ constexpr int lq_pad4(int n) {
+  return n <= 4 ? 4 : ((n - 4 + 7) / 8) * 8 + 4;
+}
+
+// K1 accumulators: At = A' (nx x nx), Wt = (A fu)' and Yt = (W Guu^{-1})'
+// (nu x nx), Cg (nx x nx); all with row stride LV
 struct ElemAcc {
-  double *A, *W, *Y, *Cg;
+  double *At, *Wt, *Yt, *Cg;
 };
 
+// V, Phi, Rux (nu x nx), the ElemAcc blocks: stride LV; T (nx x nm): stride LT
+// fu: nx x nu with row stride LU
 template <int NU, bool TC>
-__device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, double *V,
-                                              const double *fx, const double *fu, double *G,
-                                              double *T, double *Rux, double *Phi, int *st_s,
-                                              const ElemAcc *el) {
+__device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, int LU, bool zero_V,
+                                              double *V, const double *fx, const double *fu,
+                                              double *G, double *T, double *Rux, double *Phi,
+                                              int *st_s, const ElemAcc *el) {
   const int nm = nx + nu;
   const int tid = threadIdx.x, nthr = blockDim.x;
   LQ_STAMP2(1);
   if (!zero_V) {
-    // T = V [fx fu]
-    cta_mmx<TC>(T, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fx, nx, 1, nx, nx, nx);
-    cta_mmx<TC>(T + nx, nm, nullptr, 0, 0.0, 1.0, V, nx, 1, fu, nu, 1, nx, nu, nx);
+    // T = V [fx fu]   (V symmetric: read as V')
+    cta_mmx<TC>(T, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fx, nx, 1, nx, nx, nx);
+    cta_mmx<TC>(T + nx, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fu, LU, 1, nx, nu, nx, 3);
   }
-  if (el)  // W = A fu
-    cta_mmx<TC>(el->W, nu, nullptr, 0, 0.0, 1.0, el->A, nx, 1, fu, nu, 1, nx, nu, nx);
+  if (el)  // Wt = fu' At  (W = A fu)
+    cta_mmx<TC>(el->Wt, LV, nullptr, 0, 0.0, 1.0, fu, 1, LU, el->At, LV, 1, nu, nx, nx, 2);
   if (!zero_V || el) __syncthreads();
   LQ_STAMP2(2);
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
-    cta_mmx<TC>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, nm, 1, nx, nx, nx);
-    cta_mmx<TC>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, nu, T, nm, 1, nu, nx, nx);
-    cta_mmx<TC>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, nu, T + nx, nm, 1, nu,
-           nu, nx);
+    cta_mmx<TC>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx);
+    cta_mmx<TC>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
+    cta_mmx<TC>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
+                nu, nu, nx, 3);
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
@@ -219,25 +245,26 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, bool zero_V, doubl
   __syncthreads();
   LQ_STAMP2(4);
   // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
-  // K1: rows of Y = W Guu^{-1} on the next nx threads
+  // K1: columns of Yt = Guu^{-1} Wt on the next nx threads
 #ifndef LQ_SKIP_SOLVE  // (timing experiments only)
   for (int j = tid; j < (el ? 2 * nx : nx); j += nthr) {
     if (j < nx) {
-      for (int i = 0; i < nu; i++) Rux[i * nx + j] = G[(nx + i) * nm + j];
-      ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, nx);
+      for (int i = 0; i < nu; i++) Rux[i * LV + j] = G[(nx + i) * nm + j];
+      ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
     } else {
       const int i = j - nx;
-      for (int l = 0; l < nu; l++) el->Y[i * nu + l] = el->W[i * nu + l];
-      ldlt_solve_any<NU>(Guu, nm, nu, el->Y + i * nu, 1);
+      for (int l = 0; l < nu; l++) el->Yt[l * LV + i] = el->Wt[l * LV + i];
+      ldlt_solve_any<NU>(Guu, nm, nu, el->Yt + i, LV);
     }
   }
 #endif
   __syncthreads();
   LQ_STAMP2(5);
-  // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W'
-  cta_mmx<TC>(V, nx, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, nx, 1, nx, nx, nu);
-  cta_mmx<TC>(Phi, nx, fx, nx, 1.0, -1.0, fu, nu, 1, Rux, nx, 1, nx, nx, nu);
-  if (el) cta_mmx<TC>(el->Cg, nx, el->Cg, nx, 1.0, 1.0, el->Y, nu, 1, el->W, 1, nu, nx, nx, nu);
+  // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W' = Yt' Wt
+  cta_mmx<TC>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu);
+  cta_mmx<TC>(Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
+  if (el)
+    cta_mmx<TC>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu);
   __syncthreads();
 }
 
@@ -251,26 +278,28 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_element
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
+  const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
   SmemCarver sm(smem_raw);
   StagePipe sp;
   stage_pipe_init(nx, nu, sm, sp);
-  double *J = sm.take(nx * nx), *A0 = sm.take(nx * nx), *A1 = sm.take(nx * nx);
-  double *Cg = sm.take(nx * nx), *T = sm.take(nx * nm);
-  double *Rux = sm.take(nu * nx), *Phi = sm.take(nx * nx);
-  double *W = sm.take(nx * nu), *Y = sm.take(nx * nu);
+  double *fup = TC ? sm.take(nx * LU) : nullptr;
+  double *J = sm.take(nx * LV), *A0 = sm.take(nx * LV), *A1 = sm.take(nx * LV);
+  double *Cg = sm.take(nx * LV), *T = sm.take(nx * LT);
+  double *Rux = sm.take(nu * LV), *Phi = sm.take(nx * LV);
+  double *Wt = sm.take(nu * LV), *Yt = sm.take(nu * LV);
   __shared__ int st_s;
   if (threadIdx.x == 0) {
     st_s = 0;
     if (d.use_tma) stage_issue(d, nx, nu, sp, b, kb - 1, 0);
   }
-  for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
-    const int r = i / nx, c = i - r * nx;
+  for (int i = threadIdx.x; i < nx * LV; i += blockDim.x) {
+    const int r = i / LV, c = i - r * LV;
     J[i] = 0.0;
     Cg[i] = 0.0;
     A0[i] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
-  double *A = A0, *An = A1;
+  double *At = A0, *Atn = A1;  // At = A' (transposed accumulator)
   int it = 0;
   for (int k = kb - 1; k >= ka; k--, it++) {
     const int buf = it & 1;
@@ -278,23 +307,24 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_element
       fence_proxy_async();
       stage_issue(d, nx, nu, sp, b, k - 1, buf ^ 1);
     }
-    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
-    ElemAcc el{A, W, Y, Cg};
-    riccati_stage<NU, TC>(nx, nu, k == kb - 1, J, sp.fx(buf), sp.fu(buf), sp.G(buf), T, Rux, Phi,
-                  &st_s, &el);
-    // J symmetrised ; A <- A Phi
-    cta_symmetrize(J, nx, nx);
-    cta_mmx<TC>(An, nx, nullptr, 0, 0.0, 1.0, A, nx, 1, Phi, nx, 1, nx, nx, nx);
-    double *t = A; A = An; An = t;
+    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
+    ElemAcc el{At, Wt, Yt, Cg};
+    riccati_stage<NU, TC>(nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
+                          sp.G(buf), T, Rux, Phi, &st_s, &el);
+    // J symmetrised ; A <- A Phi, i.e. At <- Phi' At
+    cta_symmetrize(J, LV, nx);
+    cta_mmx<TC>(Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
+    double *t = At; At = Atn; Atn = t;
     __syncthreads();
   }
-  cta_symmetrize(Cg, nx, nx);
+  cta_symmetrize(Cg, LV, nx);
   __syncthreads();
   const size_t o = ((size_t)b * d.ft.nel + s) * nx * nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
-    d.segA[o + i] = A[i];
-    d.segC[o + i] = Cg[i];
-    d.segJ[o + i] = J[i];
+    const int r = i / nx, c = i - r * nx;
+    d.segA[o + i] = At[c * LV + r];
+    d.segC[o + i] = Cg[r * LV + c];
+    d.segJ[o + i] = J[r * LV + c];
   }
   // a non-positive pivot here comes from the artificial zero terminal cost
   if (threadIdx.x == 0 && st_s) atomicOr(d.status, LQ_FLAG_NOTPD);
@@ -485,12 +515,14 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
+  const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
   SmemCarver sm(smem_raw);
   StagePipe sp;
   stage_pipe_init(nx, nu, sm, sp);
-  double *V = sm.take(n2), *T = sm.take(nx * nm);
-  double *Rux = sm.take(nu * nx), *Phi = sm.take(n2);
-  double *P0 = sm.take(n2), *P1 = sm.take(n2);
+  double *fup = TC ? sm.take(nx * LU) : nullptr;
+  double *V = sm.take(nx * LV), *T = sm.take(nx * LT);
+  double *Rux = sm.take(nu * LV), *Phi = sm.take(nx * LV);
+  double *P0 = sm.take(nx * LV), *P1 = sm.take(nx * LV);
   __shared__ int st_s;
   if (threadIdx.x == 0) {
     st_s = 0;
@@ -502,12 +534,12 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     const int r = i / nx, c = i - r * nx;
     const double v = d.segVb[so + i];
-    V[i] = v;
+    V[r * LV + c] = v;
     Vend[i] = v;  // Vxx at the segment end (for the last segment: Vxx[K])
-    P0[i] = (r == c) ? 1.0 : 0.0;
+    P0[r * LV + c] = (r == c) ? 1.0 : 0.0;
   }
   __syncthreads();
-  double *Psi = P0, *Psin = P1;
+  double *Pt = P0, *Ptn = P1;  // Pt = Psi' (transposed accumulator)
   int it = 0;
   for (int k = kb - 1; k >= ka; k--, it++) {
     const int buf = it & 1;
@@ -516,32 +548,45 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
       stage_issue(d, nx, nu, sp, b, k - 1, buf ^ 1);
     }
     LQ_STAMP2(0);
-    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1);
+    stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
     double *G = sp.G(buf);
-    riccati_stage<NU, TC>(nx, nu, false, V, sp.fx(buf), sp.fu(buf), G, T, Rux, Phi, &st_s, nullptr);
+    riccati_stage<NU, TC>(nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T, Rux,
+                          Phi, &st_s, nullptr);
     LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;
     double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * n2;
-    cta_symmetrize(V, nx, nx);
-    for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) Rk[i] = Rux[i];
+    cta_symmetrize(V, LV, nx);
+    for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) {
+      const int r = i / nx, c = i - r * nx;
+      Rk[i] = Rux[r * LV + c];
+    }
     for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) {
       const int r = i / nu, c = i - r * nu;
       Lk[i] = G[(nx + r) * nm + nx + c];
     }
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) Pk[i] = Phi[i];
-    // Psi <- Psi Phi
-    cta_mmx<TC>(Psin, nx, nullptr, 0, 0.0, 1.0, Psi, nx, 1, Phi, nx, 1, nx, nx, nx);
-    double *t = Psi; Psi = Psin; Psin = t;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const int r = i / nx, c = i - r * nx;
+      Pk[i] = Phi[r * LV + c];
+    }
+    // Psi <- Psi Phi, i.e. Pt <- Phi' Pt
+    cta_mmx<TC>(Ptn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Pt, LV, 1, nx, nx, nx);
+    double *t = Pt; Pt = Ptn; Ptn = t;
     __syncthreads();
     LQ_STAMP2(7);
     // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
     // s-1 and is written there
     if (k > ka || s == 0) {
       double *Vk = d.V + ((size_t)b * (d.K + 1) + k) * n2;
-      for (int i = threadIdx.x; i < n2; i += blockDim.x) Vk[i] = V[i];
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+        const int r = i / nx, c = i - r * nx;
+        Vk[i] = V[r * LV + c];
+      }
     }
   }
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) d.segPsi[po + i] = Psi[i];
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const int r = i / nx, c = i - r * nx;
+    d.segPsi[po + i] = Pt[c * LV + r];
+  }
   // an indefinite (but non-singular) Guu is accepted like the reference's BKP
   if (threadIdx.x == 0 && (st_s & LQ_FLAG_SING)) atomicOr(d.status, LQ_FLAG_SING);
 }
