@@ -93,6 +93,8 @@ struct hqpcu_handle {
   int thr_factor = 128, thr_chain = 128, thr_stage = 64;
   int max_el = 0;  // elements per instance the seg* arrays were sized for
   int n_sm = 148, k1_ctas_per_sm = 3;
+  int seg_warps = 4;      // warps per segment CTA of K1/K3 (1: one warp per segment)
+  int seg_warps_req = 0;  // HQPCU_SEG_WARPS override (0: automatic)
   int ring_scan = 8, psi_chunk = 2, ring_chain = LQ_RING;
   size_t smem_scan = 0;
   // CUDA graphs of the fixed launch sequences (factor; step per pointer set):
@@ -223,6 +225,18 @@ static void build_tree(LqTree &t, int P, int R) {
 }
 
 // segments per instance, stages per segment and the hierarchies above them
+// One warp per segment (no CTA barriers, 3x3 register-blocked products) wins
+// when there are many small independent recursions (measured at 4096 x nx=12:
+// factor 0.55 vs 0.67 ms); a single horizon of few, fat segments needs the
+// four cooperating warps.
+static void choose_seg_warps(hqpcu_handle *h) {
+  if (h->seg_warps_req)
+    h->seg_warps = h->seg_warps_req;
+  else
+    h->seg_warps = (h->smem_k3 && 8 * h->smem_k3 <= 227 * 1024 &&
+                    (long long)h->d.P * h->dims.batch >= 8LL * h->n_sm) ? 1 : 4;
+}
+
 static void choose_segments(hqpcu_handle *h, int nseg) {
   drop_graphs(h);  // the launch geometry is about to change
   const int K = h->dims.K;
@@ -247,6 +261,7 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   P = std::max(1, (K + L - 1) / L);
   d.P = P;
   d.L = L;
+  choose_seg_warps(h);
   build_tree(d.ft, P, 2);
   build_tree(d.st, P, LQ_SCAN_R);
 }
@@ -306,6 +321,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   h->dims = *dims;
   h->device = dims->device;
   {
+    const char *sw = getenv("HQPCU_SEG_WARPS");
+    if (sw) h->seg_warps_req = atoi(sw) == 1 ? 1 : 4;
     const char *env = getenv("HQPCU_GRAPHS");  // "0": plain launches (debugging, ncu per-kernel lists)
     h->use_graphs = !(env && env[0] == '0');
     if (h->use_graphs &&
@@ -509,8 +526,9 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     const size_t bv = pad2((size_t)nx * LV), bt = pad2((size_t)nx * LT), bu = pad2((size_t)nu * LV);
     const size_t bf = compiled ? pad2((size_t)nx * lq_pad4(nu)) : 0;  // re-packed fu
     h->smem_k1 = pipe + (bf + 4 * bv + bt + bu + bv + 2 * bu) * sizeof(double);
-    h->smem_k3 = pipe + (bf + bv + bt + bu + 3 * bv) * sizeof(double);
+    h->smem_k3 = pipe + (bf + bv + bt + 2 * bu + 3 * bv) * sizeof(double);
   }
+  choose_seg_warps(h);
   // (+ odd-stride augmented matrix and the scratch of the warp inverse)
   const size_t invs = pad2((size_t)nx * (nx + 1) + 2 * (nx + 2));
   h->smem_k2 = (4 * nn + pad2((size_t)nx * (2 * nx + 1)) + invs) * sizeof(double);
@@ -537,8 +555,10 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     return HQPCU_E_UNSUPPORTED;
   }
 #define SET_A(NX_, NU_)                                                        \
-  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_>, h->smem_k1));      \
-  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_>, h->smem_k3));
+  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, 4>, h->smem_k1));   \
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, 4>, h->smem_k3));   \
+  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k1)); \
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k3));
 #define SET_B(NX_)                                                             \
   TRY(set_smem((const void *)elem_scan_kernel<NX_>, h->smem_k2));             \
   TRY(set_smem((const void *)range_scan_factor_kernel<NX_>, h->smem_k2));     \
@@ -654,8 +674,20 @@ static int launch_eq_factor(hqpcu_handle *h) {
   return HQPCU_OK;
 }
 
-#define L_K1(NX_, NU_) LAUNCH(h, (seg_element_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k1, s>>>(d))
-#define L_K3(NX_, NU_) LAUNCH(h, (seg_riccati_kernel<NX_, NU_>), <<<gseg, 128, h->smem_k3, s>>>(d))
+#define L_K1(NX_, NU_)                                                                         \
+  do {                                                                                         \
+    if ((NX_) > 0 && h->seg_warps == 1)                                                        \
+      LAUNCH(h, (seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), <<<gseg, 32, h->smem_k1, s>>>(d)); \
+    else                                                                                       \
+      LAUNCH(h, (seg_element_kernel<NX_, NU_, 4>), <<<gseg, 128, h->smem_k1, s>>>(d));        \
+  } while (0)
+#define L_K3(NX_, NU_)                                                                         \
+  do {                                                                                         \
+    if ((NX_) > 0 && h->seg_warps == 1)                                                        \
+      LAUNCH(h, (seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), <<<gseg, 32, h->smem_k3, s>>>(d)); \
+    else                                                                                       \
+      LAUNCH(h, (seg_riccati_kernel<NX_, NU_, 4>), <<<gseg, 128, h->smem_k3, s>>>(d));        \
+  } while (0)
 #define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_cmp, s>>>(d, l))
 #define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), LQ_NT2, h->smem_k2, s>>>(d, h->ftop(), 1))
 #define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, LQ_NT2, h->smem_k2, s>>>(d, l, 0))
@@ -836,7 +868,9 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
   const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
   cudaStream_t s = h->stream;
   LAUNCH(h, solve_pre_kernel, <<<gall, 128, sv, s>>>(d, r1, r2, r3, r4));
-  launch_back(h, 0);
+  // a single segment that is the whole horizon starts from known boundary
+  // values: no zero-boundary pass
+  if (d.P > 1 || h->ranged()) launch_back(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, true, d.st.cnt[l + 1], l, 0, r2);
   CU(cudaGetLastError());
@@ -855,7 +889,7 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
     launch_scan(h, true, d.st.cnt[l + 1], l, 2, r2);
   launch_back(h, 1);
   LAUNCH(h, solve_mid_kernel, <<<gk, 128, sv, s>>>(d, r2));
-  launch_fwd(h, 0);
+  if (d.P > 1 || h->ranged()) launch_fwd(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, false, d.st.cnt[l + 1], l, 0, r2);
   CU(cudaGetLastError());

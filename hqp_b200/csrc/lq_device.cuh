@@ -287,7 +287,7 @@ __device__ __forceinline__ void mm_tc_block(double *C, int ldc, const double *C0
                                             double beta, double alpha, const double *A, int ar,
                                             int ac, const double *B, int br, int bc, int M,
                                             int N, int Kd, int ti0, int tj0, int nr, int g,
-                                            int t) {
+                                            int t, int ns = S) {
   double acc[R][S][2];
   bool va[R], vb[S];
   const double *ap[R], *bp[S];
@@ -302,7 +302,7 @@ __device__ __forceinline__ void mm_tc_block(double *C, int ldc, const double *C0
 #pragma unroll
   for (int s = 0; s < S; s++) {
     const int j0 = (tj0 + s) << 3;
-    vb[s] = (j0 + 8 <= N) || (j0 + g < N);
+    vb[s] = s < ns && ((j0 + 8 <= N) || (j0 + g < N));
     bp[s] = B + (j0 + g) * bc + t * br;
   }
 #pragma unroll
@@ -317,7 +317,8 @@ __device__ __forceinline__ void mm_tc_block(double *C, int ldc, const double *C0
     for (int r = 0; r < R; r++) {
       if (r < nr) {
 #pragma unroll
-        for (int s = 0; s < S; s++) dmma_m8n8k4(acc[r][s][0], acc[r][s][1], af[r], bf[s]);
+        for (int s = 0; s < S; s++)
+          if (s < ns) dmma_m8n8k4(acc[r][s][0], acc[r][s][1], af[r], bf[s]);
       }
     }
   }
@@ -329,6 +330,7 @@ __device__ __forceinline__ void mm_tc_block(double *C, int ldc, const double *C0
     const bool vr = (i0 + 8 <= M) || (ic < M);
 #pragma unroll
     for (int s = 0; s < S; s++) {
+      if (s >= ns) continue;
       const int j0 = (tj0 + s) << 3, jc = j0 + 2 * t;
       const bool v0 = vr && ((j0 + 8 <= N) || (jc < N));
       const bool v1 = vr && ((j0 + 8 <= N) || (jc + 1 < N));
@@ -367,10 +369,22 @@ template <int NW>
 __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
                                           double beta, double alpha, const double *A, int ar,
                                           int ac, const double *B, int br, int bc, int M, int N,
-                                          int Kd, int wofs = 0) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                                          int Kd, int wofs = 0, int warp_id = -1) {
+  // warp_id >= 0: the product is shared by a subset of NW warps numbered 0..NW-1
+  const int lane = threadIdx.x & 31, warp = warp_id >= 0 ? warp_id : (int)(threadIdx.x >> 5);
   const int g = lane >> 2, t = lane & 3;
   const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
+  if constexpr (NW == 1) {
+    // one warp owns the whole product: 3x3 blocks, 6 fragment loads per 9 DMMAs
+#pragma unroll
+    for (int bi = 0; bi < TI; bi += 3) {
+#pragma unroll
+      for (int bj = 0; bj < TJ; bj += 3)
+        mm_tc_block<3, 3>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, bi, bj,
+                          TI - bi < 3 ? TI - bi : 3, g, t, TJ - bj < 3 ? TJ - bj : 3);
+    }
+    return;
+  }
   const int npr = TJ >> 1;                       // 1x2 blocks per tile row
   const int nrow_units = TI * npr;
   const int ncol_units = (TJ & 1) ? (TI + 2) / 3 : 0;
@@ -395,11 +409,16 @@ template <bool TC, int NW = LQ_NT / 32>
 __device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
                                         double beta, double alpha, const double *A, int ar,
                                         int ac, const double *B, int br, int bc, int M, int N,
-                                        int Kd, int wofs = 0) {
-  if constexpr (TC)
-    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs);
-  else
-    cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+                                        int Kd, int wofs = 0, int warp_id = -1) {
+  if constexpr (TC) {
+    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs, warp_id);
+  } else {
+    if (warp_id >= 0)  // subset of NW warps
+      cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd,
+             warp_id * 32 + (int)(threadIdx.x & 31), NW * 32);
+    else
+      cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+  }
 }
 
 // A <- 0.5 (A + A')  (n x n, lda); one thread per (i<j) pair
@@ -411,6 +430,44 @@ __device__ __forceinline__ void cta_symmetrize(double *A, int lda, int n) {
       const double v = 0.5 * (A[i * lda + j] + A[j * lda + i]);
       A[i * lda + j] = v;
       A[j * lda + i] = v;
+    }
+  }
+}
+
+// A <- 0.5 (A + A') through registers, 8x8 tile pairs (ti <= tj) dealt to the NW
+// warps: row-wise double2 reads of both tiles, the transposed partner of every
+// element fetched with shuffles, row-wise double2 writes -- no column-strided
+// shared-memory access (the element-wise version above spends ~1.5 k cycles per
+// call on 4-way bank conflicts at lda = 20).  lda and n even, A 16-byte aligned.
+template <int NW>
+__device__ __forceinline__ void cta_symmetrize_tc(double *A, int lda, int n) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int TN = (n + 7) >> 3;
+  int u = 0;
+#pragma unroll
+  for (int ti = 0; ti < TN; ti++) {
+#pragma unroll
+    for (int tj = ti; tj < TN; tj++, u++) {
+      if (warp != u % NW) continue;
+      const int i0 = ti << 3, j0 = tj << 3;
+      const bool va = (i0 + g < n) && (j0 + 2 * t < n);  // a: rows of tile (ti, tj)
+      const bool vb = (j0 + g < n) && (i0 + 2 * t < n);  // b: rows of tile (tj, ti)
+      double2 a = make_double2(0.0, 0.0), b2 = make_double2(0.0, 0.0);
+      if (va) a = *reinterpret_cast<const double2 *>(A + (i0 + g) * lda + j0 + 2 * t);
+      if (vb) b2 = *reinterpret_cast<const double2 *>(A + (j0 + g) * lda + i0 + 2 * t);
+      // partner of a.{x,y} = element (j0 + 2t + e, i0 + g): array b of lane
+      // (g' = 2t + e, t' = g / 2), component g % 2; and symmetrically for b
+      const int s0 = (2 * t) * 4 + (g >> 1), s1 = (2 * t + 1) * 4 + (g >> 1);
+      const bool odd = g & 1;
+      const double bx0 = __shfl_sync(0xffffffffu, b2.x, s0), by0 = __shfl_sync(0xffffffffu, b2.y, s0);
+      const double bx1 = __shfl_sync(0xffffffffu, b2.x, s1), by1 = __shfl_sync(0xffffffffu, b2.y, s1);
+      const double ax0 = __shfl_sync(0xffffffffu, a.x, s0), ay0 = __shfl_sync(0xffffffffu, a.y, s0);
+      const double ax1 = __shfl_sync(0xffffffffu, a.x, s1), ay1 = __shfl_sync(0xffffffffu, a.y, s1);
+      const double2 an = make_double2(0.5 * (a.x + (odd ? by0 : bx0)), 0.5 * (a.y + (odd ? by1 : bx1)));
+      const double2 bn = make_double2(0.5 * (b2.x + (odd ? ay0 : ax0)), 0.5 * (b2.y + (odd ? ay1 : ax1)));
+      if (va) *reinterpret_cast<double2 *>(A + (i0 + g) * lda + j0 + 2 * t) = an;
+      if (ti != tj && vb) *reinterpret_cast<double2 *>(A + (j0 + g) * lda + i0 + 2 * t) = bn;
     }
   }
 }

@@ -209,70 +209,99 @@ struct ElemAcc {
 
 // V, Phi, Rux (nu x nx), the ElemAcc blocks: stride LV; T (nx x nm): stride LT
 // fu: nx x nu with row stride LU
-template <int NU, bool TC>
+// `idle(w, nw)`: work for the nw warps that have nothing to do while warp 0
+// factors Guu and solves for Rux (K3: the copy-outs and the Psi update of the
+// previous stage); called with (0, 1) on a one-warp CTA.
+struct NoIdle {
+  __device__ __forceinline__ void operator()(int, int) const {}
+};
+template <int NU, bool TC, int NW, class Idle = NoIdle>
 __device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, int LU, bool zero_V,
                                               double *V, const double *fx, const double *fu,
                                               double *G, double *T, double *Rux, double *Phi,
-                                              int *st_s, const ElemAcc *el) {
+                                              int *st_s, const ElemAcc *el, Idle idle = Idle()) {
   const int nm = nx + nu;
   const int tid = threadIdx.x, nthr = blockDim.x;
   LQ_STAMP2(1);
   if (!zero_V) {
     // T = V [fx fu]   (V symmetric: read as V')
-    cta_mmx<TC>(T, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fx, nx, 1, nx, nx, nx);
-    cta_mmx<TC>(T + nx, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fu, LU, 1, nx, nu, nx, 3);
+    cta_mmx<TC, NW>(T, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fx, nx, 1, nx, nx, nx);
+    cta_mmx<TC, NW>(T + nx, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fu, LU, 1, nx, nu, nx, 3);
   }
   if (el)  // Wt = fu' At  (W = A fu)
-    cta_mmx<TC>(el->Wt, LV, nullptr, 0, 0.0, 1.0, fu, 1, LU, el->At, LV, 1, nu, nx, nx, 2);
+    cta_mmx<TC, NW>(el->Wt, LV, nullptr, 0, 0.0, 1.0, fu, 1, LU, el->At, LV, 1, nu, nx, nx, 2);
   if (!zero_V || el) __syncthreads();
   LQ_STAMP2(2);
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
-    cta_mmx<TC>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx);
-    cta_mmx<TC>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
-    cta_mmx<TC>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
+    cta_mmx<TC, NW>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx);
+    cta_mmx<TC, NW>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
+    cta_mmx<TC, NW>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
                 nu, nu, nx, 3);
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
   LQ_STAMP2(3);
-#ifndef LQ_SKIP_LDL  // (timing experiments only)
-  if (warp_id_uniform() == 0) {  // uniform branch: no WARPSYNC around the shuffles inside
-    const int st = warp_ldlt_any<NU>(Guu, nm, nu);
-    if (st && tid == 0) atomicOr(st_s, st);
-  }
-#endif
-  __syncthreads();
-  LQ_STAMP2(4);
-  // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
-  // K1: columns of Yt = Guu^{-1} Wt on the next nx threads
-#ifndef LQ_SKIP_SOLVE  // (timing experiments only)
-  for (int j = tid; j < (el ? 2 * nx : nx); j += nthr) {
-    if (j < nx) {
-      for (int i = 0; i < nu; i++) Rux[i * LV + j] = G[(nx + i) * nm + j];
-      ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+  if (el) {
+    // K1: LDL' by warp 0, then the 2 nx triangular solves spread over the CTA
+    if (warp_id_uniform() == 0) {  // uniform branch: no WARPSYNC around the shuffles inside
+      const int st = warp_ldlt_any<NU>(Guu, nm, nu);
+      if (st && tid == 0) atomicOr(st_s, st);
+    }
+    __syncthreads();
+    LQ_STAMP2(4);
+    // Rux = Guu^{-1} Gux : one right-hand side (column of Gux) per thread;
+    // columns of Yt = Guu^{-1} Wt on the next nx threads
+    for (int j = tid; j < 2 * nx; j += nthr) {
+      if (j < nx) {
+        for (int i = 0; i < nu; i++) Rux[i * LV + j] = G[(nx + i) * nm + j];
+        ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+      } else {
+        const int i = j - nx;
+        for (int l = 0; l < nu; l++) el->Yt[l * LV + i] = el->Wt[l * LV + i];
+        ldlt_solve_any<NU>(Guu, nm, nu, el->Yt + i, LV);
+      }
+    }
+  } else {
+    // K3: warp 0 factors and solves back to back (no CTA barrier in between);
+    // the other warps run the deferred work of the previous stage meanwhile
+    const int wu = warp_id_uniform();
+    if (wu == 0) {
+      const int st = warp_ldlt_any<NU>(Guu, nm, nu);
+      if (st && tid == 0) atomicOr(st_s, st);
+      __syncwarp();
+      LQ_STAMP2(4);
+      for (int j = tid; j < nx; j += 32) {
+        for (int i = 0; i < nu; i++) Rux[i * LV + j] = G[(nx + i) * nm + j];
+        ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+      }
+      if (NW == 1) {
+        __syncwarp();
+        idle(0, 1);
+      }
     } else {
-      const int i = j - nx;
-      for (int l = 0; l < nu; l++) el->Yt[l * LV + i] = el->Wt[l * LV + i];
-      ldlt_solve_any<NU>(Guu, nm, nu, el->Yt + i, LV);
+      idle(wu - 1, NW - 1);
     }
   }
-#endif
   __syncthreads();
   LQ_STAMP2(5);
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W' = Yt' Wt
-  cta_mmx<TC>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu);
-  cta_mmx<TC>(Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
+  cta_mmx<TC, NW>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu);
+  cta_mmx<TC, NW>(Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
   if (el)
-    cta_mmx<TC>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu);
+    cta_mmx<TC, NW>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu);
   __syncthreads();
 }
 
 // ---------------------------------------------------------------------------
 // K1: condense segment s of instance b with zero terminal cost.
 // ---------------------------------------------------------------------------
-template <int NX, int NU>
-__global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_element_kernel(LqDev d) {
+// NW warps per CTA: 4 = the CTA-cooperative version (every product split over the
+// warps, barriers between the phases of a stage); 1 = one warp per segment (no
+// barrier wait, all DMMAs of a stage issued by the same warp).
+template <int NX, int NU, int NW>
+__global__ void __launch_bounds__(32 * NW, (NX == 20 && NW == 4 ? LQ_K13_MINB : 0))
+seg_element_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -309,11 +338,11 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_element
     }
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
     ElemAcc el{At, Wt, Yt, Cg};
-    riccati_stage<NU, TC>(nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
+    riccati_stage<NU, TC, NW>(nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
                           sp.G(buf), T, Rux, Phi, &st_s, &el);
     // J symmetrised ; A <- A Phi, i.e. At <- Phi' At
-    cta_symmetrize(J, LV, nx);
-    cta_mmx<TC>(Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
+    if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx); else cta_symmetrize(J, LV, nx);
+    cta_mmx<TC, NW>(Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
     double *t = At; At = Atn; Atn = t;
     __syncthreads();
   }
@@ -508,8 +537,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
 // ---------------------------------------------------------------------------
 // K3: Riccati recursion inside segment s from its terminal Vb.
 // ---------------------------------------------------------------------------
-template <int NX, int NU>
-__global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati_kernel(LqDev d) {
+template <int NX, int NU, int NW>
+__global__ void __launch_bounds__(32 * NW, (NX == 20 && NW == 4 ? LQ_K13_MINB : 0))
+seg_riccati_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -521,7 +551,7 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
   stage_pipe_init(nx, nu, sm, sp);
   double *fup = TC ? sm.take(nx * LU) : nullptr;
   double *V = sm.take(nx * LV), *T = sm.take(nx * LT);
-  double *Rux = sm.take(nu * LV), *Phi = sm.take(nx * LV);
+  double *RuxA = sm.take(nu * LV), *RuxB = sm.take(nu * LV), *Phi = sm.take(nx * LV);
   double *P0 = sm.take(nx * LV), *P1 = sm.take(nx * LV);
   __shared__ int st_s;
   if (threadIdx.x == 0) {
@@ -540,6 +570,39 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
   }
   __syncthreads();
   double *Pt = P0, *Ptn = P1;  // Pt = Psi' (transposed accumulator)
+  double *Rux = RuxA, *Rprev = RuxB;
+  // Results of stage kp (Rux in `Rprev`, Phi, symmetrised V) leave for HBM and
+  // enter Psi while stage kp-1 factors Guu: written by `nw` warps, `w` = index
+  // of the calling warp among them.  V and Phi are not overwritten before the
+  // barrier that ends that phase, Rux is double-buffered.
+  auto flush = [&](int kp, const double *Rp, const double *Ptc, double *Ptd, int w, int nw) {
+    const size_t ks = (size_t)b * d.K + kp;
+    double *Rk = d.Rux + ks * nu * nx, *Pk = d.Phi + ks * n2;
+    const int t0 = w * 32 + (int)(threadIdx.x & 31), nt = nw * 32;
+    // Psi <- Psi Phi, i.e. Pt <- Phi' Pt
+    if (nw == NW)
+      cta_mmx<TC, NW>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx, nx, nx);
+    else
+      cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx,
+                                        nx, nx, 0, w);
+    for (int i = t0; i < nu * nx; i += nt) {
+      const int r = i / nx, c = i - r * nx;
+      Rk[i] = Rp[r * LV + c];
+    }
+    for (int i = t0; i < n2; i += nt) {
+      const int r = i / nx, c = i - r * nx;
+      Pk[i] = Phi[r * LV + c];
+    }
+    // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
+    // s-1 and is written there
+    if (kp > ka || s == 0) {
+      double *Vk = d.V + ((size_t)b * (d.K + 1) + kp) * n2;
+      for (int i = t0; i < n2; i += nt) {
+        const int r = i / nx, c = i - r * nx;
+        Vk[i] = V[r * LV + c];
+      }
+    }
+  };
   int it = 0;
   for (int k = kb - 1; k >= ka; k--, it++) {
     const int buf = it & 1;
@@ -550,42 +613,32 @@ __global__ void __launch_bounds__(128, (NX == 20 ? LQ_K13_MINB : 0)) seg_riccati
     LQ_STAMP2(0);
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
     double *G = sp.G(buf);
-    riccati_stage<NU, TC>(nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T, Rux,
-                          Phi, &st_s, nullptr);
+    const bool have_prev = it > 0;
+    const double *Rp = Rprev, *Ptc = Pt;
+    double *Ptd = Ptn;
+    riccati_stage<NU, TC, NW>(nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T,
+                              Rux, Phi, &st_s, nullptr, [&](int w, int nw) {
+                                if (have_prev) flush(k + 1, Rp, Ptc, Ptd, w, nw);
+                              });
+    if (have_prev) { double *t = Pt; Pt = Ptn; Ptn = t; }
     LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;
-    double *Rk = d.Rux + ks * nu * nx, *Lk = d.LD + ks * nu * nu, *Pk = d.Phi + ks * n2;
-    cta_symmetrize(V, LV, nx);
-    for (int i = threadIdx.x; i < nu * nx; i += blockDim.x) {
-      const int r = i / nx, c = i - r * nx;
-      Rk[i] = Rux[r * LV + c];
-    }
+    double *Lk = d.LD + ks * nu * nu;
+    if constexpr (TC) cta_symmetrize_tc<NW>(V, LV, nx); else cta_symmetrize(V, LV, nx);
     for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) {
       const int r = i / nu, c = i - r * nu;
       Lk[i] = G[(nx + r) * nm + nx + c];
     }
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-      const int r = i / nx, c = i - r * nx;
-      Pk[i] = Phi[r * LV + c];
-    }
-    // Psi <- Psi Phi, i.e. Pt <- Phi' Pt
-    cta_mmx<TC>(Ptn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Pt, LV, 1, nx, nx, nx);
-    double *t = Pt; Pt = Ptn; Ptn = t;
+    { double *t = Rux; Rux = Rprev; Rprev = t; }
     __syncthreads();
     LQ_STAMP2(7);
-    // interior value Hessians; Vxx[a_s], s > 0, is the end value of segment
-    // s-1 and is written there
-    if (k > ka || s == 0) {
-      double *Vk = d.V + ((size_t)b * (d.K + 1) + k) * n2;
-      for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-        const int r = i / nx, c = i - r * nx;
-        Vk[i] = V[r * LV + c];
-      }
-    }
   }
+  // the last stage's results, by the whole CTA
+  flush(ka, Rprev, Pt, Ptn, (int)(threadIdx.x >> 5), NW);
+  __syncthreads();
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     const int r = i / nx, c = i - r * nx;
-    d.segPsi[po + i] = Pt[c * LV + r];
+    d.segPsi[po + i] = Ptn[c * LV + r];
   }
   // an indefinite (but non-singular) Guu is accepted like the reference's BKP
   if (threadIdx.x == 0 && (st_s & LQ_FLAG_SING)) atomicOr(d.status, LQ_FLAG_SING);
