@@ -102,6 +102,10 @@ struct hqpcu_handle {
   struct GraphEntry { std::vector<const void *> key; cudaGraphExec_t exec; long long launches; };
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
+  // programmatic dependent launch inside the hot sequences: measured SLOWER at C2
+  // (0.845 vs 0.794 ms per unit: early-scheduled dependents hold SM resources), so
+  // off unless HQPCU_PDL=1
+  bool use_pdl = false;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the user stream may be stream 0)
   // horizon split: right-hand sides remembered between the three step phases
   const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
@@ -123,6 +127,40 @@ struct hqpcu_handle {
       cudaEventRecord(sp_.e0, (h)->stream);                                   \
     }                                                                         \
     kname __VA_ARGS__;                                                        \
+    (h)->launches++;                                                          \
+    if ((h)->profiling) {                                                     \
+      cudaEventRecord(sp_.e1, (h)->stream);                                   \
+      (h)->spans.push_back(sp_);                                              \
+    }                                                                         \
+  } while (0)
+
+// Launch with programmatic stream serialisation (PDL): the kernel may be
+// scheduled while its predecessor drains; it calls pdl_enter() before touching
+// global memory, which waits for the predecessor's completion and flush.
+template <class... KArgs, class... Args>
+static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block,
+                             size_t smem, cudaStream_t s, Args &&...args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#define LAUNCHP(h, kname, grid_, block_, smem_, strm_, ...)                    \
+  do {                                                                        \
+    hqpcu_handle::Span sp_{#kname, nullptr, nullptr};                         \
+    if ((h)->profiling) {                                                     \
+      cudaEventCreate(&sp_.e0);                                               \
+      cudaEventCreate(&sp_.e1);                                               \
+      cudaEventRecord(sp_.e0, (h)->stream);                                   \
+    }                                                                         \
+    launch_ex((h)->use_pdl && !(h)->profiling, kname, grid_, block_, smem_, strm_, __VA_ARGS__); \
     (h)->launches++;                                                          \
     if ((h)->profiling) {                                                     \
       cudaEventRecord(sp_.e1, (h)->stream);                                   \
@@ -323,6 +361,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   {
     const char *sw = getenv("HQPCU_SEG_WARPS");
     if (sw) h->seg_warps_req = atoi(sw) == 1 ? 1 : 4;
+    const char *pe = getenv("HQPCU_PDL");
+    h->use_pdl = pe && pe[0] == '1';
     const char *env = getenv("HQPCU_GRAPHS");  // "0": plain launches (debugging, ncu per-kernel lists)
     h->use_graphs = !(env && env[0] == '0');
     if (h->use_graphs &&
@@ -677,21 +717,21 @@ static int launch_eq_factor(hqpcu_handle *h) {
 #define L_K1(NX_, NU_)                                                                         \
   do {                                                                                         \
     if ((NX_) > 0 && h->seg_warps == 1)                                                        \
-      LAUNCH(h, (seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), <<<gseg, 32, h->smem_k1, s>>>(d)); \
+      LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k1, s, d); \
     else                                                                                       \
-      LAUNCH(h, (seg_element_kernel<NX_, NU_, 4>), <<<gseg, 128, h->smem_k1, s>>>(d));        \
+      LAUNCHP(h, (seg_element_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k1, s, d);        \
   } while (0)
 #define L_K3(NX_, NU_)                                                                         \
   do {                                                                                         \
     if ((NX_) > 0 && h->seg_warps == 1)                                                        \
-      LAUNCH(h, (seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), <<<gseg, 32, h->smem_k3, s>>>(d)); \
+      LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k3, s, d); \
     else                                                                                       \
-      LAUNCH(h, (seg_riccati_kernel<NX_, NU_, 4>), <<<gseg, 128, h->smem_k3, s>>>(d));        \
+      LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k3, s, d);        \
   } while (0)
-#define L_CMP(NX_) LAUNCH(h, elem_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_cmp, s>>>(d, l))
-#define L_TOP(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<dim3(1, d.batch), LQ_NT2, h->smem_k2, s>>>(d, h->ftop(), 1))
-#define L_DWN(NX_) LAUNCH(h, elem_scan_kernel<NX_>, <<<gl, LQ_NT2, h->smem_k2, s>>>(d, l, 0))
-#define L_PSI(NX_) LAUNCH(h, psi_compose_kernel<NX_>, <<<gl, LQ_NT2, h->smem_psi, s>>>(d, l, h->psi_chunk))
+#define L_CMP(NX_) LAUNCHP(h, elem_compose_kernel<NX_>, gl, LQ_NT2, h->smem_cmp, s, d, l)
+#define L_TOP(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, dim3(1, d.batch), LQ_NT2, h->smem_k2, s, d, h->ftop(), 1)
+#define L_DWN(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, gl, LQ_NT2, h->smem_k2, s, d, l, 0)
+#define L_PSI(NX_) LAUNCHP(h, psi_compose_kernel<NX_>, gl, LQ_NT2, h->smem_psi, s, d, l, h->psi_chunk)
 
 // factor, part 1: bound diagonal, segment elements, tree up-sweep
 static int launch_factor_up(hqpcu_handle *h) {
@@ -702,7 +742,7 @@ static int launch_factor_up(hqpcu_handle *h) {
   if (d.m) {
     const size_t tot = (size_t)d.batch * d.N;
     const int blocks = (int)std::min<size_t>((tot + 255) / 256, 148 * 8);
-    LAUNCH(h, hdiag_kernel, <<<blocks, 256, 0, s>>>(d));
+    LAUNCHP(h, hdiag_kernel, blocks, 256, 0, s, d);
   }
   if (d.P > 1 || h->ranged()) {
     LQ_DISPATCH_NXNU(d.nx, d.nu, L_K1);
@@ -827,7 +867,7 @@ static void launch_back(hqpcu_handle *h, int mode) {
   const LqDev &d = h->d;
   const dim3 gseg(d.P, d.batch);
   cudaStream_t s = h->stream;
-#define L_(NX_) LAUNCH(h, solve_back_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode, h->ring_chain))
+#define L_(NX_) LAUNCHP(h, solve_back_kernel<NX_>, gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s, d, mode, h->ring_chain)
   LQ_DISPATCH_NX(d.nx, d.nu, L_);
 #undef L_
 }
@@ -835,7 +875,7 @@ static void launch_fwd(hqpcu_handle *h, int mode) {
   const LqDev &d = h->d;
   const dim3 gseg(d.P, d.batch);
   cudaStream_t s = h->stream;
-#define L_(NX_) LAUNCH(h, solve_fwd_kernel<NX_>, <<<gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s>>>(d, mode, h->ring_chain))
+#define L_(NX_) LAUNCHP(h, solve_fwd_kernel<NX_>, gseg, (NX_) ? 32 : h->thr_chain, h->smem_chain, s, d, mode, h->ring_chain)
   LQ_DISPATCH_NX(d.nx, d.nu, L_);
 #undef L_
 }
@@ -847,9 +887,9 @@ static void launch_scan(hqpcu_handle *h, bool back, int groups, int lev, int pha
 #define L_(NX_)                                                                               \
   do {                                                                                        \
     if (back)                                                                                 \
-      LAUNCH(h, (solve_scan_kernel<true, NX_>), <<<g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s>>>(d, lev, phase, r2, h->ring_scan)); \
+      LAUNCHP(h, (solve_scan_kernel<true, NX_>), g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s, d, lev, phase, r2, h->ring_scan); \
     else                                                                                      \
-      LAUNCH(h, (solve_scan_kernel<false, NX_>), <<<g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s>>>(d, lev, phase, r2, h->ring_scan)); \
+      LAUNCHP(h, (solve_scan_kernel<false, NX_>), g, (NX_) ? 32 : h->thr_chain, h->smem_scan, s, d, lev, phase, r2, h->ring_scan); \
   } while (0)
   LQ_DISPATCH_NX(d.nx, d.nu, L_);
 #undef L_
@@ -867,7 +907,7 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
   const dim3 gall((d.K + 1 + LQ_SPB - 1) / LQ_SPB, d.batch), gseg(d.P, d.batch);
   const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
   cudaStream_t s = h->stream;
-  LAUNCH(h, solve_pre_kernel, <<<gall, 128, sv, s>>>(d, r1, r2, r3, r4));
+  LAUNCHP(h, solve_pre_kernel, gall, 128, sv, s, d, r1, r2, r3, r4);
   // a single segment that is the whole horizon starts from known boundary
   // values: no zero-boundary pass
   if (d.P > 1 || h->ranged()) launch_back(h, 0);
@@ -888,7 +928,7 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   for (int l = h->stop() - 1; l >= 0; l--)
     launch_scan(h, true, d.st.cnt[l + 1], l, 2, r2);
   launch_back(h, 1);
-  LAUNCH(h, solve_mid_kernel, <<<gk, 128, sv, s>>>(d, r2));
+  LAUNCHP(h, solve_mid_kernel, gk, 128, sv, s, d, r2);
   if (d.P > 1 || h->ranged()) launch_fwd(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, false, d.st.cnt[l + 1], l, 0, r2);
@@ -908,7 +948,7 @@ static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, co
   for (int l = h->stop() - 1; l >= 0; l--)
     launch_scan(h, false, d.st.cnt[l + 1], l, 2, r2);
   launch_fwd(h, 1);
-  LAUNCH(h, solve_post_kernel, <<<gall, 128, sv, s>>>(d, r3, r4, dx, dy, dz, dw));
+  LAUNCHP(h, solve_post_kernel, gall, 128, sv, s, d, r3, r4, dx, dy, dz, dw);
   CU(cudaGetLastError());
   return HQPCU_OK;
 }

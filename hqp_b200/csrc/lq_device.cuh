@@ -84,6 +84,15 @@ __device__ long long g_dbg[32];  // clock64 stamps of one CTA (timing builds onl
 #define LQ_STAMP2(i) do { } while (0)
 #endif
 
+// Programmatic dependent launch: let the next kernel of the stream be scheduled
+// now (it blocks in its own pdl_enter()), then wait until the previous kernel
+// has completed and its writes are visible.  No-ops without a programmatic
+// dependency.  Must run before the first access to global memory.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.launch_dependents;");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // warp index as a value the compiler knows to be warp-uniform (a shuffle
 // result): branches on it are uniform, so the *_sync collectives inside
 // warp-specialised code are not wrapped in WARPSYNC / ENDCOLLECTIVE pairs

@@ -53,6 +53,7 @@
 // batch*N variables.
 // ---------------------------------------------------------------------------
 __global__ void hdiag_kernel(LqDev d) {
+  pdl_enter();
   const size_t total = (size_t)d.batch * d.N;
   for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
        t += (size_t)gridDim.x * blockDim.x) {
@@ -302,6 +303,7 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, in
 template <int NX, int NU, int NW>
 __global__ void __launch_bounds__(32 * NW, (NX == 20 && NW == 4 ? LQ_K13_MINB : 0))
 seg_element_kernel(LqDev d) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -366,6 +368,7 @@ seg_element_kernel(LqDev d) {
 
 template <int NX>
 __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LQ_STAMP(0);
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
@@ -455,6 +458,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
 // ---------------------------------------------------------------------------
 template <int NX>
 __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int top) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -540,6 +544,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
 template <int NX, int NU, int NW>
 __global__ void __launch_bounds__(32 * NW, (NX == 20 && NW == 4 ? LQ_K13_MINB : 0))
 seg_riccati_kernel(LqDev d) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nu = NX > 0 ? NU : d.nu, nm = nx + nu, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
@@ -652,6 +657,7 @@ seg_riccati_kernel(LqDev d) {
 // threads, smem: (chunk + ceil(chunk/2)) * nx*nx doubles.
 template <int NX>
 __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, int chunk) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;

@@ -316,6 +316,7 @@ __device__ __forceinline__ int stage_pass_blocks(int nstages) {
 __global__ void __launch_bounds__(128) solve_pre_kernel(
     LqDev d, const double *__restrict__ r1, const double *__restrict__ r2,
     const double *__restrict__ r3, const double *__restrict__ r4) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -369,6 +370,7 @@ __global__ void __launch_bounds__(128) solve_pre_kernel(
 // back: mode 0 from 0, writes segv0[s]; mode 1 from segvb[s], stores v[k]
 template <int NX>
 __global__ void solve_back_kernel(LqDev d, int mode, int ring_n) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
@@ -406,6 +408,7 @@ __global__ void solve_back_kernel(LqDev d, int mode, int ring_n) {
 //      mode 1 from segxa[s], stores x[k], k = a..b
 template <int NX>
 __global__ void solve_fwd_kernel(LqDev d, int mode, int ring_n) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
@@ -461,6 +464,7 @@ __global__ void solve_fwd_kernel(LqDev d, int mode, int ring_n) {
 template <bool BACK, int NX>
 __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__restrict__ r2,
                                   int ring_n) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
   ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
@@ -545,6 +549,7 @@ __device__ __forceinline__ void warp_ldlt_solve_g(const double *__restrict__ LD,
 // ---- mid -------------------------------------------------------------------
 // grid (ceil(K/LQ_SPB), batch), block 128; smem: LQ_WPB * (nx + nu) doubles
 __global__ void __launch_bounds__(128) solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -585,6 +590,7 @@ __global__ void __launch_bounds__(128) solve_post_kernel(
     LqDev d, const double *__restrict__ r3, const double *__restrict__ r4,
     double *__restrict__ dx, double *__restrict__ dy, double *__restrict__ dz,
     double *__restrict__ dw) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
