@@ -572,7 +572,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   // (+ odd-stride augmented matrix and the scratch of the warp inverse)
   const size_t invs = pad2((size_t)nx * (nx + 1) + 2 * (nx + 2));
   h->smem_k2 = (4 * nn + pad2((size_t)nx * (2 * nx + 1)) + invs) * sizeof(double);
-  h->smem_cmp = (5 * nn + pad2((size_t)nx * (3 * nx + 1)) + 2 * nn + pad2((size_t)2 * nx * nx) + invs) *
+  h->smem_cmp = (5 * nn + pad2((size_t)nx * (3 * nx + 1)) + 3 * nn + pad2((size_t)nx * (2 * nx + 4)) + invs) *
                 sizeof(double);
   // children of one group multiplied as a tree in shared memory, in chunks that fit
   h->psi_chunk = std::max(2, std::min(LQ_SCAN_R, (int)((192 * 1024) / (nn * sizeof(double)) * 2 / 3)));

@@ -851,12 +851,14 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
 // X = M0^{-1} R for the augmented M = [M0 | R] (n x nc, ldm) of the compiled
 // sizes: warp 0 inverts M0 in registers (warp_gj_inverse), then the whole CTA
 // applies the inverse to R on the tensor cores.  Same contract as
-// cta_gauss_jordan (X: n x (nc - n), ld = nc - n; barriers on entry and exit);
+// cta_gauss_jordan (X: n x (nc - n), ld = ldx or nc - n; barriers on entry and exit);
 // ldm should be odd (conflict-free row-per-lane reads).
 // scratch: NX (NX + 1) + 2 (NX + 2) doubles, rowsel: 65 ints.
 template <int NX, int NW>
 __device__ __forceinline__ void cta_inverse_apply(double *M, int ldm, int nc, double *X,
-                                                  double *scratch, int *rowsel, int *st_s) {
+                                                  double *scratch, int *rowsel, int *st_s,
+                                                  int ldx = 0) {
+  if (ldx == 0) ldx = nc - NX;
   static_assert(NX > 0, "compiled sizes only");
   __syncthreads();
   double *Minv = scratch, *rowbuf = scratch + NX * (NX + 1);
@@ -865,7 +867,7 @@ __device__ __forceinline__ void cta_inverse_apply(double *M, int ldm, int nc, do
     if (fl && (threadIdx.x & 31) == 0) *st_s |= fl;
   }
   __syncthreads();
-  cta_mm_tc<NW>(X, nc - NX, nullptr, 0, 0.0, 1.0, Minv, NX + 1, 1, M + NX, ldm, 1, NX, nc - NX,
+  cta_mm_tc<NW>(X, ldx, nullptr, 0, 0.0, 1.0, Minv, NX + 1, 1, M + NX, ldm, 1, NX, nc - NX,
                 NX);
   __syncthreads();
 }

@@ -377,16 +377,19 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
   SmemCarver sm(smem_raw);
+  const int ldx = NX > 0 ? 2 * nx + 4 : 2 * nx;  // = 4 (mod 8): conflict-free fragment reads
   double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
   double *Ai = sm.take(n2), *Ji = sm.take(n2);
-  double *M = sm.take(nx * ldm), *T1 = sm.take(n2), *T2 = sm.take(n2);
-  double *X = sm.take(2 * n2);  // [X_A | X_C], ld = 2 nx
+  double *M = sm.take(nx * ldm), *T1 = sm.take(n2), *T2 = sm.take(n2), *T3 = sm.take(n2);
+  double *X = sm.take(nx * ldx);  // [X_A | X_C]
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
   __shared__ int st_s, piv_s[65];
   __shared__ double inv_s[2];
+  constexpr int NWC = LQ_NT2 / 32;
   if (threadIdx.x == 0) st_s = 0;
   const size_t base = ((size_t)b * d.ft.nel + d.ft.off[lev]) * n2;
   {
+    // (no barrier here: these loads and the first child's are in flight together)
     const size_t o = base + (size_t)(c1 - 1) * n2;
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
       Aj[i] = d.segA[o + i];
@@ -394,7 +397,6 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
       Jj[i] = d.segJ[o + i];
     }
   }
-  __syncthreads();
   LQ_STAMP(1);
   for (int c = c1 - 2; c >= c0; c--) {
     const size_t o = base + (size_t)c * n2;
@@ -410,29 +412,32 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
     }
     __syncthreads();
     LQ_STAMP(2);
-    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    cta_mmx<TC, NWC>(M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
     __syncthreads();
     LQ_STAMP(3);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
     if constexpr (NX > 0)
-      cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, n3, X, inv_scr, piv_s, &st_s);
+      cta_inverse_apply<NX, NWC>(M, ldm, n3, X, inv_scr, piv_s, &st_s, ldx);
     else
       cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
-    // T1 = A_j X_C ; T2 = J_j X_A
-    cta_mmx<TC, LQ_NT2 / 32>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, 2 * nx, 1, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
+    // T1 = A_j X_C ; T2 = J_j X_A ; T3 = A_j X_A (the new A)
+    cta_mmx<TC, NWC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, ldx, 1, nx, nx, nx);
+    cta_mmx<TC, NWC>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, ldx, 1, nx, nx, nx, 4);
+    cta_mmx<TC, NWC>(T3, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, ldx, 1, nx, nx, nx, 2);
     __syncthreads();
     // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
-    cta_mmx<TC, LQ_NT2 / 32>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx);
+    cta_mmx<TC, NWC>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+    cta_mmx<TC, NWC>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx, 4);
     __syncthreads();
-    // A = A_j X_A (into T1, then copy)
-    cta_mmx<TC, LQ_NT2 / 32>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, 2 * nx, 1, nx, nx, nx);
-    cta_symmetrize(Cj, nx, nx);
-    cta_symmetrize(Jj, nx, nx);
-    __syncthreads();
-    for (int i = threadIdx.x; i < n2; i += blockDim.x) Aj[i] = T1[i];
+    if constexpr (TC) {
+      cta_symmetrize_tc<NWC>(Cj, nx, nx);
+      cta_symmetrize_tc<NWC>(Jj, nx, nx);
+    } else {
+      cta_symmetrize(Cj, nx, nx);
+      cta_symmetrize(Jj, nx, nx);
+    }
+    { double *t = Aj; Aj = T3; T3 = t; }
     __syncthreads();
     LQ_STAMP(5);
   }
@@ -532,7 +537,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
     // S <- J + A' X, symmetrised
     cta_mmx<TC, LQ_NT2 / 32>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
-    cta_symmetrize(S, nx, nx);
+    if constexpr (TC) cta_symmetrize_tc<LQ_NT2 / 32>(S, nx, nx); else cta_symmetrize(S, nx, nx);
     __syncthreads();
   }
   if (threadIdx.x == 0 && st_s) atomicOr(d.status, st_s);
