@@ -1158,6 +1158,7 @@ int hqpcu_range_config(hqpcu_handle *h, int has_prev, int has_next) {
     g_err = "hqpcu_range_config: only the first range may fix x0";
     return HQPCU_E_SIZES;
   }
+  drop_graphs(h);  // the launch sequences depend on the range flags
   h->d.has_prev = has_prev ? 1 : 0;
   h->d.has_next = has_next ? 1 : 0;
   h->factored = false;
@@ -1173,11 +1174,13 @@ int hqpcu_range_factor_begin(hqpcu_handle *h, const double *z, const double *w, 
     CU(cudaMemcpyAsync(h->z, z, bytes, cudaMemcpyDeviceToDevice, h->stream));
     CU(cudaMemcpyAsync(h->w, w, bytes, cudaMemcpyDeviceToDevice, h->stream));
   }
-  int rc = launch_factor_up(h);
-  if (rc) return rc;
-  LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(d, xf));
-  CU(cudaGetLastError());
-  return HQPCU_OK;
+  return run_graphed(h, {(const void *)(uintptr_t)10, xf}, [&]() {
+    int rc = launch_factor_up(h);
+    if (rc) return rc;
+    LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(h->d, xf));
+    CU(cudaGetLastError());
+    return (int)HQPCU_OK;
+  });
 }
 
 int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank, int world,
@@ -1185,16 +1188,21 @@ int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank,
   if (!h || !gathered || !xpsi) return HQPCU_E_NULL;
   const LqDev &d = h->d;
   CU(cudaSetDevice(h->device));
-  cudaStream_t s = h->stream;
+  return run_graphed(
+      h, {(const void *)(uintptr_t)11, gathered, xpsi, (const void *)(uintptr_t)rank,
+          (const void *)(uintptr_t)world},
+      [&]() {
+        cudaStream_t s = h->stream;
 #define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, LQ_NT2, h->smem_k2, s>>>(d, gathered, rank, world))
-  LQ_DISPATCH_NX(d.nx, d.nu, L_RS);
+        LQ_DISPATCH_NX(d.nx, d.nu, L_RS);
 #undef L_RS
-  int rc = launch_factor_down(h);
-  if (rc) return rc;
-  const size_t n2 = (size_t)d.nx * d.nx;
-  CU(cudaMemcpyAsync(xpsi, d.segPsi + (size_t)d.st.off[d.st.nlev - 1] * n2, n2 * sizeof(double),
-                     cudaMemcpyDeviceToDevice, s));
-  return HQPCU_OK;
+        int rc = launch_factor_down(h);
+        if (rc) return rc;
+        const size_t n2 = (size_t)d.nx * d.nx;
+        CU(cudaMemcpyAsync(xpsi, d.segPsi + (size_t)d.st.off[d.st.nlev - 1] * n2,
+                           n2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        return (int)HQPCU_OK;
+      });
 }
 
 int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
@@ -1202,12 +1210,14 @@ int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
   if (!h || !r1 || !r2 || !xv) return HQPCU_E_NULL;
   CU(cudaSetDevice(h->device));
   h->rg_r1 = r1; h->rg_r2 = r2; h->rg_r3 = r3; h->rg_r4 = r4;
-  int rc = launch_step_a(h, r1, r2, r3, r4);
-  if (rc) return rc;
-  LAUNCH(h, range_export_vec_kernel<true>,
-         <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, r2, xv));
-  CU(cudaGetLastError());
-  return HQPCU_OK;
+  return run_graphed(h, {(const void *)(uintptr_t)12, r1, r2, r3, r4, xv}, [&]() {
+    int rc = launch_step_a(h, r1, r2, r3, r4);
+    if (rc) return rc;
+    LAUNCH(h, range_export_vec_kernel<true>,
+           <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, r2, xv));
+    CU(cudaGetLastError());
+    return (int)HQPCU_OK;
+  });
 }
 
 int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, int rank,
@@ -1216,13 +1226,18 @@ int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, 
   CU(cudaSetDevice(h->device));
   const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
   const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
-  LAUNCH(h, range_scan_vec_kernel<true>, <<<1, thr, sm, h->stream>>>(h->d, gv, gpsi, rank, world));
-  int rc = launch_step_b(h, h->rg_r2);
-  if (rc) return rc;
-  LAUNCH(h, range_export_vec_kernel<false>,
-         <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, h->rg_r2, xx));
-  CU(cudaGetLastError());
-  return HQPCU_OK;
+  return run_graphed(
+      h, {(const void *)(uintptr_t)13, gv, gpsi, xx, h->rg_r2, (const void *)(uintptr_t)rank,
+          (const void *)(uintptr_t)world},
+      [&]() {
+        LAUNCH(h, range_scan_vec_kernel<true>, <<<1, thr, sm, h->stream>>>(h->d, gv, gpsi, rank, world));
+        int rc = launch_step_b(h, h->rg_r2);
+        if (rc) return rc;
+        LAUNCH(h, range_export_vec_kernel<false>,
+               <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, h->rg_r2, xx));
+        CU(cudaGetLastError());
+        return (int)HQPCU_OK;
+      });
 }
 
 int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gpsi, int rank,
@@ -1231,8 +1246,13 @@ int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gps
   CU(cudaSetDevice(h->device));
   const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
   const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
-  LAUNCH(h, range_scan_vec_kernel<false>, <<<1, thr, sm, h->stream>>>(h->d, gx, gpsi, rank, world));
-  return launch_step_c(h, h->rg_r2, h->rg_r3, h->rg_r4, dx, dy, dz, dw);
+  return run_graphed(
+      h, {(const void *)(uintptr_t)14, gx, gpsi, dx, dy, dz, dw, h->rg_r2, h->rg_r3, h->rg_r4,
+          (const void *)(uintptr_t)rank, (const void *)(uintptr_t)world},
+      [&]() {
+        LAUNCH(h, range_scan_vec_kernel<false>, <<<1, thr, sm, h->stream>>>(h->d, gx, gpsi, rank, world));
+        return launch_step_c(h, h->rg_r2, h->rg_r3, h->rg_r4, dx, dy, dz, dw);
+      });
 }
 
 int hqpcu_profile(hqpcu_handle *h, int on) {
