@@ -233,3 +233,51 @@ def test_equality_rows_match_dense_kkt():
         assert relerr(a, b) < 1e-9
     assert e.residuum(r1, r2, r3, r4, *mine) < 1e-10
     e.close()
+
+
+@pytest.mark.parametrize("env", [{"HQPCU_SEG_WARPS": "1"}, {"HQPCU_GRAPHS": "0"},
+                                 {"HQPCU_PDL": "1"}, {"HQPCU_CHAIN_CHUNK": "7"}])
+@pytest.mark.parametrize("cfg", [(20, 10, 131, 1, 0, 1, 9), (12, 4, 50, 1, 2, 0, 1),
+                                 (40, 10, 64, 1, 0, 1, 4)])
+def test_launch_variants_match_cpu_oracle(cfg, env, monkeypatch):
+    """The tuning switches read at hqpcu_create select other kernels / launch
+    paths of the same algorithm (one warp per segment, plain launches instead
+    of CUDA graphs, programmatic dependent launch, another TMA chunk size): all
+    must give the oracle's answer, twice in a row (graph replay)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    *pc, nseg = cfg
+    p = make_problem(*pc)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=23)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    for _ in range(2):
+        e.factor(z, w)
+        mine = e.step(r1, r2, r3, r4)
+        for a, b in zip(mine, ref):
+            assert relerr(a, b) < TOL
+    e.close(); o.close()
+
+
+def test_many_small_instances_one_warp_each():
+    """enough instances for the automatic one-warp-per-instance mode (>= 8 per SM)"""
+    nx, nu, K, B = 12, 4, 20, 1500
+    p = synth_lqdocp(nx, nu, K, seed=7)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=8)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, batch=B)
+    bc = lambda a: np.broadcast_to(a, (B,) + a.shape)
+    e.update(Q=bc(p.Q), fx=bc(p.fx), fu=bc(p.fu), ineq_val=bc(p.ineq_val))
+    rep = lambda a: np.tile(a, B)
+    e.factor(rep(z), rep(w))
+    out = e.step(rep(r1), rep(r2), rep(r3), rep(r4))
+    for got, want in zip(out, ref):
+        got = got.reshape(B, -1)
+        assert relerr(got[0], want) < TOL and relerr(got[B - 1], want) < TOL
+        assert np.array_equal(got[0], got[B // 2])  # identical inputs, identical bits
+    e.close(); o.close()
