@@ -270,9 +270,13 @@ static void build_tree(LqTree &t, int P, int R) {
 static void choose_seg_warps(hqpcu_handle *h) {
   if (h->seg_warps_req)
     h->seg_warps = h->seg_warps_req;
+  else if (h->smem_k3 && 8 * h->smem_k3 <= 227 * 1024 &&
+           (long long)h->d.P * h->dims.batch >= 8LL * h->n_sm)
+    h->seg_warps = 1;
   else
-    h->seg_warps = (h->smem_k3 && 8 * h->smem_k3 <= 227 * 1024 &&
-                    (long long)h->d.P * h->dims.batch >= 8LL * h->n_sm) ? 1 : 4;
+    // 5x5 tiles per product at nx = 40: eight warps per segment (measured at the
+    // C5 slice: factor 13.4 vs 14.7 ms)
+    h->seg_warps = h->dims.nx >= 32 ? 8 : 4;
 }
 
 static void choose_segments(hqpcu_handle *h, int nseg) {
@@ -287,7 +291,10 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
     else {
       // one wave of segment CTAs: (SMs x resident CTAs per SM of the K1 kernel),
       // but never fewer than 8 stages per segment
-      const int wave = std::max(1, h->n_sm * std::max(1, h->k1_ctas_per_sm));
+      // (one resident CTA per SM at nx >= 32: two waves, the shorter solve chains
+      //  pay for it -- measured at the C5 slice)
+      const int wave = std::max(1, h->n_sm * std::max(1, h->k1_ctas_per_sm)) *
+                       (h->dims.nx >= 32 ? 2 : 1);
       const int per_inst = std::max(1, wave / std::max(1, h->dims.batch));
       P = std::max(2, std::min(per_inst, K / 8));
     }
@@ -360,7 +367,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   h->device = dims->device;
   {
     const char *sw = getenv("HQPCU_SEG_WARPS");
-    if (sw) h->seg_warps_req = atoi(sw) == 1 ? 1 : 4;
+    if (sw) h->seg_warps_req = atoi(sw) == 1 ? 1 : (atoi(sw) == 8 ? 8 : 4);
     const char *pe = getenv("HQPCU_PDL");
     h->use_pdl = pe && pe[0] == '1';
     const char *env = getenv("HQPCU_GRAPHS");  // "0": plain launches (debugging, ncu per-kernel lists)
@@ -597,6 +604,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
 #define SET_A(NX_, NU_)                                                        \
   TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, 4>, h->smem_k1));   \
   TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, 4>, h->smem_k3));   \
+  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>, h->smem_k1)); \
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>, h->smem_k3)); \
   TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k1)); \
   TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k3));
 #define SET_B(NX_)                                                             \
@@ -716,14 +725,18 @@ static int launch_eq_factor(hqpcu_handle *h) {
 
 #define L_K1(NX_, NU_)                                                                         \
   do {                                                                                         \
-    if ((NX_) > 0 && h->seg_warps == 1)                                                        \
+    if ((NX_) >= 32 && h->seg_warps == 8)                                                      \
+      LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>), gseg, 256, h->smem_k1, s, d); \
+    else if ((NX_) > 0 && h->seg_warps == 1)                                                   \
       LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k1, s, d); \
     else                                                                                       \
       LAUNCHP(h, (seg_element_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k1, s, d);        \
   } while (0)
 #define L_K3(NX_, NU_)                                                                         \
   do {                                                                                         \
-    if ((NX_) > 0 && h->seg_warps == 1)                                                        \
+    if ((NX_) >= 32 && h->seg_warps == 8)                                                      \
+      LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>), gseg, 256, h->smem_k3, s, d); \
+    else if ((NX_) > 0 && h->seg_warps == 1)                                                   \
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k3, s, d); \
     else                                                                                       \
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k3, s, d);        \
