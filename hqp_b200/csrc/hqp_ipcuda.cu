@@ -33,7 +33,9 @@ static thread_local std::string g_err;
 // Compile-time specialisations of the factor kernels for the stage shapes named
 // in BASELINE.json; any other shape runs the <0,0> (runtime-dimension) build of
 // the same code.
-#define LQ_SCAN_R 32  // radix of the solve hierarchy
+#ifndef LQ_SCAN_R
+#define LQ_SCAN_R 32  // largest radix of the solve hierarchy (buffers are sized for it)
+#endif
 #define LQ_DISPATCH_NXNU(nx_, nu_, CALL)                                       \
   do {                                                                        \
     if ((nx_) == 20 && (nu_) == 10) { CALL(20, 10); }                         \
@@ -308,7 +310,11 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   d.L = L;
   choose_seg_warps(h);
   build_tree(d.ft, P, 2);
-  build_tree(d.st, P, LQ_SCAN_R);
+  // solve hierarchy: up (R steps) + top (P/R) + down (R) sequential chain steps,
+  // shortest for R ~ sqrt(P) (measured at P = 435: R = 21 beats 32 by 5 % per step)
+  int R = (int)std::ceil(std::sqrt((double)P));
+  R = std::max(8, std::min(R, LQ_SCAN_R));
+  build_tree(d.st, P, R);
 }
 
 static int set_smem(const void *fn, size_t bytes) {
@@ -514,7 +520,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_alloc(h, &d.hdiag, SB * d.N));
   // element arrays are sized for the hierarchy chosen here; hqpcu_set_nseg may
   // only shrink it
-  const size_t PM = (size_t)std::max(d.st.nel, 1);
+  // (the solve hierarchy's radix follows P: any radix >= 2 needs < 2 P elements)
+  const size_t PM = (size_t)2 * std::max(d.P, 1) + 64;
   const size_t PF = (size_t)std::max(d.ft.nel, 1);
   h->max_el = d.P;
   h->dims.nseg = d.P;
