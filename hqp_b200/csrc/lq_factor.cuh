@@ -676,10 +676,30 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
   const int TJ = (nx + 7) >> 3, ntiles = TJ * TJ;
   double *src = bufA;
   int have = 0;
+  __shared__ uint64_t tma_bar;
+  uint32_t tma_phase = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(&tma_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
   for (int done = c0; done < c1;) {
     const int take = min(chunk - have, c1 - done);
-    for (int i = threadIdx.x; i < take * n2; i += blockDim.x)
-      bufA[(size_t)have * n2 + i] = d.segPsi[base + (size_t)done * n2 + i];
+    if (d.use_tma) {
+      // the children are contiguous: one bulk copy (a per-thread copy loop pays
+      // the memory latency once per unrolled group of loads)
+      if (threadIdx.x == 0) {
+        if (done > c0) fence_proxy_async();  // bufA was read through the generic proxy
+        const uint32_t bytes = (uint32_t)take * n2 * 8;
+        mbar_expect_tx(&tma_bar, bytes);
+        tma_load_1d(bufA + (size_t)have * n2, d.segPsi + base + (size_t)done * n2, bytes, &tma_bar);
+      }
+      mbar_wait(&tma_bar, tma_phase);
+      tma_phase ^= 1;
+    } else {
+      for (int i = threadIdx.x; i < take * n2; i += blockDim.x)
+        bufA[(size_t)have * n2 + i] = d.segPsi[base + (size_t)done * n2 + i];
+    }
     done += take;
     int cnt = have + take;
     __syncthreads();
