@@ -35,6 +35,7 @@ struct LqDev {
   int use_tma;        // per-stage slabs are 16-byte multiples: bulk-copy path
   // horizon split across ranks (lq_range.cuh): this handle owns a contiguous
   // stage range of a longer horizon
+  int spw;            // stages per warp of the stage-parallel solve passes
   int has_prev;       // a rank before this one supplies the state at stage 0
   int has_next;       // a rank behind this one supplies the terminal value
   double *Vext;       // [nx*nx] value Hessian handed over from the ranks behind

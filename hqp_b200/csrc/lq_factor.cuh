@@ -581,6 +581,7 @@ seg_riccati_kernel(LqDev d) {
   __syncthreads();
   double *Pt = P0, *Ptn = P1;  // Pt = Psi' (transposed accumulator)
   double *Rux = RuxA, *Rprev = RuxB;
+  const bool need_psi = d.P > 1 || d.has_prev || d.has_next;
   // Results of stage kp (Rux in `Rprev`, Phi, symmetrised V) leave for HBM and
   // enter Psi while stage kp-1 factors Guu: written by `nw` warps, `w` = index
   // of the calling warp among them.  V and Phi are not overwritten before the
@@ -589,12 +590,15 @@ seg_riccati_kernel(LqDev d) {
     const size_t ks = (size_t)b * d.K + kp;
     double *Rk = d.Rux + ks * nu * nx, *Pk = d.Phi + ks * n2;
     const int t0 = w * 32 + (int)(threadIdx.x & 31), nt = nw * 32;
-    // Psi <- Psi Phi, i.e. Pt <- Phi' Pt
-    if (nw == NW)
-      cta_mmx<TC, NW>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx, nx, nx);
-    else
-      cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx,
-                                        nx, nx, 0, w);
+    // Psi <- Psi Phi, i.e. Pt <- Phi' Pt (only the solve hierarchy reads Psi: not
+    // needed when the segment is the whole horizon)
+    if (need_psi) {
+      if (nw == NW)
+        cta_mmx<TC, NW>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx, nx, nx);
+      else
+        cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1,
+                                          nx, nx, nx, 0, w);
+    }
     for (int i = t0; i < nu * nx; i += nt) {
       const int r = i / nx, c = i - r * nx;
       Rk[i] = Rp[r * LV + c];
@@ -646,10 +650,11 @@ seg_riccati_kernel(LqDev d) {
   // the last stage's results, by the whole CTA
   flush(ka, Rprev, Pt, Ptn, (int)(threadIdx.x >> 5), NW);
   __syncthreads();
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    const int r = i / nx, c = i - r * nx;
-    d.segPsi[po + i] = Ptn[c * LV + r];
-  }
+  if (need_psi)
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const int r = i / nx, c = i - r * nx;
+      d.segPsi[po + i] = Ptn[c * LV + r];
+    }
   // an indefinite (but non-singular) Guu is accepted like the reference's BKP
   if (threadIdx.x == 0 && (st_s & LQ_FLAG_SING)) atomicOr(d.status, LQ_FLAG_SING);
 }

@@ -303,17 +303,15 @@ __device__ __forceinline__ void chain_run_warp(const double *M, const double *a,
 // column-wise reads of the stage blocks) and several stages per warp, so that a
 // pass is a few hundred fat CTAs instead of K tiny ones (CTA launch rate, not
 // bandwidth, limited the one-CTA-per-stage version).
-#define LQ_SPW 1                       // stages per warp
+#ifndef LQ_WPB
 #define LQ_WPB 4                       // warps per CTA
-#define LQ_SPB (LQ_SPW * LQ_WPB)       // stages per CTA
+#endif
 
-__device__ __forceinline__ int stage_pass_blocks(int nstages) {
-  return (nstages + LQ_SPB - 1) / LQ_SPB;
-}
 
 // ---- pre ------------------------------------------------------------------
-// grid (ceil((K+1)/LQ_SPB), batch), block 128; smem: LQ_WPB * (nm + nx) doubles
-__global__ void __launch_bounds__(128) solve_pre_kernel(
+// grid (ceil((K+1)/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nm + nx) doubles
+template <int SPW>
+__global__ void __launch_bounds__(32 * LQ_WPB) solve_pre_kernel(
     LqDev d, const double *__restrict__ r1, const double *__restrict__ r2,
     const double *__restrict__ r3, const double *__restrict__ r4) {
   pdl_enter();
@@ -326,8 +324,8 @@ __global__ void __launch_bounds__(128) solve_pre_kernel(
   const double *z = d.z + (size_t)b * d.m, *w = d.w + (size_t)b * d.m;
   const double *cv = d.cval + (size_t)b * d.nnz;
   const double *r3b = r3 + (size_t)b * d.m, *r4b = r4 + (size_t)b * d.m;
-  for (int s = 0; s < LQ_SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+  for (int s = 0; s < SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
     if (k > d.K) break;
     const int dk = (k < d.K) ? nm : nx;
     const size_t xo = (size_t)b * d.N + (size_t)k * nm;
@@ -547,8 +545,9 @@ __device__ __forceinline__ void warp_ldlt_solve_g(const double *__restrict__ LD,
 }
 
 // ---- mid -------------------------------------------------------------------
-// grid (ceil(K/LQ_SPB), batch), block 128; smem: LQ_WPB * (nx + nu) doubles
-__global__ void __launch_bounds__(128) solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
+// grid (ceil(K/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nx + nu) doubles
+template <int SPW>
+__global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
@@ -556,8 +555,8 @@ __global__ void __launch_bounds__(128) solve_mid_kernel(LqDev d, const double *_
   double *t = reinterpret_cast<double *>(smem_raw) + warp * (nx + nu);  // nx
   double *Gu = t + nx;                                                   // nu
   const int b = blockIdx.y;
-  for (int s = 0; s < LQ_SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+  for (int s = 0; s < SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
     if (k >= d.K) break;
     const size_t ks = (size_t)b * d.K + k;
     const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
@@ -585,8 +584,9 @@ __global__ void __launch_bounds__(128) solve_mid_kernel(LqDev d, const double *_
 }
 
 // ---- post -------------------------------------------------------------------
-// grid (ceil((K+1)/LQ_SPB), batch), block 128; smem: LQ_WPB * (nm + nx) doubles
-__global__ void __launch_bounds__(128) solve_post_kernel(
+// grid (ceil((K+1)/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nm + nx) doubles
+template <int SPW>
+__global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
     LqDev d, const double *__restrict__ r3, const double *__restrict__ r4,
     double *__restrict__ dx, double *__restrict__ dy, double *__restrict__ dz,
     double *__restrict__ dw) {
@@ -598,8 +598,8 @@ __global__ void __launch_bounds__(128) solve_post_kernel(
   double *xn = xs + nm;                                                   // nx: x_{k+1}
   const int b = blockIdx.y;
   const double *cv = d.cval + (size_t)b * d.nnz;
-  for (int s = 0; s < LQ_SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * LQ_SPW + s;
+  for (int s = 0; s < SPW; s++) {
+    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
     if (k > d.K) break;
     const double *xk = d.x + ((size_t)b * (d.K + 1) + k) * nx;
     const size_t ks = (size_t)b * d.K + k;
