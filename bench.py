@@ -195,6 +195,7 @@ def run_ours(args, wl):
     nx, nu, K, batch = wl["nx"], wl["nu"], wl["K"], wl["batch"]
 
     N1 = 0  # bytes bookkeeping below
+    update_sparse_ms = None
     if world == 1:
         # one horizon (or one batch of instances) on the GPU
         p = synth_lqdocp(nx, nu, K, seed=1234)
@@ -216,6 +217,15 @@ def run_ours(args, wl):
             t0 = time.perf_counter()
             eng.update()
             update_ms = 1e3 * (time.perf_counter() - t0)
+            # the same update from the sparse values (map registered
+            # once, values uploaded + scattered on the device per SQP iteration)
+            vals, dst, dst2 = p.value_map()
+            eng.set_value_map(dst, dst2)
+            eng.update_values(vals)
+            t0 = time.perf_counter()
+            eng.update_values(vals)
+            update_sparse_ms = 1e3 * (time.perf_counter() - t0)
+            del dst, dst2
         host = [rep(a) for a in (z, w, r1, r2, r3, r4)]
         lp = p
         parallelism = "single"
@@ -401,6 +411,8 @@ def run_ours(args, wl):
                 "gpu_launches": int(gpu_launches), "clocks": clocks}
         if update_ms is not None:
             line["config"]["update_ms_once_per_sqp_iteration"] = update_ms
+            if update_sparse_ms is not None:
+                line["config"]["update_ms_from_sparse_values"] = update_sparse_ms
         if ip_solve is not None:
             line["ip_solve"] = ip_solve
         print(json.dumps(line), flush=True)

@@ -109,6 +109,10 @@ struct hqpcu_handle {
   // off unless HQPCU_PDL=1
   bool use_pdl = false;
   cudaStream_t cap_stream = nullptr;  // capture happens here (the user stream may be stream 0)
+  // row f1: registered scatter map (values -> stage slabs)
+  long long vm_n = 0;
+  long long *vm_dst = nullptr, *vm_dst2 = nullptr;
+  double *vm_vals = nullptr;
   // horizon split: right-hand sides remembered between the three step phases
   const double *rg_r1 = nullptr, *rg_r2 = nullptr, *rg_r3 = nullptr, *rg_r4 = nullptr;
   bool ranged() const { return d.has_prev || d.has_next; }
@@ -654,6 +658,7 @@ int hqpcu_destroy(hqpcu_handle *h) {
   cudaDeviceSynchronize();
   drop_graphs(h);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->vm_dst) { cudaFree(h->vm_dst); cudaFree(h->vm_dst2); cudaFree(h->vm_vals); }
   for (void *p : h->allocs) cudaFree(p);
   ips_free(h);
   if (h->res_host) cudaFreeHost(h->res_host);
@@ -697,6 +702,87 @@ int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx, const doubl
   for (int i = 0; i < h->q.n_eq; i++)
     for (int e = h->dims_eq_ptr[i]; e < h->dims_eq_ptr[i + 1]; e++) h->eq_rowsum[i] += fabs(eq_val[e]);
   CU(cudaStreamSynchronize(h->stream));
+  return HQPCU_OK;
+}
+
+// ---- update from sparse values (row f1) ---------------------------------------
+__global__ void scatter_values_kernel(long long n, const double *__restrict__ vals,
+                                      const long long *__restrict__ dst,
+                                      const long long *__restrict__ dst2, double *Q, double *fx,
+                                      double *fu, long long szQ, long long szX) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const double v = vals[i];
+    long long p = dst[i];
+    for (int rep = 0; rep < 2; rep++) {
+      if (p >= 0) {
+        if (p < szQ) Q[p] = v;
+        else if (p < szQ + szX) fx[p - szQ] = v;
+        else fu[p - szQ - szX] = v;
+      }
+      p = dst2[i];
+    }
+  }
+}
+
+int hqpcu_set_value_map(hqpcu_handle *h, long long n, const long long *dst,
+                        const long long *dst2) {
+  if (!h || n < 0 || (n && (!dst || !dst2))) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  if (d.batch != 1) {
+    g_err = "hqpcu_set_value_map: batch == 1";
+    return HQPCU_E_UNSUPPORTED;
+  }
+  const long long szQ = (long long)(d.K + 1) * d.nm * d.nm, szX = (long long)d.K * d.nx * d.nx,
+                  szU = (long long)d.K * d.nx * d.nu;
+  for (long long i = 0; i < n; i++)
+    if (dst[i] < 0 || dst[i] >= szQ + szX + szU || dst2[i] < -1 || dst2[i] >= szQ + szX + szU) {
+      g_err = "hqpcu_set_value_map: target outside the stage slabs";
+      return HQPCU_E_SIZES;
+    }
+  CU(cudaSetDevice(h->device));
+  if (h->vm_dst) { cudaFree(h->vm_dst); cudaFree(h->vm_dst2); cudaFree(h->vm_vals); }
+  h->vm_dst = h->vm_dst2 = nullptr;
+  h->vm_vals = nullptr;
+  h->vm_n = n;
+  const size_t nn = (size_t)std::max<long long>(n, 1);
+  CU(cudaMalloc(&h->vm_dst, nn * sizeof(long long)));
+  CU(cudaMalloc(&h->vm_dst2, nn * sizeof(long long)));
+  CU(cudaMalloc(&h->vm_vals, nn * sizeof(double)));
+  CU(cudaMemcpy(h->vm_dst, dst, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(h->vm_dst2, dst2, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice));
+  return HQPCU_OK;
+}
+
+int hqpcu_update_values(hqpcu_handle *h, const double *vals, const double *ineq_val,
+                        const double *eq_val) {
+  if (!h || !h->vm_dst || (h->vm_n && !vals) || (h->d.nnz && !ineq_val) || (h->q.nnz && !eq_val))
+    return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  const size_t szQ = (size_t)(d.K + 1) * d.nm * d.nm, szX = (size_t)d.K * d.nx * d.nx,
+               szU = (size_t)d.K * d.nx * d.nu;
+  CU(cudaMemcpyAsync(h->vm_vals, vals, (size_t)h->vm_n * sizeof(double), cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(h->Q, 0, szQ * sizeof(double), s));
+  CU(cudaMemsetAsync(h->fx, 0, szX * sizeof(double), s));
+  CU(cudaMemsetAsync(h->fu, 0, szU * sizeof(double), s));
+  if (h->vm_n) {
+    const int blocks = (int)std::min<long long>((h->vm_n + 255) / 256, 148 * 16);
+    LAUNCH(h, scatter_values_kernel, <<<blocks, 256, 0, s>>>(h->vm_n, h->vm_vals, h->vm_dst, h->vm_dst2,
+                                                            h->Q, h->fx, h->fu, (long long)szQ,
+                                                            (long long)szX));
+    CU(cudaGetLastError());
+  }
+  if (d.nnz)
+    CU(cudaMemcpyAsync(h->cval, ineq_val, d.nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+  if (h->q.nnz)
+    CU(cudaMemcpyAsync(h->eqval, eq_val, (size_t)h->q.nnz * sizeof(double), cudaMemcpyHostToDevice, s));
+  h->eq_rowsum.assign(h->q.n_eq, 0.0);
+  for (int i = 0; i < h->q.n_eq; i++)
+    for (int e = h->dims_eq_ptr[i]; e < h->dims_eq_ptr[i + 1]; e++) h->eq_rowsum[i] += fabs(eq_val[e]);
+  h->factored = false;
+  CU(cudaStreamSynchronize(s));
   return HQPCU_OK;
 }
 

@@ -34,6 +34,7 @@ Hqp_IpCuda::Hqp_IpCuda()
   _nseg = 0;
   _device = 0;
   _dev_solve = 1;
+  _sparse_update = 1;
   _K = _nx = _nu = _n = _me = _m = 0;
   _fixed_x0 = 0;
   _n_eq = 0;
@@ -42,6 +43,7 @@ Hqp_IpCuda::Hqp_IpCuda()
   _ifList.append(new If_Int("mat_nseg", &_nseg));
   _ifList.append(new If_Int("mat_device", &_device));
   _ifList.append(new If_Int("mat_dev_solve", &_dev_solve));
+  _ifList.append(new If_Int("mat_sparse_update", &_sparse_update));
 }
 
 //--------------------------------------------------------------------------
@@ -238,7 +240,50 @@ void Hqp_IpCuda::init(const Hqp_Program *qp)
   _r2p.assign(_me > 0 ? _me : 1, 0.0);
   _dyp.assign(_me > 0 ? _me : 1, 0.0);
 
+  if (_sparse_update) build_value_map(qp);
   update(qp);
+}
+
+//--------------------------------------------------------------------------
+//   where every stored entry of Q (upper triangle) and of the
+//   dynamics rows of A lives in the device slabs.  Registered once per init();
+//   update() then uploads the values only and the device scatters them
+//   (replaces the sp_extract_mat walk of hqp/Hqp_IpLQDOCP.C:747-755).
+void Hqp_IpCuda::build_value_map(const Hqp_Program *qp)
+{
+  const SPMAT *A = qp->A, *Q = qp->Q;
+  const int nm = _nx + _nu;
+  const long long szQ = (long long)(_K + 1) * nm * nm, szX = (long long)_K * _nx * _nx;
+  std::vector<long long> dst, dst2;
+  int i, j, k;
+  for (i = 0; i < _n; i++) {
+    const SPROW *r = Q->row + i;
+    k = i / nm < _K ? i / nm : _K;
+    const int li = i - k * nm;
+    for (j = 0; j < r->len; j++) {
+      const int lj = r->elt[j].col - k * nm;
+      if (lj < 0 || lj >= nm)
+        m_error(E_FORMAT, "Hqp_IpCuda::init: Q couples stages");
+      dst.push_back((long long)k * nm * nm + (long long)li * nm + lj);
+      dst2.push_back(li != lj ? (long long)k * nm * nm + (long long)lj * nm + li : -1);
+    }
+  }
+  for (i = 0; i < _K * _nx; i++) {
+    const SPROW *r = A->row + i;
+    k = i / _nx;
+    const int li = i - k * _nx;
+    for (j = 0; j < r->len - 1; j++) {
+      const int lc = r->elt[j].col - k * nm;
+      if (lc < 0 || lc >= nm)
+        m_error(E_FORMAT, "Hqp_IpCuda::init: dynamics row leaves its stage");
+      dst.push_back(lc < _nx ? szQ + ((long long)k * _nx + li) * _nx + lc
+                             : szQ + szX + ((long long)k * _nx + li) * _nu + lc - _nx);
+      dst2.push_back(-1);
+    }
+  }
+  _vals.assign(dst.size() > 0 ? dst.size() : 1, 0.0);
+  check(hqpcu_set_value_map(_h, (long long)dst.size(), dst.empty() ? NULL : &dst[0],
+                            dst2.empty() ? NULL : &dst2[0]), "Hqp_IpCuda::init");
 }
 
 //--------------------------------------------------------------------------
@@ -252,6 +297,43 @@ void Hqp_IpCuda::update(const Hqp_Program *qp)
   int i, j, k;
 
   assert(_h != NULL && (int)A->m == _me && (int)C->m == _m && (int)Q->n == _n);
+
+  if (_sparse_update) {
+    // values in the order of build_value_map(); the device scatters them
+    size_t p = 0;
+    for (i = 0; i < _n; i++) {
+      const SPROW *r = Q->row + i;
+      for (j = 0; j < r->len; j++, p++) {
+        if (p >= _vals.size()) m_error(E_FORMAT, "Hqp_IpCuda::update: pattern of Q changed");
+        _vals[p] = r->elt[j].val;
+      }
+    }
+    for (i = 0; i < _K * _nx; i++) {
+      const SPROW *r = A->row + i;
+      for (j = 0; j < r->len - 1; j++, p++) {
+        if (p >= _vals.size()) m_error(E_FORMAT, "Hqp_IpCuda::update: pattern of A changed");
+        _vals[p] = r->elt[j].val;
+      }
+      if (r->len < 1 || r->elt[r->len - 1].val != -1.0)
+        m_error(E_FORMAT, "Hqp_IpCuda::update: dynamics row lost its -1");
+    }
+    if (p != _vals.size() && !(p == 0 && _vals.size() == 1))
+      m_error(E_FORMAT, "Hqp_IpCuda::update: pattern of Q or A changed");
+    for (i = 0; i < _n_eq; i++) {
+      const SPROW *r = A->row + _rowmap[_me - _n_eq + i];
+      if (r->len != _eq_ptr[i + 1] - _eq_ptr[i])
+        m_error(E_FORMAT, "Hqp_IpCuda::update: pattern of A changed");
+      for (j = 0; j < r->len; j++) _eval[_eq_ptr[i] + j] = r->elt[j].val;
+    }
+    for (i = 0; i < _m; i++) {
+      const SPROW *r = C->row + i;
+      if (r->len != _ineq_ptr[i + 1] - _ineq_ptr[i])
+        m_error(E_FORMAT, "Hqp_IpCuda::update: pattern of C changed");
+      for (j = 0; j < r->len; j++) _cval[_ineq_ptr[i] + j] = r->elt[j].val;
+    }
+    check(hqpcu_update_values(_h, &_vals[0], &_cval[0], &_eval[0]), "Hqp_IpCuda::update");
+    return;
+  }
 
   // Q: upper triangle -> full symmetric stage blocks
   std::fill(_Q.begin(), _Q.end(), 0.0);

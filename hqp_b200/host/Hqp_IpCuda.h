@@ -27,6 +27,7 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
   int _nseg;      ///< mat_nseg: horizon segments (0 = automatic, 1 = sequential)
   int _device;    ///< mat_device: CUDA device ordinal
   int _dev_solve; ///< mat_dev_solve: run the refinement loop of solve() on the device
+  int _sparse_update; ///< mat_sparse_update: upload SPMAT values + device-side scatter (row f1)
 
   // stage structure derived from the sparsity of A and C (cf. Hqp_IpLQDOCP
   // Get_Dim / Get_Constr_Dim / Check_Structure)
@@ -38,6 +39,8 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
   std::vector<int> _eq_ptr;
   // packed host slabs (reused between updates)
   std::vector<double> _Q, _fx, _fu, _cval, _eval;
+  std::vector<double> _vals;  ///< values of Q / dynamics rows of A in map order (sparse update)
+  void build_value_map(const Hqp_Program *qp);
   std::vector<double> _r2p, _dyp; ///< permuted copies when _rowmap is not the identity
   bool _identity_rows;
 

@@ -195,6 +195,21 @@ class IpCuda:
         return dict(x=x, y=y, z=z[:self.m], w=w[:self.m], iters=it.value,
                     result=names[res.value], gap=gap.value)
 
+    def set_value_map(self, dst, dst2):
+        dst = np.ascontiguousarray(dst, np.int64)
+        dst2 = np.ascontiguousarray(dst2, np.int64)
+        _check(lib().hqpcu_set_value_map(self.h, ctypes.c_longlong(len(dst)),
+                                         dst.ctypes.data_as(ctypes.c_void_p),
+                                         dst2.ctypes.data_as(ctypes.c_void_p)),
+               "hqpcu_set_value_map")
+
+    def update_values(self, vals, ineq_val=None, eq_val=None):
+        p = self.prob
+        iv = np.ascontiguousarray(p.ineq_val if ineq_val is None else ineq_val, np.float64)
+        ev = np.ascontiguousarray(p.eq_val if eq_val is None else eq_val, np.float64)
+        vals = np.ascontiguousarray(vals, np.float64)
+        _check(lib().hqpcu_update_values(self.h, _hp(vals), _hp(iv), _hp(ev)), "hqpcu_update_values")
+
     def get_factor(self):
         p, B = self.prob, self.batch
         V = np.zeros((B, p.K + 1, p.nx, p.nx))

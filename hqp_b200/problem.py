@@ -155,6 +155,37 @@ class LQProblem:
         return _coo_to_csr(self.me, np.concatenate(rows), np.concatenate(cols),
                            np.concatenate(vals))
 
+    def value_map(self):
+        """(vals, dst, dst2) for hqpcu_set_value_map /
+        hqpcu_update_values, built from the CSR patterns of Q (upper triangle) and
+        of A exactly as a host that only holds the sparse matrices would: value i
+        of [Q entries in CSR order | entries of the K*nx dynamics rows of A, the
+        -1 of x_{k+1} left out] goes to slab position dst[i] (and dst2[i], the
+        mirrored entry of the symmetric Q block, or -1)."""
+        nm, nx, nu, K = self.nm, self.nx, self.nu, self.K
+        szQ, szX = (K + 1) * nm * nm, K * nx * nx
+        qp, qj, qv = self.csr_Q_upper()
+        qi = np.repeat(np.arange(self.N), np.diff(qp))
+        k = np.minimum(qi // nm, K)
+        li, lj = qi - k * nm, qj.astype(np.int64) - k * nm
+        d1 = k * nm * nm + li * nm + lj
+        d2 = np.where(li != lj, k * nm * nm + lj * nm + li, -1)
+        ap, aj, av = self.csr_A()
+        ai = np.repeat(np.arange(self.me), np.diff(ap))
+        dyn = ai < K * nx
+        ai, aj, av = ai[dyn], aj[dyn].astype(np.int64), av[dyn]
+        ka = ai // nx
+        lc = aj - ka * nm
+        keep = lc < nm                      # drops the -1 entry in the columns of stage k+1
+        ai, ka, lc, av = ai[keep], ka[keep], lc[keep], av[keep]
+        r = ai - ka * nx
+        da = np.where(lc < nx, szQ + (ka * nx + r) * nx + lc,
+                      szQ + szX + (ka * nx + r) * nu + (lc - nx))
+        vals = np.concatenate([qv, av]).astype(np.float64)
+        dst = np.concatenate([d1, da]).astype(np.int64)
+        dst2 = np.concatenate([d2, -np.ones(len(da), np.int64)]).astype(np.int64)
+        return np.ascontiguousarray(vals), np.ascontiguousarray(dst), np.ascontiguousarray(dst2)
+
     def csr_C(self):
         return (self.ineq_ptr.astype(np.int32), self.ineq_col.astype(np.int32),
                 self.ineq_val.astype(np.float64))

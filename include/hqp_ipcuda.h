@@ -93,6 +93,24 @@ int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx,
                      const double *fu, const double *ineq_val,
                      const double *eq_val);
 
+/* --- update from sparse values -----------------------------
+ * Replaces the host-side walk that writes every SPMAT entry into a dense
+ * stage block (sp_extract_mat_iter in Hqp_IpLQDOCP::update,
+ * hqp/Hqp_IpLQDOCP.C:747-755; meschach/addon2_hqp.c:649-709) by a device-side
+ * scatter: the caller registers ONCE (the sparsity pattern is fixed between
+ * init() calls) where each stored entry of Q and of the dynamics rows of A goes,
+ * then uploads only the value array per SQP iteration.
+ *   dst[i]  position of value i in the virtual slab [ Q | fx | fu ] of one
+ *           instance (offsets 0, (K+1) nm^2, (K+1) nm^2 + K nx^2)
+ *   dst2[i] second position written with the same value (the mirrored entry of
+ *           the symmetric Q block), or -1
+ * hqpcu_update_values: vals [n] (host); the slabs are zeroed, then filled by
+ * one kernel.  batch == 1.                                                      */
+int hqpcu_set_value_map(hqpcu_handle *h, long long n, const long long *dst,
+                        const long long *dst2);
+int hqpcu_update_values(hqpcu_handle *h, const double *vals,
+                        const double *ineq_val, const double *eq_val);
+
 /* --- factor: once per IP iteration (Hqp_IpLQDOCP::factor, :796-862) --------- */
 int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w);
 int hqpcu_factor_dev(hqpcu_handle *h, const double *z, const double *w);

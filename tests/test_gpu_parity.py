@@ -281,3 +281,29 @@ def test_many_small_instances_one_warp_each():
         assert relerr(got[0], want) < TOL and relerr(got[B - 1], want) < TOL
         assert np.array_equal(got[0], got[B // 2])  # identical inputs, identical bits
     e.close(); o.close()
+
+
+def test_update_from_sparse_values_equals_dense_update():
+    """row f1: hqpcu_set_value_map + hqpcu_update_values (device-side scatter of
+    the CSR values) must leave exactly the factor that the dense update leaves."""
+    p = make_problem(20, 10, 64, 1, 2, 1)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=31)
+    a = IpCuda(p, nseg=4)
+    a.update()
+    a.factor(z, w)
+    ref = a.step(r1, r2, r3, r4)
+    Va, Ra = a.get_factor()
+    b = IpCuda(p, nseg=4)
+    vals, dst, dst2 = p.value_map()
+    b.set_value_map(dst, dst2)
+    for _ in range(2):                   # the map is registered once, values per update
+        b.update_values(vals)
+        b.factor(z, w)
+        out = b.step(r1, r2, r3, r4)
+        Vb, Rb = b.get_factor()
+        assert np.array_equal(Va, Vb) and np.array_equal(Ra, Rb)
+        for x, y in zip(out, ref):
+            assert np.array_equal(x, y)
+    with pytest.raises(Exception):
+        b.set_value_map(np.array([10 ** 12]), np.array([-1]))
+    a.close(); b.close()
