@@ -149,15 +149,32 @@ class RangeSolver:
             dist.all_gather_into_tensor(out, flat, group=self.group)
         return out.view((self.world,) + tuple(t.shape))
 
+    def _gather_async(self, t):
+        """all-gather that is only waited for at its first use (overlaps with the
+        kernels enqueued meanwhile); -> (output, work or None)"""
+        import torch
+        import torch.distributed as dist
+        flat = t.contiguous().view(-1)
+        out = torch.empty(self.world * flat.numel(), dtype=t.dtype, device=t.device)
+        if self.world == 1:
+            out.copy_(flat)
+            return out.view((self.world,) + tuple(t.shape)), None
+        work = dist.all_gather_into_tensor(out, flat, group=self.group, async_op=True)
+        return out.view((self.world,) + tuple(t.shape)), work
+
     def factor(self, z, w):
         xf = self.e.factor_begin(z, w)
         gathered = self._gather(xf)
         xpsi = self.e.factor_finish(gathered, self.rank, self.world)
-        self.gpsi = self._gather(xpsi)
+        # the range transitions are first needed in the middle of the next step
+        self.gpsi, self._gpsi_work = self._gather_async(xpsi)
 
     def step(self, r1, r2, r3, r4):
         xv = self.e.step_begin(r1, r2, r3, r4)
         gv = self._gather(xv)
+        if getattr(self, "_gpsi_work", None) is not None:
+            self._gpsi_work.wait()
+            self._gpsi_work = None
         xx = self.e.step_mid(gv, self.gpsi, self.rank, self.world)
         gx = self._gather(xx)
         return self.e.step_finish(gx, self.gpsi, self.rank, self.world)
