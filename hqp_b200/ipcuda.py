@@ -178,8 +178,11 @@ class IpCuda:
                "hqpcu_residuum")
         return res.value
 
-    def mehrotra_solve(self, c=None, b=None, d=None, eps=1e-9, max_iters=0):
-        """Hqp_IpsMehrotra cold_start + solve on the device (hqpcu_mehrotra_solve)."""
+    def mehrotra_solve(self, c=None, b=None, d=None, eps=1e-9, max_iters=0, hot=None,
+                       max_warm_iters=0):
+        """Hqp_IpsMehrotra cold_start + solve on the device (hqpcu_mehrotra_solve);
+        hot = (x, y) of the previous solve: hot_start + solve
+        (hqpcu_mehrotra_hot_solve, z and w continue on the device)."""
         p = self.prob
         c = np.ascontiguousarray(p.c if c is None else c, np.float64)
         b = np.ascontiguousarray(p.b if b is None else b, np.float64)
@@ -187,10 +190,18 @@ class IpCuda:
         x, y = np.zeros(self.N), np.zeros(self.me)
         z, w = np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
         it, res, gap = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
-        _check(lib().hqpcu_mehrotra_solve(self.h, _hp(c), _hp(b), _hp(d), ctypes.c_double(eps),
-                                          max_iters, _hp(x), _hp(y), _hp(z), _hp(w),
-                                          ctypes.byref(it), ctypes.byref(res), ctypes.byref(gap)),
-               "hqpcu_mehrotra_solve")
+        if hot is not None:
+            x[:], y[:] = hot[0], hot[1]
+            _check(lib().hqpcu_mehrotra_hot_solve(self.h, _hp(c), _hp(b), _hp(d),
+                                                  ctypes.c_double(eps), max_iters, max_warm_iters,
+                                                  _hp(x), _hp(y), _hp(z), _hp(w), ctypes.byref(it),
+                                                  ctypes.byref(res), ctypes.byref(gap)),
+                   "hqpcu_mehrotra_hot_solve")
+        else:
+            _check(lib().hqpcu_mehrotra_solve(self.h, _hp(c), _hp(b), _hp(d), ctypes.c_double(eps),
+                                              max_iters, _hp(x), _hp(y), _hp(z), _hp(w),
+                                              ctypes.byref(it), ctypes.byref(res), ctypes.byref(gap)),
+                   "hqpcu_mehrotra_solve")
         names = ["optimal", "feasible", "infeasible", "suboptimal", "degenerate"]
         return dict(x=x, y=y, z=z[:self.m], w=w[:self.m], iters=it.value,
                     result=names[res.value], gap=gap.value)

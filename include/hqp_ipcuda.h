@@ -193,6 +193,18 @@ int hqpcu_mehrotra_solve(hqpcu_handle *h, const double *c, const double *b,
                          const double *d, double eps, int max_iters, double *x,
                          double *y, double *z, double *w, int *iters, int *result,
                          double *gap);
+/* Hqp_IpsMehrotra::hot_start + solve (hqp/Hqp_IpsMehrotra.C:330-352, 696-733;
+ * called by Hqp_SqpSolver.C:288-293 for every QP after the first): x, y are
+ * IN/OUT (the previous solution), z and w restart from the iterate this handle
+ * remembered during its previous solve (:475-478).  A hot start that does not
+ * contract (test > test1 / 1.2^(iter-1)), exceeds max_warm_iters (0: 25) or
+ * ends without "optimal" is restarted cold inside the call; the iterations it
+ * cost are included in *iters like the reference's _fail_iters.  Without a
+ * previous solve this is a cold-started solve.                                 */
+int hqpcu_mehrotra_hot_solve(hqpcu_handle *h, const double *c, const double *b,
+                             const double *d, double eps, int max_iters,
+                             int max_warm_iters, double *x, double *y, double *z,
+                             double *w, int *iters, int *result, double *gap);
 
 /* --- per-kernel timing with CUDA events on the launching stream (bench.py's
  *     roofline section).  hqpcu_profile_read synchronises and writes a JSON

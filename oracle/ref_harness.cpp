@@ -380,6 +380,47 @@ int ref_ips_solve(void *qp_, const char *solver, const char *mat, double eps,
   return err;
 }
 
+// A sequence of IP solves on one Hqp_Solver object: the first cold-started, the
+// following hot-started (Hqp_SqpSolver.C:284-294) after the linear terms c, b, d
+// of the program were replaced by row k of cs / bs / ds.  Outputs per solve.
+int ref_ips_solve_seq(void *qp_, const char *solver, const char *mat, double eps,
+                      int max_iters, int nsolve, const double *cs, const double *bs,
+                      const double *ds, double *xs, double *ys, double *zs, int *iters,
+                      int *results) {
+  ref_init();
+  Hqp_Program *qp = (Hqp_Program *)qp_;
+  If_ClassList<Hqp_Solver> *list = If_ClassList_Hqp_Solver();
+  Hqp_Solver *s = list ? list->createObject(solver) : NULL;
+  if (!s) return -1;
+  if (If_SetString("qp_mat_solver", mat) != IF_OK) {
+    delete s;
+    return -2;
+  }
+  int err = 0;
+  s->qp(qp);
+  s->eps(eps);
+  if (max_iters > 0) s->max_iters(max_iters);
+  const int n = qp->c->dim, me = qp->b->dim, m = qp->d->dim;
+  for (int k = 0; k < nsolve && !err; k++) {
+    for (int i = 0; i < n; i++) qp->c->ve[i] = cs[(size_t)k * n + i];
+    for (int i = 0; i < me; i++) qp->b->ve[i] = bs[(size_t)k * me + i];
+    for (int i = 0; i < m; i++) qp->d->ve[i] = ds[(size_t)k * m + i];
+    if (k == 0) {
+      m_catchall(s->init(); s->update(); s->cold_start(); s->solve(), err = _err_num);
+    } else {
+      m_catchall(s->update(); s->hot_start(); s->solve(), err = _err_num);
+    }
+    if (err) break;
+    vec_to(qp->x, xs + (size_t)k * n);
+    vec_to(s->y(), ys + (size_t)k * me);
+    if (m) vec_to(s->z(), zs + (size_t)k * m);
+    iters[k] = s->iter();
+    results[k] = (int)s->result();
+  }
+  delete s;
+  return err;
+}
+
 //------------------------------------------------------- docp example --
 // hqp_docp/Docp_Main.C restated with selectable solvers.  One call per
 // process is the supported use (global theSqpSolver state).

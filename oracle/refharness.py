@@ -142,6 +142,24 @@ def ips_solve(qp: RefQP, solver="Mehrotra", mat="LQDOCP", eps=1e-9, max_iters=0)
                 seconds=sec.value)
 
 
+def ips_solve_seq(qp: RefQP, cs, bs, ds, solver="Mehrotra", mat="LQDOCP", eps=1e-9, max_iters=0):
+    """First solve cold-started, the others hot-started with the linear terms
+    c, b, d replaced by the rows of cs, bs, ds; -> list of dict(x,y,z,iters,result)."""
+    cs, bs, ds = (np.ascontiguousarray(a, np.float64) for a in (cs, bs, ds))
+    ns = cs.shape[0]
+    xs, ys = np.zeros((ns, qp.n)), np.zeros((ns, qp.me))
+    zs = np.zeros((ns, max(qp.m, 1)))
+    it = (ctypes.c_int * ns)()
+    res = (ctypes.c_int * ns)()
+    err = lib().ref_ips_solve_seq(qp.h, solver.encode(), mat.encode(), ctypes.c_double(eps),
+                                  max_iters, ns, _dp(cs), _dp(bs), _dp(ds), _dp(xs), _dp(ys),
+                                  _dp(zs), it, res)
+    if err:
+        raise ArithmeticError(f"reference IP solve sequence failed with code {err}")
+    return [dict(x=xs[k], y=ys[k], z=zs[k][:qp.m], iters=it[k], result=HQP_RESULT[res[k]])
+            for k in range(ns)]
+
+
 def load_plugin(path):
     if lib().ref_load_plugin(os.fsencode(path)):
         raise RuntimeError(lib().ref_last_error().decode())

@@ -70,3 +70,30 @@ def test_mehrotra_matches_live_reference(dims):
     r = solve_gpu(p)
     assert r["result"] == ref["result"] and r["iters"] == ref["iters"]
     assert relerr(r["x"], ref["x"]) < 1e-8
+
+
+@pytest.mark.parametrize("name", ["ipshot_n5m3K40", "ipshot_n20m10K100"])
+@pytest.mark.parametrize("nseg", [1, 0])
+def test_hot_started_sequence_matches_reference_golden(name, nseg, golden_dir):
+    """Hqp_IpsMehrotra::hot_start + solve on the device (hqpcu_mehrotra_hot_solve):
+    the SQP pattern -- one cold-started QP, then hot-started ones with changed
+    linear terms, one of them changed so much that the reference restarts cold
+    inside solve() -- must take the reference's iteration counts (its fail_iters
+    included) and reach its solutions."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    from make_golden_hot import sequence
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    p = synth_lqdocp(*[int(v) for v in g["cfg"]])
+    cs, bs, ds = sequence(p, [float(s) for s in g["scales"]], int(g["seed"]))
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    prev = None
+    for k in range(len(cs)):
+        r = e.mehrotra_solve(c=cs[k], b=bs[k], d=ds[k], eps=1e-9, hot=prev)
+        assert r["result"] == str(g["result"][k]), k
+        assert r["iters"] == int(g["iters"][k]), (k, r["iters"], int(g["iters"][k]))
+        assert relerr(r["x"], g["x"][k]) < 1e-7
+        assert relerr(r["y"], g["y"][k]) < 1e-6
+        prev = (r["x"], r["y"])
+    e.close()
