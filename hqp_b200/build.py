@@ -72,11 +72,14 @@ def build_plugin(force=False):
     out = os.path.join(LIB, "libhqp_ipcuda_plugin.so")
     if not os.path.isdir(os.path.join(REF, "hqp")) or not os.path.exists(src):
         return out if os.path.exists(out) else None
-    if force or _newer(out, [src, hdr, os.path.join(ROOT, "include", "hqp_ipcuda.h")]):
+    if force or _newer(out, [src, hdr, os.path.join(HERE, "host", "Hqp_IpsCuda.C"),
+                             os.path.join(HERE, "host", "Hqp_IpsCuda.h"),
+                             os.path.join(ROOT, "include", "hqp_ipcuda.h")]):
         shim = os.path.join(ROOT, "oracle", "tclshim")
         _run(["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w", "-fpermissive",
               f"-I{REF}", f"-I{shim}", f"-I{REF}/iftcl", f"-I{REF}/hqp",
-              "-I" + os.path.join(ROOT, "include"), src, "-o", out,
+              "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host"), src,
+              os.path.join(HERE, "host", "Hqp_IpsCuda.C"), "-o", out,
               "-L" + LIB, "-lhqpcuda", "-Wl,-rpath,$ORIGIN"])
     return out
 

@@ -67,6 +67,11 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
                 VEC *dx, VEC *dy, VEC *dz, VEC *dw);
 
   const char *name() { return "Cuda"; }
+
+  // used by Hqp_IpsCuda (the device-resident IP solver built on this engine)
+  hqpcu_handle *handle() { return _h; }
+  bool identity_rows() const { return _identity_rows; }
+  const std::vector<int> &rowmap() const { return _rowmap; }
 };
 
 #endif

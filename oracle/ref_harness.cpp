@@ -432,7 +432,9 @@ int ref_docp_did(int kmax, const char *qp_solver, const char *mat_solver,
   If_SetReal("sqp_eps", sqp_eps);
   if (qp_solver && *qp_solver)
     if (If_SetString("sqp_qp_solver", qp_solver) != IF_OK) return -1;
-  if (If_SetString("qp_mat_solver", mat_solver) != IF_OK) {
+  // (a solver module without an exchangeable matrix solver -- "CudaMehrotra" --
+  // is selected with an empty mat_solver)
+  if (mat_solver && *mat_solver && If_SetString("qp_mat_solver", mat_solver) != IF_OK) {
     fprintf(stderr, "qp_mat_solver %s: %s\n", mat_solver, If_ResultString());
     return -2;
   }

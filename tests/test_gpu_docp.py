@@ -52,3 +52,19 @@ def test_docp_as_shipped_franke_cuda():
     assert r["sqp_iters"] == g["sqp_iters"]
     assert abs(r["objective"] - g["objective"]) <= 1e-8 * abs(g["objective"])
     assert abs(r["qp_iters"] - g["qp_iters"]) <= 3
+
+
+@needs_ref
+@pytest.mark.parametrize("key,kmax", [("K60_Mehrotra_LQDOCP", 60), ("K200_Mehrotra_LQDOCP", 200),
+                                      ("K1000_Mehrotra_LQDOCP", 1000)])
+def test_docp_device_resident_solver_matches_mehrotra(key, kmax):
+    """sqp_qp_solver CudaMehrotra (Hqp_IpsCuda): the whole IP iteration on the
+    device -- cold start, hot starts between SQP iterations, cold restarts -- under
+    the unmodified SQP driver must reproduce Hqp_IpsMehrotra + Hqp_IpLQDOCP: same
+    SQP and (total) IP iteration counts, same objective."""
+    g = gold()[key]
+    r = refharness.docp_did(kmax, "CudaMehrotra", "", plugin=PLUGIN)
+    assert r["result"] == "optimal"
+    assert r["sqp_iters"] == g["sqp_iters"]
+    assert r["qp_iters"] == g["qp_iters"]
+    assert abs(r["objective"] - g["objective"]) <= 1e-8 * abs(g["objective"])
