@@ -346,12 +346,15 @@ def run_ours(args, wl):
     if world == 1 and batch == 1:
         try:
             eng.mehrotra_solve()                      # warm (graphs captured)
+            s0 = eng.solve_stats()
             t0 = time.perf_counter()
             r = eng.mehrotra_solve()
             dt = time.perf_counter() - t0
+            s1 = eng.solve_stats()
             ip_solve = {"result": r["result"], "iterations": r["iters"], "ms_total": 1e3 * dt,
                         "ms_per_iteration": 1e3 * dt / max(r["iters"], 1),
                         "stages_per_s": K * r["iters"] / dt, "gap": r["gap"],
+                        "mean_kkt_steps_per_refined_solve": (s1[1] - s0[1]) / max(s1[0] - s0[0], 1),
                         "note": "hqpcu_mehrotra_solve: cold start + IP iterations, host c/b/d in, "
                                 "x/y/z/w out; each iteration = 1 factor + 2 refined solves + vector kernels"}
         except Exception as ex:  # reported, never fatal for the metric

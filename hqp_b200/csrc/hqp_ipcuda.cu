@@ -70,6 +70,7 @@ struct hqpcu_handle {
   hqpcu_dims dims;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  long long n_solves = 0, n_solve_steps = 0;  // hqpcu_solve_stats
   int device = 0;
   int nseg_req = 0;
   std::vector<void *> allocs;
@@ -674,6 +675,12 @@ int hqpcu_set_stream(hqpcu_handle *h, void *s) {
 }
 
 long long hqpcu_launch_count(const hqpcu_handle *h) { return h ? h->launches : 0; }
+int hqpcu_solve_stats(const hqpcu_handle *h, long long *solves, long long *steps) {
+  if (!h || !solves || !steps) return HQPCU_E_NULL;
+  *solves = h->n_solves;
+  *steps = h->n_solve_steps;
+  return HQPCU_OK;
+}
 int hqpcu_nseg(const hqpcu_handle *h) { return h ? h->d.P : 0; }
 
 // ------------------------------------------------------------------ update --
@@ -1246,6 +1253,8 @@ static int solve_core(hqpcu_handle *h, double eps, const double *r1, const doubl
   }
   if (res_out) *res_out = res;
   if (nsteps) *nsteps = steps;
+  h->n_solves++;
+  h->n_solve_steps += steps;
   return HQPCU_OK;
 }
 

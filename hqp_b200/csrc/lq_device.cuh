@@ -773,17 +773,10 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
       if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
     }
   }
-#ifdef LQ_SKIP_GJ  // (timing experiments only)
-  if (threadIdx.x < n) piv_s[threadIdx.x] = threadIdx.x;
-#endif
   __syncthreads();
   unsigned long long used = 0ull;  // rows already consumed as pivot rows
   const int q = threadIdx.x & 3, jl = threadIdx.x >> 2, ncol = blockDim.x >> 2;
-#ifdef LQ_SKIP_GJ
-  for (int p = 0; p < 0; p++) {
-#else
   for (int p = 0; p < n; p++) {
-#endif
     const int r = piv_s[p];
     const double inv = inv_s[p & 1];
     used |= 1ull << r;

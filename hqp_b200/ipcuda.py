@@ -221,6 +221,11 @@ class IpCuda:
         vals = np.ascontiguousarray(vals, np.float64)
         _check(lib().hqpcu_update_values(self.h, _hp(vals), _hp(iv), _hp(ev)), "hqpcu_update_values")
 
+    def solve_stats(self):
+        a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        _check(lib().hqpcu_solve_stats(self.h, ctypes.byref(a), ctypes.byref(b)), "hqpcu_solve_stats")
+        return a.value, b.value
+
     def get_factor(self):
         p, B = self.prob, self.batch
         V = np.zeros((B, p.K + 1, p.nx, p.nx))

@@ -79,6 +79,11 @@ int hqpcu_set_stream(hqpcu_handle *h, void *cuda_stream);
 const char *hqpcu_last_error(void);
 /* kernels launched by this handle since creation (bench.py "gpu_launches") */
 long long hqpcu_launch_count(const hqpcu_handle *h);
+/* refined solves (hqpcu_solve*, and the two per IP iteration inside
+ * hqpcu_mehrotra_*) since creation and the steps they took: steps / solves =
+ * mean number of KKT solves per Hqp_IpMatrix::solve (1 = no refinement needed,
+ * hqp/Hqp_IpMatrix.C:65-128)                                                   */
+int hqpcu_solve_stats(const hqpcu_handle *h, long long *solves, long long *steps);
 /* segments actually used per instance */
 int hqpcu_nseg(const hqpcu_handle *h);
 
