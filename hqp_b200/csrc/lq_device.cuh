@@ -553,6 +553,7 @@ __device__ __forceinline__ int warp_ldlt_reg(double *A, int lda) {
     }
     a[p] = (lane == p) ? inv : li;
   }
+  __syncwarp();  // lanes >= M read row M-1 above: order them before its write-back
   if (lane < M) {
 #pragma unroll
     for (int j = 0; j < M; j++)
@@ -698,12 +699,12 @@ __device__ __forceinline__ int warp_gj_inverse(const double *M, int ldm, double 
         *reinterpret_cast<double2 *>(rb + j) = v;
       }
       rb[N] = myinv;
-      if (NR > 1) rowsel[64] = krr;
+      if (NR > 1) rb[N + 1] = (double)krr;  // (double-buffered with the row)
       rowsel[p] = lane + 32 * krr;
     }
     __syncwarp();
     const double inv = rb[N];
-    const int rsel = NR > 1 ? rowsel[64] : 0;
+    const int rsel = NR > 1 ? (int)rb[N + 1] : 0;
     // row_i -= (a_ip / piv) row_r for i != r; the pivot row stays unscaled, the
     // unit column of the right-hand identity takes the place of column p
     double m[NR];

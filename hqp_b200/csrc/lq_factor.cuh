@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   __shared__ double inv_s[2];
   constexpr int NWC = LQ_NT2 / 32;
   if (threadIdx.x == 0) st_s = 0;
+  __syncthreads();  // (before any load: costs nothing on the critical path)
   const size_t base = ((size_t)b * d.ft.nel + d.ft.off[lev]) * n2;
   {
     // (no barrier here: these loads and the first child's are in flight together)
