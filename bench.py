@@ -357,6 +357,17 @@ def run_ours(args, wl):
                         "mean_kkt_steps_per_refined_solve": (s1[1] - s0[1]) / max(s1[0] - s0[0], 1),
                         "note": "hqpcu_mehrotra_solve: cold start + IP iterations, host c/b/d in, "
                                 "x/y/z/w out; each iteration = 1 factor + 2 refined solves + vector kernels"}
+            # the same QP through the unmodified reference on the host
+            # (Hqp_IpsMehrotra + Hqp_IpLQDOCP, oracle/_ref), bounded to <= 10^4 stages
+            if rank == 0 and K <= 10000:
+                from oracle import refharness
+                if refharness.available():
+                    rr = refharness.ips_solve(refharness.RefQP(p), "Mehrotra", "LQDOCP", 1e-9)
+                    ip_solve["reference_cpu"] = {
+                        "iterations": rr["iters"], "result": rr["result"],
+                        "ms_total": 1e3 * rr["seconds"],
+                        "x_relative_difference": float(np.max(np.abs(rr["x"] - r["x"])) /
+                                                       max(1e-300, np.max(np.abs(rr["x"]))))}
         except Exception as ex:  # reported, never fatal for the metric
             ip_solve = {"error": str(ex)}
 
