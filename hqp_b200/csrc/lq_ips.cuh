@@ -69,6 +69,7 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
   const double *cv = d.cval;
   for (int i = threadIdx.x; i < dk; i += blockDim.x) {
     double qx = 0.0;
+#pragma unroll 10
     for (int l = 0; l < dk; l++) qx = fma(Qk[l * nm + i], xs[l], qx);
     xQx = fma(xs[i], qx, xQx);
     xc = fma(xs[i], v.c[xo + i], xc);
@@ -76,9 +77,11 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
     if (k < d.K) {
       if (i < nx) {
         const double *fx = d.fx + (size_t)k * nx * nx;
+#pragma unroll 10
         for (int l = 0; l < nx; l++) s = fma(-fx[l * nx + i], yk[l], s);
       } else {
         const double *fu = d.fu + (size_t)k * nx * nu;
+#pragma unroll 10
         for (int l = 0; l < nx; l++) s = fma(-fu[l * nu + (i - nx)], yk[l], s);
       }
     }
@@ -97,7 +100,9 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
     const double *fx = d.fx + (size_t)k * nx * nx, *fu = d.fu + (size_t)k * nx * nu;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
       double s = -xn[i];
+#pragma unroll 10
       for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
+#pragma unroll 10
       for (int l = 0; l < nu; l++) s = fma(fu[i * nu + l], xs[nx + l], s);
       const size_t ro = (size_t)k * nx + i;
       const double t = -(s + v.b[ro]);

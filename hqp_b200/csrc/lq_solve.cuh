@@ -692,13 +692,16 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
   // t1 = r1 + Q dx - A' dy - C' dz, rows of stage k
   for (int i = threadIdx.x; i < dk; i += blockDim.x) {
     double s = r1[xo + i];
+#pragma unroll 10
     for (int l = 0; l < dk; l++) s = fma(Qk[l * nm + i], xs[l], s);  // Q symmetric
     if (k < d.K) {
       if (i < nx) {
         const double *fx = d.fx + ks * nx * nx;
+#pragma unroll 10
         for (int l = 0; l < nx; l++) s = fma(-fx[l * nx + i], yk[l], s);
       } else {
         const double *fu = d.fu + ks * nx * nu;
+#pragma unroll 10
         for (int l = 0; l < nx; l++) s = fma(-fu[l * nu + (i - nx)], yk[l], s);
       }
     }
@@ -719,7 +722,9 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
     const double *fx = d.fx + ks * nx * nx, *fu = d.fu + ks * nx * nu;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
       double s = -dx[xo + nm + i];
+#pragma unroll 10
       for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
+#pragma unroll 10
       for (int l = 0; l < nu; l++) s = fma(fu[i * nu + l], xs[nx + l], s);
       const double t = r2[yo + (size_t)k * nx + i] - s;
       if (t2) t2[yo + (size_t)k * nx + i] = t;
