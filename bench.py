@@ -196,8 +196,11 @@ def run_ours(args, wl):
 
     N1 = 0  # bytes bookkeeping below
     update_sparse_ms = None
-    if world == 1:
-        # one horizon (or one batch of instances) on the GPU
+    sharded_instances = world > 1 and batch > 1
+    if world == 1 or sharded_instances:
+        # one horizon (or one batch of instances) on the GPU; with N > 1 GPUs a batch
+        # workload shards its independent instances: `batch` per rank, no collective
+        # in the KKT path
         p = synth_lqdocp(nx, nu, K, seed=1234)
         z, w, r1, r2, r3, r4 = synth_rhs(p, seed=4321)
         eng = IpCuda(p, batch=batch, device=local, nseg=args.nseg)
@@ -228,12 +231,11 @@ def run_ours(args, wl):
             del dst, dst2
         host = [rep(a) for a in (z, w, r1, r2, r3, r4)]
         lp = p
-        parallelism = "single"
+        parallelism = (f"{world} x {batch} independent instances, sharded over the ranks, no collective"
+                       if sharded_instances else "single")
     else:
         # horizon split: ONE horizon of world*K stages, contiguous
         # stage ranges per rank, boundary elements exchanged with all-gathers
-        if batch != 1:
-            raise RuntimeError("--gpus N > 1 is the horizon split of a single instance")
         from hqp_b200.dist import CudaRangeEngine, RangeSolver, local_vectors, split_problem
         pg = synth_lqdocp(nx, nu, K * world, seed=1234)
         gvec = synth_rhs(pg, seed=4321)
@@ -260,7 +262,7 @@ def run_ours(args, wl):
     from hqp_b200 import ipcuda as _ic
     L = _ic.lib()
 
-    if world == 1:
+    if world == 1 or sharded_instances:
         def unit_dev():
             eng.factor_dev(dvec[0].data_ptr(), dvec[1].data_ptr())
             for _ in range(2):
