@@ -395,6 +395,8 @@ def run_ours(args, wl):
         # the kernel that performs the algorithmic factor work of every stage
         kname = [k for k in per if k.startswith("seg_riccati_kernel")][0]
         kms = per[kname]
+        k1n = [k for k in per if k.strip("()").startswith("seg_element_kernel")]
+        bf_read = 8 * ((nx + nu) * (nx + nu + 1) // 2 + nx * (nx + nu) + 2 * mc)
         ach = K * batch * bf / (kms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak,
                     "unit": "GB/s", "frac": ach / peak,
@@ -404,6 +406,13 @@ def run_ours(args, wl):
                     "algorithmic_bytes_per_stage": {"factor": bf, "step": bs},
                     "algorithmic_flops_per_stage": {"factor": ff, "step": fs},
                     "kernel_ms_per_unit": per, "dominant_kernel": dom,
+                    # K1 (seg_element) is the parallel-in-time condensation: it reads the
+                    # same Q, fx, fu, z/w bytes as K3 and writes only P boundary elements;
+                    # its time is overhead of the algorithm, reported next to K3
+                    "k1_condensation": ({"kernel": k1n[0], "ms": per[k1n[0]],
+                                         "read_bytes_per_launch": K * batch * bf_read,
+                                         "frac_of_hbm": K * batch * bf_read / (per[k1n[0]] * 1e-3) / 1e9 / peak}
+                                        if k1n else None),
                     "factor_ms": t_factor, "step_ms": t_solve,
                     "factor_frac_of_hbm": K * batch * bf / (t_factor * 1e-3) / 1e9 / peak,
                     "step_frac_of_hbm": K * batch * bs / (t_solve * 1e-3) / 1e9 / peak}
