@@ -1046,7 +1046,7 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   const LqDev &d = h->d;
   const int spb = d.spw * LQ_WPB;
   const dim3 gk((d.K + spb - 1) / spb, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)LQ_WPB * (d.nx + d.nu) * sizeof(double);
+  const size_t sv = (size_t)LQ_WPB * (d.nx + d.nu + d.nu * d.nu) * sizeof(double);
   cudaStream_t s = h->stream;
   launch_scan(h, true, 1, h->stop(), 1, r2);
   for (int l = h->stop() - 1; l >= 0; l--)

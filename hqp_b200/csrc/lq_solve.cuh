@@ -552,8 +552,9 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const d
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *t = reinterpret_cast<double *>(smem_raw) + warp * (nx + nu);  // nx
-  double *Gu = t + nx;                                                   // nu
+  double *t = reinterpret_cast<double *>(smem_raw) + warp * (nx + nu + nu * nu);  // nx
+  double *Gu = t + nx;                                                            // nu
+  double *LDs = Gu + nu;                                                          // nu x nu
   const int b = blockIdx.y;
   for (int s = 0; s < SPW; s++) {
     const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
@@ -562,6 +563,13 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const d
     const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
     const double *fu = d.fu + ks * nx * nu;
     const double *g = d.g + (size_t)b * d.N + (size_t)k * nm;
+    // the factor of Guu goes to shared memory up front: the substitution below
+    // would otherwise pay a global-memory latency on each of its 2 nu dependent steps
+    {
+      const double *LDg = d.LD + ks * nu * nu;
+#pragma unroll 4
+      for (int i = lane; i < nu * nu; i += 32) LDs[i] = LDg[i];
+    }
     for (int i = lane; i < nx; i += 32) t[i] = vp[i] + d.q[ks * nx + i];
     __syncwarp();
     for (int j = lane; j < nu; j += 32) {
@@ -571,7 +579,7 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const d
       Gu[j] = a;
     }
     __syncwarp();
-    warp_ldlt_solve_g(d.LD + ks * nu * nu, nu, Gu, lane);
+    warp_ldlt_solve_g(LDs, nu, Gu, lane);
     for (int j = lane; j < nu; j += 32) d.Ru[ks * nu + j] = Gu[j];
     for (int i = lane; i < nx; i += 32) {
       double a = r2[(size_t)b * d.me + (size_t)k * nx + i];
