@@ -318,6 +318,12 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   {
     const char *env = getenv("HQPCU_SPW");
     d.spw = env ? std::max(1, std::min(2, atoi(env))) : (h->dims.batch >= 64 ? 2 : 1);
+    // lanes per stage: half a warp when a stage is at most 16 wide and there are
+    // enough of them (a full warp would leave most lanes idle); implies spw = 2
+    const char *lg = getenv("HQPCU_LANE_GROUP");
+    d.lgw = lg ? (atoi(lg) == 16 ? 16 : 32)
+               : ((h->dims.nx + h->dims.nu <= 16 && h->dims.batch >= 64) ? 16 : 32);
+    if (d.lgw == 16) d.spw = 2;
   }
   choose_seg_warps(h);
   build_tree(d.ft, P, 2);
@@ -1023,14 +1029,16 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
     g_err = "step before factor";
     return HQPCU_E_NULL;
   }
-  const int spb = d.spw * LQ_WPB;  // stages per CTA
+  const int spb = d.spw * LQ_WPB * (32 / d.lgw);  // stages per CTA
   const dim3 gall((d.K + 1 + spb - 1) / spb, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
+  const size_t sv = (size_t)LQ_WPB * (32 / d.lgw) * (d.nm + d.nx) * sizeof(double);
   cudaStream_t s = h->stream;
-  if (d.spw == 1)
-    LAUNCHP(h, solve_pre_kernel<1>, gall, 32 * LQ_WPB, sv, s, d, r1, r2, r3, r4);
+  if (d.lgw == 16)
+    LAUNCHP(h, (solve_pre_kernel<2, 16>), gall, 32 * LQ_WPB, sv, s, d, r1, r2, r3, r4);
+  else if (d.spw == 1)
+    LAUNCHP(h, (solve_pre_kernel<1, 32>), gall, 32 * LQ_WPB, sv, s, d, r1, r2, r3, r4);
   else
-    LAUNCHP(h, solve_pre_kernel<2>, gall, 32 * LQ_WPB, sv, s, d, r1, r2, r3, r4);
+    LAUNCHP(h, (solve_pre_kernel<2, 32>), gall, 32 * LQ_WPB, sv, s, d, r1, r2, r3, r4);
   // a single segment that is the whole horizon starts from known boundary
   // values: no zero-boundary pass
   if (d.P > 1 || h->ranged()) launch_back(h, 0);
@@ -1044,18 +1052,20 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
 // stage-parallel middle pass, zero-boundary forward chains, up-sweep
 static int launch_step_b(hqpcu_handle *h, const double *r2) {
   const LqDev &d = h->d;
-  const int spb = d.spw * LQ_WPB;
+  const int spb = d.spw * LQ_WPB * (32 / d.lgw);
   const dim3 gk((d.K + spb - 1) / spb, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)LQ_WPB * (d.nx + d.nu + d.nu * d.nu) * sizeof(double);
+  const size_t sv = (size_t)LQ_WPB * (32 / d.lgw) * (d.nx + d.nu + d.nu * d.nu) * sizeof(double);
   cudaStream_t s = h->stream;
   launch_scan(h, true, 1, h->stop(), 1, r2);
   for (int l = h->stop() - 1; l >= 0; l--)
     launch_scan(h, true, d.st.cnt[l + 1], l, 2, r2);
   launch_back(h, 1);
-  if (d.spw == 1)
-    LAUNCHP(h, solve_mid_kernel<1>, gk, 32 * LQ_WPB, sv, s, d, r2);
+  if (d.lgw == 16)
+    LAUNCHP(h, (solve_mid_kernel<2, 16>), gk, 32 * LQ_WPB, sv, s, d, r2);
+  else if (d.spw == 1)
+    LAUNCHP(h, (solve_mid_kernel<1, 32>), gk, 32 * LQ_WPB, sv, s, d, r2);
   else
-    LAUNCHP(h, solve_mid_kernel<2>, gk, 32 * LQ_WPB, sv, s, d, r2);
+    LAUNCHP(h, (solve_mid_kernel<2, 32>), gk, 32 * LQ_WPB, sv, s, d, r2);
   if (d.P > 1 || h->ranged()) launch_fwd(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, false, d.st.cnt[l + 1], l, 0, r2);
@@ -1068,18 +1078,20 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
 static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, const double *r4,
                          double *dx, double *dy, double *dz, double *dw) {
   const LqDev &d = h->d;
-  const int spb = d.spw * LQ_WPB;  // stages per CTA
+  const int spb = d.spw * LQ_WPB * (32 / d.lgw);  // stages per CTA
   const dim3 gall((d.K + 1 + spb - 1) / spb, d.batch), gseg(d.P, d.batch);
-  const size_t sv = (size_t)LQ_WPB * (d.nm + d.nx) * sizeof(double);
+  const size_t sv = (size_t)LQ_WPB * (32 / d.lgw) * (d.nm + d.nx) * sizeof(double);
   cudaStream_t s = h->stream;
   launch_scan(h, false, 1, h->stop(), 1, r2);
   for (int l = h->stop() - 1; l >= 0; l--)
     launch_scan(h, false, d.st.cnt[l + 1], l, 2, r2);
   launch_fwd(h, 1);
-  if (d.spw == 1)
-    LAUNCHP(h, solve_post_kernel<1>, gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
+  if (d.lgw == 16)
+    LAUNCHP(h, (solve_post_kernel<2, 16>), gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
+  else if (d.spw == 1)
+    LAUNCHP(h, (solve_post_kernel<1, 32>), gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
   else
-    LAUNCHP(h, solve_post_kernel<2>, gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
+    LAUNCHP(h, (solve_post_kernel<2, 32>), gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
   CU(cudaGetLastError());
   return HQPCU_OK;
 }

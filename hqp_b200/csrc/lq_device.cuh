@@ -36,6 +36,7 @@ struct LqDev {
   // horizon split across ranks (lq_range.cuh): this handle owns a contiguous
   // stage range of a longer horizon
   int spw;            // stages per warp of the stage-parallel solve passes
+  int lgw;            // lanes per stage there (32, or 16: two stages side by side)
   int has_prev;       // a rank before this one supplies the state at stage 0
   int has_next;       // a rank behind this one supplies the terminal value
   double *Vext;       // [nx*nx] value Hessian handed over from the ranks behind

@@ -310,52 +310,62 @@ __device__ __forceinline__ void chain_run_warp(const double *M, const double *a,
 
 // ---- pre ------------------------------------------------------------------
 // grid (ceil((K+1)/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nm + nx) doubles
-template <int SPW>
+// W lanes per stage (32: one stage per warp at a time; 16: two -- for nm <= 16 a
+// full warp per stage leaves more than half of the lanes idle).
+template <int SPW, int W>
 __global__ void __launch_bounds__(32 * LQ_WPB) solve_pre_kernel(
     LqDev d, const double *__restrict__ r1, const double *__restrict__ r2,
     const double *__restrict__ r3, const double *__restrict__ r4) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int G = 32 / W;
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *gk = reinterpret_cast<double *>(smem_raw) + warp * (nm + nx);  // nm
-  double *fk = gk + nm;                                                   // nx
+  const int sub = lane / W, sl = lane % W;
+  double *gk = reinterpret_cast<double *>(smem_raw) + (warp * G + sub) * (nm + nx);  // nm
+  double *fk = gk + nm;                                                              // nx
   const int b = blockIdx.y;
   const double *z = d.z + (size_t)b * d.m, *w = d.w + (size_t)b * d.m;
   const double *cv = d.cval + (size_t)b * d.nnz;
   const double *r3b = r3 + (size_t)b * d.m, *r4b = r4 + (size_t)b * d.m;
   for (int s = 0; s < SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
-    if (k > d.K) break;
+    const int k0 = (blockIdx.x * LQ_WPB + warp) * G * SPW + s;  // stage of lane group 0
+    if (k0 > d.K) break;                                        // (uniform in the warp)
+    const int k = k0 + sub * SPW;
+    const bool on = k <= d.K;
     const int dk = (k < d.K) ? nm : nx;
     const size_t xo = (size_t)b * d.N + (size_t)k * nm;
-    for (int i = lane; i < dk; i += 32) {
-      double a = -r1[xo + i];
-      const int gv = k * nm + i;
-      for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++) {
-        const int r = d.vcol_row[e];
-        a = fma(cv[d.vcol_nz[e]], (z[r] * r3b[r] + r4b[r]) / w[r], a);
+    if (on) {
+      for (int i = sl; i < dk; i += W) {
+        double a = -r1[xo + i];
+        const int gv = k * nm + i;
+        for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++) {
+          const int r = d.vcol_row[e];
+          a = fma(cv[d.vcol_nz[e]], (z[r] * r3b[r] + r4b[r]) / w[r], a);
+        }
+        gk[i] = a;
+        d.g[xo + i] = a;
       }
-      gk[i] = a;
-      d.g[xo + i] = a;
+      if (k < d.K)
+        for (int i = sl; i < nx; i += W) fk[i] = r2[(size_t)b * d.me + (size_t)k * nx + i];
     }
-    if (k < d.K)
-      for (int i = lane; i < nx; i += 32) fk[i] = r2[(size_t)b * d.me + (size_t)k * nx + i];
     __syncwarp();
-    if (k == d.K) {
-      for (int i = lane; i < nx; i += 32) d.v[((size_t)b * (d.K + 1) + k) * nx + i] = gk[i];
-    } else {
-      const size_t ks = (size_t)b * d.K + k;
-      const double *Rux = d.Rux + ks * nu * nx;
-      const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
-      for (int i = lane; i < nx; i += 32) {
-        double a0 = gk[i], a1 = 0.0;
+    if (on) {
+      if (k == d.K) {
+        for (int i = sl; i < nx; i += W) d.v[((size_t)b * (d.K + 1) + k) * nx + i] = gk[i];
+      } else {
+        const size_t ks = (size_t)b * d.K + k;
+        const double *Rux = d.Rux + ks * nu * nx;
+        const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
+        for (int i = sl; i < nx; i += W) {
+          double a0 = gk[i], a1 = 0.0;
 #pragma unroll 10
-        for (int l = 0; l < nu; l++) a0 = fma(-Rux[l * nx + i], gk[nx + l], a0);
+          for (int l = 0; l < nu; l++) a0 = fma(-Rux[l * nx + i], gk[nx + l], a0);
 #pragma unroll 10
-        for (int l = 0; l < nx; l++) a1 = fma(Vp[l * nx + i], fk[l], a1);  // Vxx symmetric
-        d.wv[ks * nx + i] = a0;
-        d.q[ks * nx + i] = a1;
+          for (int l = 0; l < nx; l++) a1 = fma(Vp[l * nx + i], fk[l], a1);  // Vxx symmetric
+          d.wv[ks * nx + i] = a0;
+          d.q[ks * nx + i] = a1;
+        }
       }
     }
     __syncwarp();
@@ -526,66 +536,82 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
 // warp-cooperative solve of (L D L') y = b, y in shared memory (m <= 32 per pass
 // of 32 lanes; larger m loops).  LD row-major in GLOBAL memory (ld = m): the
 // column sweeps read it once, coalesced per column pair.
+// `sl`, W: lane index inside, and width of, the lane group that owns this system
+// (W = 32: the whole warp; W = 16: two systems per warp).  `on` = false: the group
+// has no system but takes part in the warp barriers.
 __device__ __forceinline__ void warp_ldlt_solve_g(const double *__restrict__ LD, int m,
-                                                  double *y, int lane) {
+                                                  double *y, int sl, int W = 32,
+                                                  bool on = true) {
   // forward: for each column l, rows i > l subtract L[i][l] y[l]
   for (int l = 0; l < m; l++) {
-    const double yl = y[l];
-    for (int i = l + 1 + lane; i < m; i += 32) y[i] = fma(-LD[i * m + l], yl, y[i]);
+    if (on) {
+      const double yl = y[l];
+      for (int i = l + 1 + sl; i < m; i += W) y[i] = fma(-LD[i * m + l], yl, y[i]);
+    }
     __syncwarp();
   }
-  for (int i = lane; i < m; i += 32) y[i] *= LD[i * m + i];
+  if (on)
+    for (int i = sl; i < m; i += W) y[i] *= LD[i * m + i];
   __syncwarp();
   // backward: for each row l (descending), entries i < l subtract L[l][i] y[l]
   for (int l = m - 1; l > 0; l--) {
-    const double yl = y[l];
-    for (int i = lane; i < l; i += 32) y[i] = fma(-LD[l * m + i], yl, y[i]);
+    if (on) {
+      const double yl = y[l];
+      for (int i = sl; i < l; i += W) y[i] = fma(-LD[l * m + i], yl, y[i]);
+    }
     __syncwarp();
   }
 }
 
 // ---- mid -------------------------------------------------------------------
 // grid (ceil(K/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nx + nu) doubles
-template <int SPW>
+template <int SPW, int W>
 __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const double *__restrict__ r2) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int G = 32 / W;
   const int nx = d.nx, nu = d.nu, nm = d.nm;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *t = reinterpret_cast<double *>(smem_raw) + warp * (nx + nu + nu * nu);  // nx
-  double *Gu = t + nx;                                                            // nu
-  double *LDs = Gu + nu;                                                          // nu x nu
+  const int sub = lane / W, sl = lane % W;
+  double *t = reinterpret_cast<double *>(smem_raw) + (warp * G + sub) * (nx + nu + nu * nu);  // nx
+  double *Gu = t + nx;                                                                        // nu
+  double *LDs = Gu + nu;                                                                      // nu x nu
   const int b = blockIdx.y;
   for (int s = 0; s < SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
-    if (k >= d.K) break;
-    const size_t ks = (size_t)b * d.K + k;
-    const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
+    const int k0 = (blockIdx.x * LQ_WPB + warp) * G * SPW + s;
+    if (k0 >= d.K) break;  // (uniform in the warp)
+    const int k = k0 + sub * SPW;
+    const bool on = k < d.K;
+    const size_t ks = (size_t)b * d.K + (on ? k : 0);
+    const double *vp = d.v + ((size_t)b * (d.K + 1) + (on ? k : 0) + 1) * nx;
     const double *fu = d.fu + ks * nx * nu;
-    const double *g = d.g + (size_t)b * d.N + (size_t)k * nm;
-    // the factor of Guu goes to shared memory up front: the substitution below
-    // would otherwise pay a global-memory latency on each of its 2 nu dependent steps
-    {
+    const double *g = d.g + (size_t)b * d.N + (size_t)(on ? k : 0) * nm;
+    if (on) {
+      // the factor of Guu goes to shared memory up front: the substitution below
+      // would otherwise pay a global-memory latency on each of its 2 nu dependent steps
       const double *LDg = d.LD + ks * nu * nu;
 #pragma unroll 4
-      for (int i = lane; i < nu * nu; i += 32) LDs[i] = LDg[i];
-    }
-    for (int i = lane; i < nx; i += 32) t[i] = vp[i] + d.q[ks * nx + i];
-    __syncwarp();
-    for (int j = lane; j < nu; j += 32) {
-      double a = g[nx + j];
-#pragma unroll 10
-      for (int l = 0; l < nx; l++) a = fma(fu[l * nu + j], t[l], a);
-      Gu[j] = a;
+      for (int i = sl; i < nu * nu; i += W) LDs[i] = LDg[i];
+      for (int i = sl; i < nx; i += W) t[i] = vp[i] + d.q[ks * nx + i];
     }
     __syncwarp();
-    warp_ldlt_solve_g(LDs, nu, Gu, lane);
-    for (int j = lane; j < nu; j += 32) d.Ru[ks * nu + j] = Gu[j];
-    for (int i = lane; i < nx; i += 32) {
-      double a = r2[(size_t)b * d.me + (size_t)k * nx + i];
+    if (on)
+      for (int j = sl; j < nu; j += W) {
+        double a = g[nx + j];
 #pragma unroll 10
-      for (int l = 0; l < nu; l++) a = fma(-fu[i * nu + l], Gu[l], a);
-      d.c[ks * nx + i] = a;
+        for (int l = 0; l < nx; l++) a = fma(fu[l * nu + j], t[l], a);
+        Gu[j] = a;
+      }
+    __syncwarp();
+    warp_ldlt_solve_g(LDs, nu, Gu, sl, W, on);
+    if (on) {
+      for (int j = sl; j < nu; j += W) d.Ru[ks * nu + j] = Gu[j];
+      for (int i = sl; i < nx; i += W) {
+        double a = r2[(size_t)b * d.me + (size_t)k * nx + i];
+#pragma unroll 10
+        for (int l = 0; l < nu; l++) a = fma(-fu[i * nu + l], Gu[l], a);
+        d.c[ks * nx + i] = a;
+      }
     }
     __syncwarp();
   }
@@ -593,7 +619,7 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const d
 
 // ---- post -------------------------------------------------------------------
 // grid (ceil((K+1)/(spw*LQ_WPB)), batch), block 32*LQ_WPB; smem: LQ_WPB * (nm + nx) doubles
-template <int SPW>
+template <int SPW, int W>
 __global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
     LqDev d, const double *__restrict__ r3, const double *__restrict__ r4,
     double *__restrict__ dx, double *__restrict__ dy, double *__restrict__ dz,
@@ -601,24 +627,29 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
+  constexpr int G = 32 / W;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *xs = reinterpret_cast<double *>(smem_raw) + warp * (nm + nx);  // nm: [x_k ; u_k] -> dx
+  const int sub = lane / W, sl = lane % W;
+  double *xs = reinterpret_cast<double *>(smem_raw) + (warp * G + sub) * (nm + nx);  // nm: [x_k ; u_k] -> dx
   double *xn = xs + nm;                                                   // nx: x_{k+1}
   const int b = blockIdx.y;
   const double *cv = d.cval + (size_t)b * d.nnz;
   for (int s = 0; s < SPW; s++) {
-    const int k = (blockIdx.x * LQ_WPB + warp) * SPW + s;
-    if (k > d.K) break;
-    const double *xk = d.x + ((size_t)b * (d.K + 1) + k) * nx;
+    const int k0 = (blockIdx.x * LQ_WPB + warp) * G * SPW + s;
+    if (k0 > d.K) break;  // (uniform in the warp)
+    const int k = k0 + sub * SPW;
+    const bool on = k <= d.K;
+    const double *xk = d.x + ((size_t)b * (d.K + 1) + (on ? k : 0)) * nx;
     const size_t ks = (size_t)b * d.K + k;
-    for (int i = lane; i < nx; i += 32) {
-      xs[i] = xk[i];
-      if (k < d.K) xn[i] = xk[nx + i];
-    }
+    if (on)
+      for (int i = sl; i < nx; i += W) {
+        xs[i] = xk[i];
+        if (k < d.K) xn[i] = xk[nx + i];
+      }
     __syncwarp();
-    if (k < d.K) {
+    if (on && k < d.K) {
       const double *Rux = d.Rux + ks * nu * nx;
-      for (int j = lane; j < nu; j += 32) {
+      for (int j = sl; j < nu; j += W) {
         double a = d.Ru[ks * nu + j];
 #pragma unroll 10
         for (int l = 0; l < nx; l++) a = fma(Rux[j * nx + l], xs[l], a);
@@ -627,17 +658,17 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
       // p_k = Vxx[k+1] x[k+1] + v[k+1]   (:2169-2171)
       const double *Vp = d.V + ((size_t)b * (d.K + 1) + k + 1) * nx * nx;
       const double *vp = d.v + ((size_t)b * (d.K + 1) + k + 1) * nx;
-      for (int i = lane; i < nx; i += 32) {
+      for (int i = sl; i < nx; i += W) {
         double a = vp[i];
 #pragma unroll 10
         for (int l = 0; l < nx; l++) a = fma(Vp[l * nx + i], xn[l], a);
         dy[(size_t)b * d.me + (size_t)k * nx + i] = a;
       }
     }
-    if (k == 0 && d.fixed_x0) {  // y_0 = -(Vx[0] + Vxx[0] x_0)   (:2153-2159)
+    if (on && k == 0 && d.fixed_x0) {  // y_0 = -(Vx[0] + Vxx[0] x_0)   (:2153-2159)
       const double *V0 = d.V + (size_t)b * (d.K + 1) * nx * nx;
       const double *v0 = d.v + (size_t)b * (d.K + 1) * nx;
-      for (int i = lane; i < nx; i += 32) {
+      for (int i = sl; i < nx; i += W) {
         double a = v0[i];
 #pragma unroll 10
         for (int l = 0; l < nx; l++) a = fma(V0[l * nx + i], xs[l], a);
@@ -647,23 +678,25 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
     __syncwarp();
     const int dk = (k < d.K) ? nm : nx;
     // dx = -[x;u]   (:952)
-    for (int i = lane; i < dk; i += 32) {
-      const double a = -xs[i];
-      xs[i] = a;
-      dx[(size_t)b * d.N + (size_t)k * nm + i] = a;
-    }
+    if (on)
+      for (int i = sl; i < dk; i += W) {
+        const double a = -xs[i];
+        xs[i] = a;
+        dx[(size_t)b * d.N + (size_t)k * nm + i] = a;
+      }
     __syncwarp();
     // dw = C dx - r3 ; dz = (r4 - z dw)/w   (:955-960)
-    for (int rr = d.srow_ptr[k] + lane; rr < d.srow_ptr[k + 1]; rr += 32) {
-      const int r = d.srow[rr];
-      double a = 0.0;
-      for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
-        a = fma(cv[e], xs[d.ineq_lcol[e]], a);
-      const size_t ro = (size_t)b * d.m + r;
-      const double dwr = a - r3[ro];
-      dw[ro] = dwr;
-      dz[ro] = (r4[ro] - d.z[ro] * dwr) / d.w[ro];
-    }
+    if (on)
+      for (int rr = d.srow_ptr[k] + sl; rr < d.srow_ptr[k + 1]; rr += W) {
+        const int r = d.srow[rr];
+        double a = 0.0;
+        for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
+          a = fma(cv[e], xs[d.ineq_lcol[e]], a);
+        const size_t ro = (size_t)b * d.m + r;
+        const double dwr = a - r3[ro];
+        dw[ro] = dwr;
+        dz[ro] = (r4[ro] - d.z[ro] * dwr) / d.w[ro];
+      }
     __syncwarp();
   }
 }
