@@ -380,11 +380,28 @@ template <int NW>
 __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, int ldc0,
                                           double beta, double alpha, const double *A, int ar,
                                           int ac, const double *B, int br, int bc, int M, int N,
-                                          int Kd, int wofs = 0, int warp_id = -1) {
+                                          int Kd, int wofs = 0, int warp_id = -1,
+                                          bool lower = false) {
   // warp_id >= 0: the product is shared by a subset of NW warps numbered 0..NW-1
   const int lane = threadIdx.x & 31, warp = warp_id >= 0 ? warp_id : (int)(threadIdx.x >> 5);
   const int g = lane >> 2, t = lane & 3;
   const int TI = (M + 7) >> 3, TJ = (N + 7) >> 3;
+  if (lower) {
+    // symmetric result (M == N): only the tiles on and below the diagonal; the
+    // caller mirrors them (cta_symmetrize_tc, mirror mode).  Per tile row:
+    // 1x2 blocks and, for an odd count, the diagonal tile alone.
+    int u = 0;
+#pragma unroll
+    for (int ti = 0; ti < TI; ti++) {
+#pragma unroll
+      for (int tj = 0; tj <= ti; tj += 2, u++) {
+        if (NW == 1 || warp == (u + wofs) % NW)
+          mm_tc_block<1, 2>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, ti, tj,
+                            1, g, t, tj + 1 <= ti ? 2 : 1);
+      }
+    }
+    return;
+  }
   if constexpr (NW == 1) {
     // one warp owns the whole product: 3x3 blocks, 6 fragment loads per 9 DMMAs
 #pragma unroll
@@ -420,9 +437,11 @@ template <bool TC, int NW = LQ_NT / 32>
 __device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
                                         double beta, double alpha, const double *A, int ar,
                                         int ac, const double *B, int br, int bc, int M, int N,
-                                        int Kd, int wofs = 0, int warp_id = -1) {
+                                        int Kd, int wofs = 0, int warp_id = -1,
+                                        bool lower = false) {
   if constexpr (TC) {
-    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs, warp_id);
+    cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs, warp_id,
+                  lower);
   } else {
     if (warp_id >= 0)  // subset of NW warps
       cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd,
@@ -450,8 +469,11 @@ __device__ __forceinline__ void cta_symmetrize(double *A, int lda, int n) {
 // element fetched with shuffles, row-wise double2 writes -- no column-strided
 // shared-memory access (the element-wise version above spends ~1.5 k cycles per
 // call on 4-way bank conflicts at lda = 20).  lda and n even, A 16-byte aligned.
+// mirror = true: the tiles above the diagonal are stale (product computed with
+// `lower`): they are overwritten with the transposed lower tiles, only the
+// diagonal tiles are averaged.
 template <int NW>
-__device__ __forceinline__ void cta_symmetrize_tc(double *A, int lda, int n) {
+__device__ __forceinline__ void cta_symmetrize_tc(double *A, int lda, int n, bool mirror = false) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int TN = (n + 7) >> 3;
@@ -475,10 +497,13 @@ __device__ __forceinline__ void cta_symmetrize_tc(double *A, int lda, int n) {
       const double bx1 = __shfl_sync(0xffffffffu, b2.x, s1), by1 = __shfl_sync(0xffffffffu, b2.y, s1);
       const double ax0 = __shfl_sync(0xffffffffu, a.x, s0), ay0 = __shfl_sync(0xffffffffu, a.y, s0);
       const double ax1 = __shfl_sync(0xffffffffu, a.x, s1), ay1 = __shfl_sync(0xffffffffu, a.y, s1);
-      const double2 an = make_double2(0.5 * (a.x + (odd ? by0 : bx0)), 0.5 * (a.y + (odd ? by1 : bx1)));
+      const bool copy = mirror && ti != tj;
+      const double2 an = copy ? make_double2(odd ? by0 : bx0, odd ? by1 : bx1)
+                              : make_double2(0.5 * (a.x + (odd ? by0 : bx0)),
+                                             0.5 * (a.y + (odd ? by1 : bx1)));
       const double2 bn = make_double2(0.5 * (b2.x + (odd ? ay0 : ax0)), 0.5 * (b2.y + (odd ? ay1 : ax1)));
       if (va) *reinterpret_cast<double2 *>(A + (i0 + g) * lda + j0 + 2 * t) = an;
-      if (ti != tj && vb) *reinterpret_cast<double2 *>(A + (j0 + g) * lda + i0 + 2 * t) = bn;
+      if (ti != tj && !copy && vb) *reinterpret_cast<double2 *>(A + (j0 + g) * lda + i0 + 2 * t) = bn;
     }
   }
 }

@@ -235,7 +235,8 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, in
   LQ_STAMP2(2);
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
-    cta_mmx<TC, NW>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx);
+    // (Gxx and V are symmetric: tiles on and below the diagonal only, mirrored later)
+    cta_mmx<TC, NW>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx, 0, -1, TC);
     cta_mmx<TC, NW>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
     cta_mmx<TC, NW>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
                 nu, nu, nx, 3);
@@ -287,10 +288,11 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, in
   __syncthreads();
   LQ_STAMP2(5);
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W' = Yt' Wt
-  cta_mmx<TC, NW>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu);
+  cta_mmx<TC, NW>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu, 0, -1, TC);
   cta_mmx<TC, NW>(Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
   if (el)
-    cta_mmx<TC, NW>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu);
+    cta_mmx<TC, NW>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu, 2,
+                    -1, TC);
   __syncthreads();
 }
 
@@ -343,12 +345,12 @@ seg_element_kernel(LqDev d) {
     riccati_stage<NU, TC, NW>(nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
                           sp.G(buf), T, Rux, Phi, &st_s, &el);
     // J symmetrised ; A <- A Phi, i.e. At <- Phi' At
-    if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx); else cta_symmetrize(J, LV, nx);
+    if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx, true); else cta_symmetrize(J, LV, nx);
     cta_mmx<TC, NW>(Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
     double *t = At; At = Atn; Atn = t;
     __syncthreads();
   }
-  cta_symmetrize(Cg, LV, nx);
+  if constexpr (TC) cta_symmetrize_tc<NW>(Cg, LV, nx, true); else cta_symmetrize(Cg, LV, nx);
   __syncthreads();
   const size_t o = ((size_t)b * d.ft.nel + s) * nx * nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
@@ -639,7 +641,7 @@ seg_riccati_kernel(LqDev d) {
     LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;
     double *Lk = d.LD + ks * nu * nu;
-    if constexpr (TC) cta_symmetrize_tc<NW>(V, LV, nx); else cta_symmetrize(V, LV, nx);
+    if constexpr (TC) cta_symmetrize_tc<NW>(V, LV, nx, true); else cta_symmetrize(V, LV, nx);
     for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) {
       const int r = i / nu, c = i - r * nu;
       Lk[i] = G[(nx + r) * nm + nx + c];
