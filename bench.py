@@ -41,7 +41,7 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel
 # (seg_riccati_kernel) from the committed `ncu --set full` capture; null where no
 # capture exists.  Compare with K * algorithmic bytes per stage (C2: 160.4 MB).
-NCU_TRAFFIC = {"c2": (124.024064e6 + 51.595776e6, "profiles/r01_ncu_full_k1k3_v4.md (K3 section)")}
+NCU_TRAFFIC = {"c2": (124.024832e6 + 50.681344e6, "profiles/r01_ncu_full_k1k3_v7.md (K3 section)")}
 METRIC = "LQ-DOCP KKT factor+solve stages/s"
 UNIT = "stages/s"
 
