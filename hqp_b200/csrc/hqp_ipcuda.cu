@@ -18,7 +18,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "lq_device.cuh"
@@ -60,6 +63,20 @@ static thread_local std::string g_err;
     }                                                                         \
   } while (0)
 
+// end of a launch sequence: the first launch error of the sequence (LAUNCHP
+// records cudaLaunchKernelEx's status) or whatever the runtime still holds
+#define CUL(h)                                                                \
+  do {                                                                        \
+    cudaError_t e_ = (h)->launch_err;                                         \
+    (h)->launch_err = cudaSuccess;                                            \
+    const cudaError_t g_ = cudaGetLastError();                                \
+    if (e_ == cudaSuccess) e_ = g_;                                           \
+    if (e_ != cudaSuccess) {                                                  \
+      g_err = std::string("kernel launch: ") + cudaGetErrorString(e_);        \
+      return HQPCU_E_CUDA;                                                    \
+    }                                                                         \
+  } while (0)
+
 struct IpsState;
 
 struct hqpcu_handle {
@@ -70,9 +87,11 @@ struct hqpcu_handle {
   hqpcu_dims dims;
   cudaStream_t stream = nullptr;
   long long launches = 0;
+  cudaError_t launch_err = cudaSuccess;  // first failed cudaLaunchKernelEx since the last check
   long long n_solves = 0, n_solve_steps = 0;  // hqpcu_solve_stats
   int device = 0;
-  int nseg_req = 0;
+  int nseg_req = 0;       // segment count asked for (0 = automatic); hqpcu_set_nseg updates it
+  bool demoted = false;   // E_NOTPD fallback to the sequential sweep is in force until the next update
   std::vector<void *> allocs;
   // owned device copies
   double *Q = nullptr, *fx = nullptr, *fu = nullptr, *cval = nullptr, *z = nullptr, *w = nullptr;
@@ -167,7 +186,11 @@ static cudaError_t launch_ex(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3
       cudaEventCreate(&sp_.e1);                                               \
       cudaEventRecord(sp_.e0, (h)->stream);                                   \
     }                                                                         \
-    launch_ex((h)->use_pdl && !(h)->profiling, kname, grid_, block_, smem_, strm_, __VA_ARGS__); \
+    {                                                                         \
+      const cudaError_t le_ = launch_ex((h)->use_pdl && !(h)->profiling, kname, grid_, block_,    \
+                                        smem_, strm_, __VA_ARGS__);                               \
+      if (le_ != cudaSuccess && (h)->launch_err == cudaSuccess) (h)->launch_err = le_;            \
+    }                                                                         \
     (h)->launches++;                                                          \
     if ((h)->profiling) {                                                     \
       cudaEventRecord(sp_.e1, (h)->stream);                                   \
@@ -334,9 +357,20 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   build_tree(d.st, P, R);
 }
 
+// The attribute is global per function and device: handles with different block
+// sizes share it, so it is only ever raised (a smaller, later handle must not
+// lower the limit under an earlier one).
 static int set_smem(const void *fn, size_t bytes) {
-  if (bytes > 48 * 1024)
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> cur;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  size_t &have = cur[{dev, fn}];
+  if (bytes > 48 * 1024 && bytes > have) {
     CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+  }
   // all of the L1/shared array as shared memory: these kernels live in shared
   // memory and their occupancy is bounded by it (ncu: occupancy_limit_shared_mem)
   CU(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -654,6 +688,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(set_smem((const void *)(solve_scan_kernel<false, NX_>), h->smem_scan));
   LQ_DISPATCH_NX(nx, nu, SET_C);
 #undef SET_C
+  if (dims->n_eq)
+    TRY(set_smem((const void *)eq_invert_kernel, (size_t)3 * dims->n_eq * dims->n_eq * sizeof(double)));
 #undef TRY
   *out = h;
   return HQPCU_OK;
@@ -690,9 +726,18 @@ int hqpcu_solve_stats(const hqpcu_handle *h, long long *solves, long long *steps
 int hqpcu_nseg(const hqpcu_handle *h) { return h ? h->d.P : 0; }
 
 // ------------------------------------------------------------------ update --
+// new matrix values: a sequential-sweep fallback taken for the previous values
+// (E_NOTPD at a segment end) ends here
+static void undo_demotion(hqpcu_handle *h) {
+  if (!h->demoted) return;
+  h->demoted = false;
+  choose_segments(h, h->nseg_req);
+}
+
 static int update_impl(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
                        const double *cv, const double *ev, cudaMemcpyKind kind) {
   if (!h || !Q || !fx || !fu || (h->d.nnz && !cv) || (h->q.nnz && !ev)) return HQPCU_E_NULL;
+  undo_demotion(h);
   const LqDev &d = h->d;
   const size_t B = d.batch;
   CU(cudaSetDevice(h->device));
@@ -771,6 +816,7 @@ int hqpcu_update_values(hqpcu_handle *h, const double *vals, const double *ineq_
                         const double *eq_val) {
   if (!h || !h->vm_dst || (h->vm_n && !vals) || (h->d.nnz && !ineq_val) || (h->q.nnz && !eq_val))
     return HQPCU_E_NULL;
+  undo_demotion(h);
   const LqDev &d = h->d;
   CU(cudaSetDevice(h->device));
   cudaStream_t s = h->stream;
@@ -785,7 +831,7 @@ int hqpcu_update_values(hqpcu_handle *h, const double *vals, const double *ineq_
     LAUNCH(h, scatter_values_kernel, <<<blocks, 256, 0, s>>>(h->vm_n, h->vm_vals, h->vm_dst, h->vm_dst2,
                                                             h->Q, h->fx, h->fu, (long long)szQ,
                                                             (long long)szX));
-    CU(cudaGetLastError());
+    CUL(h);
   }
   if (d.nnz)
     CU(cudaMemcpyAsync(h->cval, ineq_val, d.nnz * sizeof(double), cudaMemcpyHostToDevice, s));
@@ -831,7 +877,7 @@ static int launch_eq_factor(hqpcu_handle *h) {
   }
   LAUNCH(h, eq_schur_kernel, <<<(ne * ne + 127) / 128, 128, 0, s>>>(d, q));
   LAUNCH(h, eq_invert_kernel, <<<1, 128, (size_t)3 * ne * ne * sizeof(double), s>>>(d, q));
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -876,7 +922,7 @@ static int launch_factor_up(hqpcu_handle *h) {
       LQ_DISPATCH_NX(d.nx, d.nu, L_CMP);
     }
   }
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -898,8 +944,7 @@ static int launch_factor_down(hqpcu_handle *h) {
   if (!d.fixed_x0 && !d.has_prev)
     LAUNCH(h, x0_factor_kernel,
            <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
-  CU(cudaGetLastError());
-  h->factored = true;
+  CUL(h);
   return HQPCU_OK;
 }
 #undef L_K1
@@ -951,20 +996,28 @@ int hqpcu_factor_dev(hqpcu_handle *h, const double *z, const double *w) {
   return factor_impl(h, z, w, cudaMemcpyDeviceToDevice);
 }
 
-int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w) {
-  int rc = factor_impl(h, z, w, cudaMemcpyHostToDevice);
-  if (rc) return rc;
-  rc = read_status(h);
-  if (rc == HQPCU_E_NOTPD && h->d.P > 1) {
-    // the zero-terminal-cost segment condensation needs Huu > 0 at segment
-    // ends; fall back to the sequential sweep ON THE GPU (still no CPU path)
+// Synchronise on a factor that was just enqueued and act on its status.  The
+// zero-terminal-cost segment condensation needs Huu > 0 at segment ends: on
+// E_NOTPD the factor is repeated as the sequential sweep ON THE GPU (still no CPU
+// path).  The demotion holds for the matrix values that caused it -- the next
+// hqpcu_update* restores the configured segment count (undo_demotion).
+static int finish_factor(hqpcu_handle *h) {
+  int rc = read_status(h);
+  if (rc == HQPCU_E_NOTPD && h->d.P > 1 && !h->ranged()) {
     choose_segments(h, 1);
+    h->demoted = true;
     rc = launch_factor(h);
     if (rc) return rc;
     rc = read_status(h);
   }
   if (rc == HQPCU_E_NOTPD) rc = HQPCU_OK;  // indefinite but non-singular: accepted
   return rc;
+}
+
+int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w) {
+  int rc = factor_impl(h, z, w, cudaMemcpyHostToDevice);
+  if (rc) return rc;
+  return finish_factor(h);
 }
 
 // status of everything enqueued so far by the _dev entry points (synchronises)
@@ -983,6 +1036,8 @@ int hqpcu_set_nseg(hqpcu_handle *h, int nseg) {
     g_err = "hqpcu_set_nseg: cannot exceed the segment count of hqpcu_create";
     return HQPCU_E_SIZES;
   }
+  h->nseg_req = nseg;
+  h->demoted = false;
   h->factored = false;
   return HQPCU_OK;
 }
@@ -1044,7 +1099,7 @@ static int launch_step_a(hqpcu_handle *h, const double *r1, const double *r2, co
   if (d.P > 1 || h->ranged()) launch_back(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, true, d.st.cnt[l + 1], l, 0, r2);
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -1069,7 +1124,7 @@ static int launch_step_b(hqpcu_handle *h, const double *r2) {
   if (d.P > 1 || h->ranged()) launch_fwd(h, 0);
   for (int l = 0; l < h->stop(); l++)
     launch_scan(h, false, d.st.cnt[l + 1], l, 0, r2);
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -1092,7 +1147,7 @@ static int launch_step_c(hqpcu_handle *h, const double *r2, const double *r3, co
     LAUNCHP(h, (solve_post_kernel<1, 32>), gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
   else
     LAUNCHP(h, (solve_post_kernel<2, 32>), gall, 32 * LQ_WPB, sv, s, d, r3, r4, dx, dy, dz, dw);
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -1119,7 +1174,7 @@ static int launch_step_plain(hqpcu_handle *h, const double *r1, const double *r2
   LAUNCH(h, eq_multiplier_kernel, <<<1, 64, (size_t)(h->q.n_eq + 2) * sizeof(double), s>>>(d, h->q, r2, dx));
   const int blocks = (int)std::min<size_t>(((size_t)d.N + 255) / 256, 148 * 8);
   LAUNCH(h, eq_combine_kernel, <<<blocks, 256, 0, s>>>(d, h->q, dx, dy, dz, dw));
-  CU(cudaGetLastError());
+  CUL(h);
   return HQPCU_OK;
 }
 
@@ -1195,7 +1250,7 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
       d, r1, r2, r3, r4, dx, dy, dz, dw, keep ? h->t1 : nullptr, keep ? h->t2 : nullptr,
       keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev,
       h->q.n_eq ? h->q.ety : nullptr));
-  CU(cudaGetLastError());
+  CUL(h);
   CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *res = *h->res_host;
@@ -1323,7 +1378,7 @@ int hqpcu_range_factor_begin(hqpcu_handle *h, const double *z, const double *w, 
     int rc = launch_factor_up(h);
     if (rc) return rc;
     LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(h->d, xf));
-    CU(cudaGetLastError());
+    CUL(h);
     return (int)HQPCU_OK;
   });
 }
@@ -1333,7 +1388,7 @@ int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank,
   if (!h || !gathered || !xpsi) return HQPCU_E_NULL;
   const LqDev &d = h->d;
   CU(cudaSetDevice(h->device));
-  return run_graphed(
+  const int rc = run_graphed(
       h, {(const void *)(uintptr_t)11, gathered, xpsi, (const void *)(uintptr_t)rank,
           (const void *)(uintptr_t)world},
       [&]() {
@@ -1348,11 +1403,17 @@ int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank,
                            n2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
         return (int)HQPCU_OK;
       });
+  if (!rc) h->factored = true;  // (not inside the body: a graph replay does not run it)
+  return rc;
 }
 
 int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
                            const double *r3, const double *r4, double *xv) {
   if (!h || !r1 || !r2 || !xv) return HQPCU_E_NULL;
+  if (!h->factored) {
+    g_err = "step before factor";
+    return HQPCU_E_NULL;
+  }
   CU(cudaSetDevice(h->device));
   h->rg_r1 = r1; h->rg_r2 = r2; h->rg_r3 = r3; h->rg_r4 = r4;
   return run_graphed(h, {(const void *)(uintptr_t)12, r1, r2, r3, r4, xv}, [&]() {
@@ -1360,7 +1421,7 @@ int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
     if (rc) return rc;
     LAUNCH(h, range_export_vec_kernel<true>,
            <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, r2, xv));
-    CU(cudaGetLastError());
+    CUL(h);
     return (int)HQPCU_OK;
   });
 }
@@ -1368,6 +1429,10 @@ int hqpcu_range_step_begin(hqpcu_handle *h, const double *r1, const double *r2,
 int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, int rank,
                          int world, double *xx) {
   if (!h || !gv || !gpsi || !xx) return HQPCU_E_NULL;
+  if (!h->factored) {
+    g_err = "step before factor";
+    return HQPCU_E_NULL;
+  }
   CU(cudaSetDevice(h->device));
   const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
   const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
@@ -1380,7 +1445,7 @@ int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, 
         if (rc) return rc;
         LAUNCH(h, range_export_vec_kernel<false>,
                <<<1, 64, (size_t)(h->d.nx + 2) * sizeof(double), h->stream>>>(h->d, h->rg_r2, xx));
-        CU(cudaGetLastError());
+        CUL(h);
         return (int)HQPCU_OK;
       });
 }
@@ -1388,6 +1453,10 @@ int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, 
 int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gpsi, int rank,
                             int world, double *dx, double *dy, double *dz, double *dw) {
   if (!h || !gx || !gpsi || !dx || !dy) return HQPCU_E_NULL;
+  if (!h->factored) {
+    g_err = "step before factor";
+    return HQPCU_E_NULL;
+  }
   CU(cudaSetDevice(h->device));
   const int thr = std::max(64, ((h->d.nx + 31) / 32) * 32);
   const size_t sm = (size_t)(2 * h->d.nx + 2) * sizeof(double);
