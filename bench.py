@@ -2,18 +2,29 @@
 """KKT factor+solve throughput of the Hqp_IpCuda engine (BASELINE.json metric).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--workload c2|c3|c5s]
+                  [--workload c2|c3|c5|c5s] [--no-extra]
 
 One "step" = one unit of interior-point KKT work on one synthetic LQ-DOCP
 horizon: 1 factor + 2 step (Mehrotra predictor + corrector).
-`value` = stages/s = K_stages * batch * n_gpus / step time, device-timed with
+`value` = stages/s = stages of the whole job / step time, device-timed with
 inputs resident in HBM; `e2e` = the same through the host-pointer C-ABI calls
-(pinned host buffers, H2D/D2H inside the timed region).
+the Hqp_IpCuda plugin makes (H2D/D2H inside the timed region; pinned buffers for
+the contract's number, pageable ones -- what Meschach VECs are -- next to it).
 
 Workloads (BASELINE.json configs):
   c2   nx=20 nu=10 K=10,000, one instance  (the configuration the metric is quoted on)
-  c3   4096 instances nx=12 nu=4 K=50, one CTA per instance
-  c5s  nx=40 nu=10 K=100,000 (single-GPU slice of the long-horizon config)
+       N > 1: weak scaling, ONE horizon of N*10,000 stages split into N ranges
+  c3   4096 instances nx=12 nu=4 K=50, one CTA per instance (N > 1: instances sharded)
+  c5   nx=40 nu=10 K=1,000,000 (BASELINE configs[4]) generated on the device;
+       N > 1: strong scaling, the horizon split into N contiguous stage ranges
+  c5s  nx=40 nu=10 K=100,000 host-generated slice of the same shape
+The default line (workload c2) carries the other configurations as sub-objects
+(`c5`, and at N = 1 `c3`) unless --no-extra is given.
+
+Multi-GPU: one process per GPU (torchrun); the horizon split lives in
+libhqpcuda.so (hqpcu_comm_init): NCCL all-gathers of the boundary elements /
+vectors are graph nodes between the kernels.  Every run ends with a refined
+solve whose KKT residual (max over ranks) is asserted before the line is printed.
 """
 from __future__ import annotations
 
@@ -31,19 +42,25 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "c2": dict(nx=20, nu=10, K=10000, batch=1,
+    "c2": dict(nx=20, nu=10, K=10000, batch=1, scaling="weak",
                name="synthetic LQ-DOCP nx=20 nu=10 K=10000 (BASELINE configs[1])"),
-    "c3": dict(nx=12, nu=4, K=50, batch=4096,
+    "c3": dict(nx=12, nu=4, K=50, batch=4096, scaling="weak",
                name="batched MPC QPs 4096 x (nx=12 nu=4 K=50) (BASELINE configs[2])"),
-    "c5s": dict(nx=40, nu=10, K=100000, batch=1,
+    "c5": dict(nx=40, nu=10, K=1000000, batch=1, scaling="strong", device_generated=True,
+               name="long-horizon LQ-DOCP nx=40 nu=10 K=1000000 (BASELINE configs[4]), "
+                    "horizon split over the GPUs"),
+    "c5s": dict(nx=40, nu=10, K=100000, batch=1, scaling="weak",
                 name="long-horizon LQ-DOCP nx=40 nu=10 K=100000 (slice of BASELINE configs[4])"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel
-# (seg_riccati_kernel) from the committed `ncu --set full` capture; null where no
-# capture exists.  Compare with K * algorithmic bytes per stage (C2: 160.4 MB).
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of seg_riccati_kernel
+# from the committed `ncu --set full` capture; null where no capture exists.
 NCU_TRAFFIC = {"c2": (124.024832e6 + 50.681344e6, "profiles/r01_ncu_full_k1k3_v7.md (K3 section)")}
 METRIC = "LQ-DOCP KKT factor+solve stages/s"
 UNIT = "stages/s"
+UNIT_OF_WORK = "1 factor + 2 step"
+# FP64 DMMA peak measured with scripts/mb/mb_dmma.cu on this pool's B200s
+# (profiles/r02_mb_dmma.md); MEASURED_PEAKS.json carries HBM and bf16 only
+FP64_TFLOPS = 37.2
 
 
 def algorithmic_bytes(nx, nu, mc):
@@ -66,6 +83,14 @@ def measured_peaks():
         with open(path) as f:
             return json.load(f).get("hbm_gbs", 6650.0), "measured"
     return 6650.0, "fallback"
+
+
+def config_of(wl, world):
+    """identical in both arms (the driver compares it)"""
+    K, batch = wl["K"], wl["batch"]
+    per_gpu = K * batch // world if wl["scaling"] == "strong" else K * batch
+    return {"workload": wl["name"], "unit_of_work": UNIT_OF_WORK, "stages_per_gpu": per_gpu,
+            "scaling": wl["scaling"]}
 
 
 class ClockSampler:
@@ -153,10 +178,52 @@ def time_reference(wl, steps, warmup, max_stages=None):
             if i >= warmup:
                 times.append(t)
     t_step = float(np.mean(times))
-    sample = (f"{Ks} of {K * batch} stages (one instance), {steps} x (1 factor + 2 step), "
+    sample = (f"{Ks} of {K * batch} stages (one instance), {steps} x ({UNIT_OF_WORK}), "
               f"single thread: the reference path is not thread-safe")
     return dict(value=Ks / t_step, unit=UNIT, cores=1, kind=kind, sample=sample,
                 ms_per_unit=1e3 * t_step, stages=Ks)
+
+
+def _c3_worker(args):
+    """one host process of the batched CPU baseline: its share of instances, one after the other"""
+    nx, nu, K, n_inst, seed = args
+    sys.path.insert(0, ROOT)
+    from hqp_b200.problem import synth_lqdocp, synth_rhs
+    from oracle import refharness
+    p = synth_lqdocp(nx, nu, K, seed=seed)
+    rhs = synth_rhs(p)
+    if refharness.available():
+        qp = refharness.RefQP(p)
+        M = refharness.RefMatrix("LQDOCP", qp)
+        M.time(*rhs, reps=1, nstep=2)
+        t0 = time.perf_counter()
+        for _ in range(n_inst):
+            M.time(*rhs, reps=1, nstep=2)
+        return time.perf_counter() - t0
+    from oracle.portoracle import PortOracle
+    o = PortOracle(p)
+    t0 = time.perf_counter()
+    for _ in range(n_inst):
+        o.factor(rhs[0], rhs[1])
+        o.step(*rhs[2:])
+        o.step(*rhs[2:])
+    return time.perf_counter() - t0
+
+
+def time_reference_batched(wl, per_proc=256):
+    """one worker process per host core, each looping over its share
+    of the independent instances with the single-threaded reference path."""
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        t0 = time.perf_counter()
+        pool.map(_c3_worker, [(wl["nx"], wl["nu"], wl["K"], per_proc, 100 + i) for i in range(cores)])
+        wall = time.perf_counter() - t0
+    # (wall includes process start and problem set-up: a lower bound on the baseline's speed)
+    return dict(value=cores * per_proc * wl["K"] / wall, unit=UNIT, cores=cores,
+                kind="reference", sample=f"{cores} processes x {per_proc} instances of "
+                f"{wl['batch']} (wall clock incl. process start-up)")
 
 
 def run_reference(args, wl):
@@ -164,13 +231,13 @@ def run_reference(args, wl):
     if rank != 0:
         return
     cap = 10000 if wl["batch"] == 1 else wl["K"]
-    cb = time_reference(wl, args.steps, min(args.warmup, 1), max_stages=cap)
+    cb = time_reference(wl, args.steps, args.warmup, max_stages=cap)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT,
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1),
-            "ms_per_step": cb["ms_per_unit"], "higher_is_better": True, "scaling": "weak",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": cb["ms_per_unit"], "higher_is_better": True, "scaling": wl["scaling"],
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": wl["name"], "unit_of_work": "1 factor + 2 step",
-                       "timed_stages": cb["stages"]},
+            "config": config_of(wl, max(args.gpus, 1)),
+            "details": {"timed_stages": cb["stages"]},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
@@ -179,33 +246,98 @@ def run_reference(args, wl):
 
 
 # ----------------------------------------------------------------------- ours --
-def run_ours(args, wl):
+class Structure:
+    """what IpCuda needs of a problem whose matrices are generated on the device"""
+
+    def __init__(self, nx, nu, K, fixed_x0, last):
+        from hqp_b200.problem import LQProblem, box_bounds_on_u
+        ptr, col, val, d = box_bounds_on_u(nx, nu, K)
+        self.prob = LQProblem(nx, nu, K, None, None, None, None, None, fixed_x0=fixed_x0,
+                              ineq_ptr=ptr, ineq_col=col, ineq_val=val, d=d)
+        self.last = last
+
+
+def device_generated_engine(wl, rank, world, local, nseg, group):
+    """C5: the rank's stage range of a K-stage horizon, matrices drawn on the device
+    (torch Philox, seeded per rank) chunk by chunk and handed to the library with
+    hqpcu_update_stages_dev -- no host copy, no second full device copy."""
+    import torch
+    from hqp_b200.dist import DistIpCuda, stage_ranges
+    nx, nu, K = wl["nx"], wl["nu"], wl["K"]
+    nm = nx + nu
+    k0, k1 = stage_ranges(K, world)[rank]
+    Kl = k1 - k0
+    st = Structure(nx, nu, Kl, fixed_x0=(rank == 0), last=(rank == world - 1))
+    t0 = time.perf_counter()
+    eng = DistIpCuda(st.prob, rank, world, device=local, nseg=nseg, group=group)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    f64 = dict(dtype=torch.float64, device=dev)
+    chunk = 50000
+    eye_m = torch.eye(nm, **f64)
+    eye_x = torch.eye(nx, **f64)
+    for c0 in range(0, Kl + 1, chunk):
+        nq = min(chunk, Kl + 1 - c0)
+        nf = min(chunk, Kl - c0) if c0 < Kl else 0
+        M = torch.rand(nq, nm, nm, generator=g, **f64) * 2 - 1
+        Q = torch.bmm(M.transpose(1, 2), M) / nm + 0.1 * eye_m      # SPD, full Hxu block
+        if c0 + nq == Kl + 1 and not st.last:
+            Q[-1].zero_()       # the trailing state block belongs to the next range
+        fx = fu = None
+        if nf:
+            fx = eye_x + 0.1 * (torch.rand(nf, nx, nx, generator=g, **f64) * 2 - 1) / nx ** 0.5
+            fu = torch.rand(nf, nx, nu, generator=g, **f64) * 2 - 1
+        torch.cuda.synchronize()
+        eng.update_stages_dev(c0, nq, Q.data_ptr(), nf, fx.data_ptr() if nf else 0,
+                              fu.data_ptr() if nf else 0)
+        torch.cuda.synchronize()
+        del M, Q, fx, fu
+    cv = torch.from_numpy(st.prob.ineq_val).to(dev)
+    eng.update_ineq_dev(cv.data_ptr())
+    torch.cuda.synchronize()
+    p = st.prob
+    dvec = [torch.rand(p.m, generator=g, **f64) + 0.5, torch.rand(p.m, generator=g, **f64) + 0.5,
+            torch.rand(p.N, generator=g, **f64) * 2 - 1, torch.rand(p.me, generator=g, **f64) * 2 - 1,
+            torch.rand(p.m, generator=g, **f64) * 2 - 1, torch.rand(p.m, generator=g, **f64) * 2 - 1]
+    if not st.last:
+        dvec[2][Kl * nm:].zero_()   # r1 of the trailing state block: owned by the next range
+    setup_ms = 1e3 * (time.perf_counter() - t0)
+    return eng, p, dvec, setup_ms
+
+
+def run_workload(args, key, steps, warmup, dist_group, extras=True):
+    """-> the JSON line (dict) on rank 0, None elsewhere"""
     import torch
     import torch.distributed as dist
+    from hqp_b200 import ipcuda as _ic
     from hqp_b200.ipcuda import IpCuda
     from hqp_b200.problem import synth_lqdocp, synth_rhs
 
+    wl = WORKLOADS[key]
     rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     nx, nu, K, batch = wl["nx"], wl["nu"], wl["K"], wl["batch"]
-
-    N1 = 0  # bytes bookkeeping below
-    update_sparse_ms = None
+    update_ms = update_sparse_ms = None
     sharded_instances = world > 1 and batch > 1
-    if world == 1 or sharded_instances:
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    if wl.get("device_generated"):
+        eng, lp, dvec, setup_ms = device_generated_engine(wl, rank, world, local, args.nseg,
+                                                          dist_group)
+        p = lp
+        Kg = K  # stages of the whole job
+        host = None
+        parallelism = (f"horizon split, {world} contiguous stage ranges of {K // world} stages; "
+                       "NCCL all-gathers inside the library's CUDA graphs (2 per factor, 2 per step)"
+                       if world > 1 else "single")
+    elif world == 1 or sharded_instances:
         # one horizon (or one batch of instances) on the GPU; with N > 1 GPUs a batch
         # workload shards its independent instances: `batch` per rank, no collective
         # in the KKT path (SURVEY 8e, C3)
         p = synth_lqdocp(nx, nu, K, seed=1234)
         z, w, r1, r2, r3, r4 = synth_rhs(p, seed=4321)
         eng = IpCuda(p, batch=batch, device=local, nseg=args.nseg)
-        stream = torch.cuda.current_stream()
-        eng.set_stream(stream.cuda_stream)
 
         def rep(a):
             return np.ascontiguousarray(np.tile(a, batch)) if batch > 1 else a
@@ -215,7 +347,6 @@ def run_ours(args, wl):
                        fx=np.broadcast_to(p.fx, (batch,) + p.fx.shape),
                        fu=np.broadcast_to(p.fu, (batch,) + p.fu.shape),
                        ineq_val=np.broadcast_to(p.ineq_val, (batch,) + p.ineq_val.shape))
-            update_ms = None
         else:
             t0 = time.perf_counter()
             eng.update()
@@ -231,67 +362,40 @@ def run_ours(args, wl):
             del dst, dst2
         host = [rep(a) for a in (z, w, r1, r2, r3, r4)]
         lp = p
+        Kg = K * batch * world
         parallelism = (f"{world} x {batch} independent instances, sharded over the ranks, no collective"
                        if sharded_instances else "single")
     else:
-        # horizon split: ONE horizon of world*K stages, contiguous
-        # stage ranges per rank, boundary elements exchanged with all-gathers
-        from hqp_b200.dist import CudaRangeEngine, RangeSolver, local_vectors, split_problem
+        # horizon split, weak: ONE horizon of world*K stages, contiguous
+        # stage ranges per rank, exchanges inside the library
+        from hqp_b200.dist import DistIpCuda, local_vectors, split_problem
         pg = synth_lqdocp(nx, nu, K * world, seed=1234)
         gvec = synth_rhs(pg, seed=4321)
         lp, rm = split_problem(pg, world)[rank]
         host = [np.ascontiguousarray(a) for a in local_vectors(pg, rm, *gvec)]
         del pg, gvec
-        stream = torch.cuda.current_stream()
         t0 = time.perf_counter()
-        reng = CudaRangeEngine(lp, rm, device=local, nseg=args.nseg)
+        eng = DistIpCuda(lp, rank, world, device=local, nseg=args.nseg, group=dist_group)
+        eng.update()
         update_ms = 1e3 * (time.perf_counter() - t0)
-        eng = reng.eng
-        solver = RangeSolver(reng, rank, world)
         p = lp
-        parallelism = f"horizon split, {world} contiguous stage ranges, 2 all-gathers per factor + 2 per step"
-    pinned = [torch.from_numpy(np.array(a)).pin_memory() for a in host]
-    dvec = [t.to(dev) for t in pinned]
+        Kg = K * world
+        parallelism = (f"horizon split, {world} contiguous stage ranges of {K} stages; NCCL "
+                       "all-gathers inside the library's CUDA graphs (2 per factor, 2 per step)")
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    if host is not None:
+        pinned = [torch.from_numpy(np.array(a)).pin_memory() for a in host]
+        dvec = [t.to(dev) for t in pinned]
     N, me, m = lp.N * batch, lp.me * batch, lp.m * batch
-    outs = [torch.empty(n, dtype=torch.float64, device=dev) for n in (N, me, max(m, 1), max(m, 1))]
-    hout = [torch.empty(n, dtype=torch.float64).pin_memory() for n in (N, me, max(m, 1), max(m, 1))]
+    outs = [torch.empty(n, **f64) for n in (N, me, max(m, 1), max(m, 1))]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
-
-    hp = [t.numpy() for t in pinned]
-    ho = [t.numpy() for t in hout]
-    from hqp_b200 import ipcuda as _ic
     L = _ic.lib()
 
-    if world == 1 or sharded_instances:
-        def unit_dev():
-            eng.factor_dev(dvec[0].data_ptr(), dvec[1].data_ptr())
-            for _ in range(2):
-                eng.step_dev(*[t.data_ptr() for t in dvec[2:]], *[t.data_ptr() for t in outs])
-
-        def unit_host():
-            _ic._check(L.hqpcu_factor(eng.h, _ic._hp(hp[0]), _ic._hp(hp[1])), "factor")
-            for _ in range(2):
-                _ic._check(L.hqpcu_step(eng.h, *[_ic._hp(a) for a in hp[2:]],
-                                        *[_ic._hp(a) for a in ho]), "step")
-    else:
-        def unit_dev():
-            solver.factor(dvec[0], dvec[1])
-            for _ in range(2):
-                solver.step(*dvec[2:])
-
-        def unit_host():
-            # host buffers in, host buffers out: pinned H2D of (z,w), then per step
-            # H2D of r1..r4 and D2H of dx..dw around the same range calls
-            dvec[0].copy_(pinned[0], non_blocking=True)
-            dvec[1].copy_(pinned[1], non_blocking=True)
-            solver.factor(dvec[0], dvec[1])
-            for _ in range(2):
-                for dt, ht in zip(dvec[2:], pinned[2:]):
-                    dt.copy_(ht, non_blocking=True)
-                res = solver.step(*dvec[2:])
-                for ht, dt in zip(hout, res):
-                    ht[:dt.numel()].copy_(dt, non_blocking=True)
-            torch.cuda.synchronize()
+    def unit_dev():
+        eng.factor_dev(dvec[0].data_ptr(), dvec[1].data_ptr())
+        for _ in range(2):
+            eng.step_dev(*[t.data_ptr() for t in dvec[2:]], *[t.data_ptr() for t in outs])
 
     def barrier():
         if world > 1:
@@ -299,7 +403,7 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     # ---- warm-up ---------------------------------------------------------
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         flush.zero_()
         unit_dev()
     st = eng.sync_status()
@@ -312,7 +416,7 @@ def run_ours(args, wl):
     barrier()
     launches0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+          for _ in range(steps)]
     for e0, e1 in ev:
         flush.zero_()            # L2 flush between timed iterations (not timed)
         e0.record(stream)
@@ -322,21 +426,65 @@ def run_ours(args, wl):
     gpu_launches = eng.launches - launches0
     ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     ms_step = float(np.mean(ms))
+    clocks = sampler.stop()
+
+    # ---- correctness of what was timed: refined solve, KKT residual (max over the
+    # ranks, all-reduced inside the library) -- asserted before anything is printed
+    res, nsolve = eng.solve_dev(*[t.data_ptr() for t in dvec[2:]], *[t.data_ptr() for t in outs])
+    torch.cuda.synchronize()
+    if not (res <= 1e-9):
+        raise RuntimeError(f"KKT residual {res} after the refined solve (rank {rank})")
 
     # ---- e2e: host buffers through the plugin-facing C ABI ----------------------
-    unit_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
+    e2e = {}
+    if host is not None:
+        hout = [torch.empty(n, dtype=torch.float64).pin_memory() for n in (N, me, max(m, 1), max(m, 1))]
+        for kind in ("pinned", "pageable"):
+            if kind == "pinned":
+                hp, ho = [t.numpy() for t in pinned], [t.numpy() for t in hout]
+            else:   # plain malloc'ed memory: what the plugin passes (VEC::ve)
+                hp = [np.array(t.numpy(), copy=True) for t in pinned]
+                ho = [np.empty(n) for n in (N, me, max(m, 1), max(m, 1))]
+
+            def unit_host():
+                _ic._check(L.hqpcu_factor(eng.h, _ic._hp(hp[0]), _ic._hp(hp[1])), "factor")
+                for _ in range(2):
+                    _ic._check(L.hqpcu_step(eng.h, *[_ic._hp(a) for a in hp[2:]],
+                                            *[_ic._hp(a) for a in ho]), "step")
+            unit_host()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                unit_host()
+            torch.cuda.synchronize()
+            e2e[kind] = (time.perf_counter() - t0) / steps
+            barrier()
+    else:
+        # device-generated workload: the host side of the same calls is the QP's own
+        # vectors; time the C-ABI host entry points on pinned copies of the inputs
+        hp = [t.cpu().pin_memory().numpy() for t in dvec]
+        ho = [torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+              for n in (N, me, max(m, 1), max(m, 1))]
+
+        def unit_host():
+            _ic._check(L.hqpcu_factor(eng.h, _ic._hp(hp[0]), _ic._hp(hp[1])), "factor")
+            for _ in range(2):
+                _ic._check(L.hqpcu_step(eng.h, *[_ic._hp(a) for a in hp[2:]],
+                                        *[_ic._hp(a) for a in ho]), "step")
         unit_host()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / args.steps
-    clocks = sampler.stop()
-    barrier()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(max(2, steps // 2)):
+            unit_host()
+        torch.cuda.synchronize()
+        e2e["pinned"] = (time.perf_counter() - t0) / max(2, steps // 2)
+        barrier()
+        del hp, ho
 
     # ---- per-kernel CUDA-event times of the same unit (roofline section) ------
     eng.profile(True)
-    for _ in range(args.steps):
+    nprof = min(steps, 5)
+    for _ in range(nprof):
         flush.zero_()
         unit_dev()
     prof = eng.profile_read()
@@ -345,23 +493,37 @@ def run_ours(args, wl):
     # ---- whole QP solve on the device (Hqp_IpsMehrotra restated, SURVEY 8d:
     # "full-IP-iteration time including vector kernels") -- reported, not the metric
     ip_solve = None
-    if world == 1 and batch == 1:
+    if batch == 1 and extras:
         try:
-            eng.mehrotra_solve()                      # warm (graphs captured)
+            if wl.get("device_generated"):
+                rng = np.random.default_rng(100 + rank)
+                cc = rng.uniform(-1, 1, lp.N)
+                if rank < world - 1:
+                    cc[(lp.K) * (nx + nu):] = 0.0
+                bb = 0.01 * rng.uniform(-1, 1, lp.me)
+                kw = dict(c=cc, b=bb, d=np.ones(lp.m))
+            elif world > 1:
+                kw = dict(c=lp.c, b=lp.b, d=lp.d)
+            else:
+                kw = {}
+            if not wl.get("device_generated"):
+                eng.mehrotra_solve(**kw)                      # warm (graphs captured)
             s0 = eng.solve_stats()
+            barrier()
             t0 = time.perf_counter()
-            r = eng.mehrotra_solve()
+            r = eng.mehrotra_solve(**kw)
             dt = time.perf_counter() - t0
             s1 = eng.solve_stats()
             ip_solve = {"result": r["result"], "iterations": r["iters"], "ms_total": 1e3 * dt,
                         "ms_per_iteration": 1e3 * dt / max(r["iters"], 1),
-                        "stages_per_s": K * r["iters"] / dt, "gap": r["gap"],
+                        "stages_per_s": Kg * r["iters"] / dt, "gap": r["gap"],
                         "mean_kkt_steps_per_refined_solve": (s1[1] - s0[1]) / max(s1[0] - s0[0], 1),
                         "note": "hqpcu_mehrotra_solve: cold start + IP iterations, host c/b/d in, "
-                                "x/y/z/w out; each iteration = 1 factor + 2 refined solves + vector kernels"}
+                                "x/y/z/w out; each iteration = 1 factor + 2 refined solves + vector "
+                                "kernels" + ("; IP scalars all-reduced over the ranks" if world > 1 else "")}
             # the same QP through the unmodified reference on the host
             # (Hqp_IpsMehrotra + Hqp_IpLQDOCP, oracle/_ref), bounded to <= 10^4 stages
-            if rank == 0 and K <= 10000:
+            if rank == 0 and world == 1 and K <= 10000 and not wl.get("device_generated"):
                 from oracle import refharness
                 if refharness.available():
                     rr = refharness.ips_solve(refharness.RefQP(p), "Mehrotra", "LQDOCP", 1e-9)
@@ -372,77 +534,158 @@ def run_ours(args, wl):
                                                        max(1e-300, np.max(np.abs(rr["x"]))))}
         except Exception as ex:  # reported, never fatal for the metric
             ip_solve = {"error": str(ex)}
+            if world > 1:
+                raise
 
-    tmax = torch.tensor([ms_step, e2e_s], dtype=torch.float64, device=dev)
+    tl = [ms_step] + [e2e.get(k, 0.0) for k in ("pinned", "pageable")]
+    tmax = torch.tensor(tl, dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_step, e2e_s = float(tmax[0]), float(tmax[1])
-    stages = K * batch * world
-    value = stages / (ms_step * 1e-3)
-    bytes_in = 8 * sum(int(np.prod(a.shape)) for a in host[:2]) + \
-        2 * 8 * sum(int(np.prod(a.shape)) for a in host[2:])
+    ms_step = float(tmax[0])
+    e2e_max = {"pinned": float(tmax[1]), "pageable": float(tmax[2])}
+    value = Kg / (ms_step * 1e-3)
+    n_in = [lp.m * batch, lp.m * batch, N, me, m, m]
+    bytes_in = 8 * (n_in[0] + n_in[1]) + 2 * 8 * sum(n_in[2:])
     bytes_out = 2 * 8 * (N + me + 2 * m)
-
-    if rank == 0:
-        mc = p.m / K
-        bf, bs = algorithmic_bytes(nx, nu, mc)
-        ff, fs = algorithmic_flops(nx, nu)
-        peak, how = measured_peaks()
-        per = {k.strip("()"): v["ms"] / args.steps for k, v in prof.items()}
-        t_factor = sum(v for k, v in per.items() if not k.startswith("solve_"))
-        t_solve = sum(v for k, v in per.items() if k.startswith("solve_")) / 2.0
-        dom = max(per, key=per.get)
-        # the kernel that performs the algorithmic factor work of every stage
-        kname = [k for k in per if k.startswith("seg_riccati_kernel")][0]
-        kms = per[kname]
-        k1n = [k for k in per if k.strip("()").startswith("seg_element_kernel")]
-        bf_read = 8 * ((nx + nu) * (nx + nu + 1) // 2 + nx * (nx + nu) + 2 * mc)
-        ach = K * batch * bf / (kms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak,
-                    "unit": "GB/s", "frac": ach / peak,
-                    "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
-                    "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
-                    "algorithmic_bytes_per_launch": K * batch * bf, "peak_source": how,
-                    "algorithmic_bytes_per_stage": {"factor": bf, "step": bs},
-                    "algorithmic_flops_per_stage": {"factor": ff, "step": fs},
-                    "kernel_ms_per_unit": per, "dominant_kernel": dom,
-                    # K1 (seg_element) is the parallel-in-time condensation: it reads the
-                    # same Q, fx, fu, z/w bytes as K3 and writes only P boundary elements;
-                    # its time is overhead of the algorithm, reported next to K3
-                    "k1_condensation": ({"kernel": k1n[0], "ms": per[k1n[0]],
-                                         "read_bytes_per_launch": K * batch * bf_read,
-                                         "frac_of_hbm": K * batch * bf_read / (per[k1n[0]] * 1e-3) / 1e9 / peak}
-                                        if k1n else None),
-                    "factor_ms": t_factor, "step_ms": t_solve,
-                    "factor_frac_of_hbm": K * batch * bf / (t_factor * 1e-3) / 1e9 / peak,
-                    "step_frac_of_hbm": K * batch * bs / (t_solve * 1e-3) / 1e9 / peak}
-        cap = 10000 if batch == 1 else K
-        # reference CPU path on the host cores: rank 0, N = 1 only
-        cb = time_reference(wl, 3, 1, max_stages=cap) if world == 1 else None
-        h2d, d2h = bytes_in * world, bytes_out * world  # whole job
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic",
-                "config": {"workload": wl["name"], "unit_of_work": "1 factor + 2 step",
-                           "stages_per_gpu": K * batch, "segments_per_instance": eng.nseg,
-                           "parallelism": parallelism,
-                           "l2": "flushed (256 MiB write) between timed iterations"},
-                "roofline": roofline,
-                "cpu_baseline": ({k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-                                 if cb else None),
-                "e2e": {"value": stages / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s},
-                "gpu_launches": int(gpu_launches), "clocks": clocks}
-        if update_ms is not None:
-            line["config"]["update_ms_once_per_sqp_iteration"] = update_ms
-            if update_sparse_ms is not None:
-                line["config"]["update_ms_from_sparse_values"] = update_sparse_ms
-        if ip_solve is not None:
-            line["ip_solve"] = ip_solve
-        print(json.dumps(line), flush=True)
+    nseg = eng.nseg
     eng.close()
+    if rank != 0:
+        return None
+
+    mc = lp.m / max(lp.K, 1)
+    bf, bs = algorithmic_bytes(nx, nu, mc)
+    ff, fs = algorithmic_flops(nx, nu)
+    peak, how = measured_peaks()
+    Kloc = lp.K * batch          # stages this rank's kernels process per launch
+    per = {k.strip("()"): v["ms"] / nprof for k, v in prof.items()}
+    solve_names = ("solve_", "range_scan_vec", "range_export_vec")
+    t_factor = sum(v for k, v in per.items() if not k.startswith(solve_names))
+    t_solve = sum(v for k, v in per.items() if k.startswith(solve_names)) / 2.0
+    dom = max(per, key=per.get)
+    kname = [k for k in per if k.startswith("seg_riccati_kernel")][0]
+    kms = per[kname]
+    k1n = [k for k in per if k.startswith("seg_element_kernel")]
+    bf_read = 8 * ((nx + nu) * (nx + nu + 1) // 2 + nx * (nx + nu) + 2 * mc)
+    # headline fraction: the algorithmic bytes of the WHOLE unit over the unit's time
+    unit_bytes = Kg * (bf + 2 * bs)
+    ach_unit = unit_bytes / (ms_step * 1e-3) / 1e9 / world      # per GPU
+    k3_ach = Kloc * bf / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "whole unit (1 factor + 2 step), per GPU",
+                "achieved": ach_unit, "peak": peak, "unit": "GB/s", "frac": ach_unit / peak,
+                "traffic": NCU_TRAFFIC.get(key, (None, None))[0],
+                "traffic_source": NCU_TRAFFIC.get(key, (None, None))[1],
+                "traffic_kernel": "seg_riccati_kernel (K3), one launch",
+                "algorithmic_bytes_per_unit": unit_bytes, "peak_source": how,
+                "algorithmic_bytes_per_stage": {"factor": bf, "step": bs},
+                "algorithmic_flops_per_stage": {"factor": ff, "step": fs},
+                "fp64": {"factor_tflops": Kloc * ff / (t_factor * 1e-3) / 1e12 if t_factor else None,
+                         "peak_tflops": FP64_TFLOPS, "peak_source": "scripts/mb/mb_dmma.cu (measured)",
+                         "arithmetic_intensity_factor": ff / bf},
+                # K3 = the kernel that does the algorithmic factor work of every stage
+                "k3": {"kernel": kname, "ms": kms, "achieved": k3_ach, "frac": k3_ach / peak,
+                       "algorithmic_bytes_per_launch": Kloc * bf},
+                # K1 (seg_element) is the parallel-in-time condensation: it reads the same
+                # Q, fx, fu, z/w bytes as K3 and writes only P boundary elements; overhead
+                # of the algorithm, reported next to K3
+                "k1_condensation": ({"kernel": k1n[0], "ms": per[k1n[0]],
+                                     "read_bytes_per_launch": Kloc * bf_read,
+                                     "frac_of_hbm": Kloc * bf_read / (per[k1n[0]] * 1e-3) / 1e9 / peak}
+                                    if k1n else None),
+                "kernel_ms_per_unit": per, "dominant_kernel": dom,
+                "kernel_ms_note": "plain launches bracketed by CUDA events (graphs off): shares, "
+                                  "not absolutes; their sum exceeds ms_per_step",
+                "factor_ms": t_factor, "step_ms": t_solve,
+                "factor_frac_of_hbm": Kloc * bf / (t_factor * 1e-3) / 1e9 / peak if t_factor else None,
+                "step_frac_of_hbm": Kloc * bs / (t_solve * 1e-3) / 1e9 / peak if t_solve else None}
+    cfg = config_of(wl, world)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": steps, "warmup": warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None,
+            "dtype": "f64", "data": ("synthetic (drawn on the device, torch Philox, seed 1234 + rank)"
+                                     if wl.get("device_generated") else "synthetic"),
+            "config": cfg,
+            "details": {"segments_per_instance": nseg, "parallelism": parallelism,
+                        "l2": "flushed (256 MiB write) between timed iterations",
+                        "kkt_residual_after_refined_solve": res, "kkt_steps_in_that_solve": nsolve},
+            "roofline": roofline,
+            "e2e": {"value": Kg / e2e_max["pinned"], "unit": UNIT,
+                    "h2d_bytes_per_step": bytes_in * world, "d2h_bytes_per_step": bytes_out * world,
+                    "ms_per_step": 1e3 * e2e_max["pinned"],
+                    "pinned": Kg / e2e_max["pinned"],
+                    "pageable": (Kg / e2e_max["pageable"]) if e2e_max["pageable"] else None,
+                    "note": "hqpcu_factor + 2 x hqpcu_step with host buffers; `value` = pinned (the "
+                            "contract), `pageable` = malloc'ed buffers as Hqp_IpCuda::step passes them"},
+            "gpu_launches": int(gpu_launches), "clocks": clocks}
+    if update_ms is not None:
+        line["details"]["update_ms_once_per_sqp_iteration"] = update_ms
+        if update_sparse_ms is not None:
+            line["details"]["update_ms_from_sparse_values"] = update_sparse_ms
+    if wl.get("device_generated"):
+        line["details"]["setup_ms_generate_and_upload"] = setup_ms
+    if ip_solve is not None:
+        line["ip_solve"] = ip_solve
+    return line
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
     if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    key = args.workload
+    line = run_workload(args, key, args.steps, args.warmup, group)
+    wl = WORKLOADS[key]
+    if rank == 0:
+        # reference CPU path on the host cores: rank 0, N = 1 only
+        if world == 1:
+            cap = 10000 if wl["batch"] == 1 else wl["K"]
+            cb = time_reference(wl, 3, 1, max_stages=cap)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            if wl["batch"] > 1:
+                try:
+                    line["cpu_baseline_all_cores"] = time_reference_batched(wl)
+                except Exception as ex:
+                    line["cpu_baseline_all_cores"] = {"error": str(ex)}
+        else:
+            line["cpu_baseline"] = None
+    # the other BASELINE configurations ride along as sub-objects of the default line
+    if key == "c2" and not args.no_extra:
+        extra = {}
+        try:
+            sub = run_workload(args, "c5", max(3, min(args.steps, 5)), 3, group)
+            if rank == 0:
+                if world == 1:
+                    cb = time_reference(WORKLOADS["c5"], 2, 1, max_stages=5000)
+                    sub["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                extra["c5"] = sub
+        except Exception as ex:
+            if world > 1:
+                raise
+            extra["c5"] = {"error": str(ex)}
+        if world == 1:
+            try:
+                sub = run_workload(args, "c3", max(3, min(args.steps, 10)), 3, group, extras=False)
+                cb = time_reference(WORKLOADS["c3"], 3, 1, max_stages=WORKLOADS["c3"]["K"])
+                sub["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                try:
+                    sub["cpu_baseline_all_cores"] = time_reference_batched(WORKLOADS["c3"])
+                except Exception as ex:
+                    sub["cpu_baseline_all_cores"] = {"error": str(ex)}
+                extra["c3"] = sub
+            except Exception as ex:
+                extra["c3"] = {"error": str(ex)}
+        if rank == 0:
+            line.update(extra)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -454,13 +697,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--nseg", type=int, default=0)
+    ap.add_argument("--no-extra", action="store_true",
+                    help="default workload only: skip the c5 / c3 sub-objects")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    wl = WORKLOADS[args.workload]
+    args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
-        run_reference(args, wl)
+        run_reference(args, WORKLOADS[args.workload])
     else:
-        run_ours(args, wl)
+        run_ours(args)
 
 
 if __name__ == "__main__":

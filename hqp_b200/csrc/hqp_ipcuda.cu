@@ -11,6 +11,8 @@
 #include "../../include/hqp_ipcuda.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound with dlopen (hqp_dist_host.inc)
 
 #include <algorithm>
 #include <cmath>
@@ -78,10 +80,12 @@ static thread_local std::string g_err;
   } while (0)
 
 struct IpsState;
+struct DistState;
 
 struct hqpcu_handle {
   LqDev d;
   IpsState *ips = nullptr;           // device-resident IP solver state (lazy)
+  DistState *dist = nullptr;         // horizon split over NCCL (hqp_dist_host.inc)
   std::vector<double> eq_rowsum;     // row sums |E| of the general equality rows
   std::vector<int> dims_eq_ptr;      // host copy of the equality CSR pointers
   hqpcu_dims dims;
@@ -379,6 +383,15 @@ static int set_smem(const void *fn, size_t bytes) {
 }
 
 static void ips_free(hqpcu_handle *h);
+// horizon split over NCCL (hqp_dist_host.inc): after hqpcu_comm_init the handle is
+// one rank's stage range and every entry point works on that range's slices
+extern "C" {  // (defined inside this file's extern "C" block)
+static void dist_free(hqpcu_handle *h);
+static bool dist_on(const hqpcu_handle *h);
+static int dist_launch_factor(hqpcu_handle *h);
+static int dist_launch_step(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                            const double *r4, double *dx, double *dy, double *dz, double *dw);
+}
 
 extern "C" {
 
@@ -704,6 +717,7 @@ int hqpcu_destroy(hqpcu_handle *h) {
   if (h->vm_dst) { cudaFree(h->vm_dst); cudaFree(h->vm_dst2); cudaFree(h->vm_vals); }
   for (void *p : h->allocs) cudaFree(p);
   ips_free(h);
+  dist_free(h);
   if (h->res_host) cudaFreeHost(h->res_host);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
@@ -850,6 +864,43 @@ int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx, const d
   return update_impl(h, Q, fx, fu, ineq_val, eq_val, cudaMemcpyDeviceToDevice);
 }
 
+// Update of a stage window from device memory: a host that produces its matrices
+// on the device (or a long horizon generated chunk by chunk) never holds a second
+// full copy.  nq blocks of Q for stages k0.., nf blocks of fx / fu for stages k0..
+int hqpcu_update_stages_dev(hqpcu_handle *h, int k0, int nq, const double *Q, int nf,
+                            const double *fx, const double *fu) {
+  if (!h || (nq && !Q) || (nf && (!fx || !fu))) return HQPCU_E_NULL;
+  const LqDev &d = h->d;
+  if (d.batch != 1 || k0 < 0 || nq < 0 || nf < 0 || k0 + nq > d.K + 1 || k0 + nf > d.K) {
+    g_err = "hqpcu_update_stages_dev: stage window outside the horizon (batch == 1)";
+    return HQPCU_E_SIZES;
+  }
+  undo_demotion(h);
+  CU(cudaSetDevice(h->device));
+  const size_t qq = (size_t)d.nm * d.nm, xx = (size_t)d.nx * d.nx, xu = (size_t)d.nx * d.nu;
+  if (nq)
+    CU(cudaMemcpyAsync(h->Q + (size_t)k0 * qq, Q, (size_t)nq * qq * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->stream));
+  if (nf) {
+    CU(cudaMemcpyAsync(h->fx + (size_t)k0 * xx, fx, (size_t)nf * xx * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->fu + (size_t)k0 * xu, fu, (size_t)nf * xu * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->stream));
+  }
+  h->factored = false;
+  return HQPCU_OK;
+}
+
+int hqpcu_update_ineq_dev(hqpcu_handle *h, const double *ineq_val) {
+  if (!h || (h->d.nnz && !ineq_val)) return HQPCU_E_NULL;
+  CU(cudaSetDevice(h->device));
+  if (h->d.nnz)
+    CU(cudaMemcpyAsync(h->cval, ineq_val, (size_t)h->d.batch * h->d.nnz * sizeof(double),
+                       cudaMemcpyDeviceToDevice, h->stream));
+  h->factored = false;
+  return HQPCU_OK;
+}
+
 // ------------------------------------------------------------------ factor --
 static int launch_step_base(hqpcu_handle *h, const double *r1, const double *r2,
                             const double *r3, const double *r4, double *dx, double *dy,
@@ -955,6 +1006,7 @@ static int launch_factor_down(hqpcu_handle *h) {
 #undef L_PSI
 
 static int launch_factor(hqpcu_handle *h) {
+  if (dist_on(h)) return dist_launch_factor(h);
   if (h->ranged()) {
     g_err = "this handle is a stage range of a split horizon: use hqpcu_range_*";
     return HQPCU_E_UNSUPPORTED;
@@ -962,7 +1014,10 @@ static int launch_factor(hqpcu_handle *h) {
   int rc = run_graphed(h, {(const void *)(uintptr_t)1}, [&]() {
     int r = launch_factor_up(h);
     if (!r) r = launch_factor_down(h);
-    if (!r && h->q.n_eq) r = launch_eq_factor(h);
+    if (!r && h->q.n_eq) {
+      h->factored = true;  // the extra solves below go through the step launchers
+      r = launch_eq_factor(h);
+    }
     return r;
   });
   if (!rc) h->factored = true;
@@ -1010,7 +1065,9 @@ static int finish_factor(hqpcu_handle *h) {
     if (rc) return rc;
     rc = read_status(h);
   }
-  if (rc == HQPCU_E_NOTPD) rc = HQPCU_OK;  // indefinite but non-singular: accepted
+  // indefinite but non-singular: accepted by the sequential sweep like the
+  // reference's BKP; a stage range of a split horizon has no sequential fallback
+  if (rc == HQPCU_E_NOTPD && !h->ranged()) rc = HQPCU_OK;
   return rc;
 }
 
@@ -1184,6 +1241,7 @@ static int launch_step(hqpcu_handle *h, const double *r1, const double *r2, cons
     g_err = "step before factor";
     return HQPCU_E_NULL;
   }
+  if (dist_on(h)) return dist_launch_step(h, r1, r2, r3, r4, dx, dy, dz, dw);
   return run_graphed(h, {(const void *)(uintptr_t)2, r1, r2, r3, r4, dx, dy, dz, dw}, [&]() {
     return launch_step_plain(h, r1, r2, r3, r4, dx, dy, dz, dw);
   });
@@ -1235,11 +1293,17 @@ int hqpcu_step(hqpcu_handle *h, const double *r1, const double *r2, const double
   return d2h_sol(h, dx, dy, dz, dw);
 }
 
+#include "hqp_dist_host.inc"
+
 // ---------------------------------------------------------------- residuum --
 static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
                            const double *r4, const double *dx, const double *dy,
                            const double *dz, const double *dw, bool keep, double *res) {
   const LqDev &d = h->d;
+  if (dist_on(h)) {  // boundary blocks of the neighbouring ranges
+    const int rc = dist_halo(h, dx, dy);
+    if (rc) return rc;
+  }
   CU(cudaMemsetAsync(h->res_dev, 0, sizeof(double), h->stream));
   const dim3 gall(d.K + 1, d.batch);
   const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
@@ -1251,6 +1315,10 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
       keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev,
       h->q.n_eq ? h->q.ety : nullptr));
   CUL(h);
+  if (dist_on(h)) {  // max over the ranges (on the bit pattern: a NaN stays on top)
+    const int rc = dist_allreduce_bits_max(h, h->res_dev, 1);
+    if (rc) return rc;
+  }
   CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *res = *h->res_host;
@@ -1284,6 +1352,13 @@ int hqpcu_residuum(hqpcu_handle *h, const double *r1, const double *r2, const do
                          h->u_dw, false, res);
 }
 
+// one KKT solve with the current factor: the single-GPU launch sequence or, for a
+// stage range of a split horizon, the one with the NCCL exchanges in it
+static int step_any(hqpcu_handle *h, const double *r1, const double *r2, const double *r3,
+                    const double *r4, double *dx, double *dy, double *dz, double *dw) {
+  return launch_step(h, r1, r2, r3, r4, dx, dy, dz, dw);
+}
+
 // ------------------------------------------------------------------- solve --
 // Hqp_IpMatrix::solve (hqp/Hqp_IpMatrix.C:65-128) on device-resident vectors.
 static int solve_core(hqpcu_handle *h, double eps, const double *r1, const double *r2,
@@ -1293,7 +1368,7 @@ static int solve_core(hqpcu_handle *h, double eps, const double *r1, const doubl
   const size_t B = d.batch;
   const size_t n1 = B * d.N, n2 = B * d.me, n3 = B * d.m;
   int steps = 1;
-  int rc = launch_step(h, r1, r2, r3, r4, dx, dy, dz, dw);
+  int rc = step_any(h, r1, r2, r3, r4, dx, dy, dz, dw);
   if (rc) return rc;
   double res = 0.0;
   rc = launch_residuum(h, r1, r2, r3, r4, dx, dy, dz, dw, true, &res);
@@ -1301,7 +1376,7 @@ static int solve_core(hqpcu_handle *h, double eps, const double *r1, const doubl
   const int ablocks = (int)std::min<size_t>((std::max(n1, n2) + 255) / 256, 148 * 8);
   for (int it = 0; it < 5 && res > eps; it++) {
     const double res_last = res;
-    rc = launch_step(h, h->t1, h->t2, h->t3, h->t4, h->e1, h->e2, h->e3, h->e4);
+    rc = step_any(h, h->t1, h->t2, h->t3, h->t4, h->e1, h->e2, h->e3, h->e4);
     if (rc) return rc;
     steps++;
     double alpha = 1.0;
@@ -1440,7 +1515,7 @@ int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, 
       h, {(const void *)(uintptr_t)13, gv, gpsi, xx, h->rg_r2, (const void *)(uintptr_t)rank,
           (const void *)(uintptr_t)world},
       [&]() {
-        LAUNCH(h, range_scan_vec_kernel<true>, <<<1, thr, sm, h->stream>>>(h->d, gv, gpsi, rank, world));
+        LAUNCH(h, range_scan_vec_kernel<true>, <<<1, thr, sm, h->stream>>>(h->d, gv, gpsi, rank, world, h->d.nx * h->d.nx));
         int rc = launch_step_b(h, h->rg_r2);
         if (rc) return rc;
         LAUNCH(h, range_export_vec_kernel<false>,
@@ -1464,7 +1539,7 @@ int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gps
       h, {(const void *)(uintptr_t)14, gx, gpsi, dx, dy, dz, dw, h->rg_r2, h->rg_r3, h->rg_r4,
           (const void *)(uintptr_t)rank, (const void *)(uintptr_t)world},
       [&]() {
-        LAUNCH(h, range_scan_vec_kernel<false>, <<<1, thr, sm, h->stream>>>(h->d, gx, gpsi, rank, world));
+        LAUNCH(h, range_scan_vec_kernel<false>, <<<1, thr, sm, h->stream>>>(h->d, gx, gpsi, rank, world, h->d.nx * h->d.nx));
         return launch_step_c(h, h->rg_r2, h->rg_r3, h->rg_r4, dx, dy, dz, dw);
       });
 }

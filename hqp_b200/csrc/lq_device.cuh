@@ -41,6 +41,10 @@ struct LqDev {
   int has_next;       // a rank behind this one supplies the terminal value
   double *Vext;       // [nx*nx] value Hessian handed over from the ranks behind
   double *xstart;     // [nx]    state at stage 0 handed over from the ranks before
+  // halo of the residual passes: [world][2 nx] = (first state, last dynamics
+  // multiplier) of every range, all-gathered before the pass (NULL: no split)
+  const double *halo;
+  int rank, world;
   // inequality structure (shared by all instances)
   const int *ineq_stage, *ineq_ptr, *ineq_lcol;
   const int *srow_ptr;  // [K+2] rows sorted by stage
@@ -669,6 +673,9 @@ __device__ __forceinline__ void ldlt_solve_any(const double *LD, int lda, int m,
 #ifdef LQ_GJ_STAMPS
 __device__ long long g_gj_stamps[80];
 #endif
+#ifndef LQ_GJ_MODE
+#define LQ_GJ_MODE 0  // warp inverse of the tree combines: 0 plain, 1 look-ahead, 2 look-ahead + shuffles
+#endif
 template <int N>
 __device__ __forceinline__ int warp_gj_inverse(const double *M, int ldm, double *Minv, int ldi,
                                                double *rowbuf, int *rowsel) {
@@ -762,6 +769,89 @@ __device__ __forceinline__ int warp_gj_inverse(const double *M, int ldm, double 
 #pragma unroll
       for (int q = 0; q < N; q++) Minv[mystep[rr] * ldi + rowsel[q]] = a[rr][q] * dinv[rr];
     }
+  }
+  return flag;
+}
+
+// Same inverse for N <= 32 with the pivot search taken off the dependent path
+// ("look-ahead"): within step p the column p+1 is updated first, its magnitude
+// keys go into the redux / ballot that pick pivot p+1 and every candidate lane
+// starts the reciprocal of its own entry -- all of which then overlaps the N-2
+// remaining column updates of step p instead of following them.  The dependent
+// chain of a step shrinks to: publish the pivot row, read 1/pivot, one multiply,
+// one multiply-add.  BCAST_SHFL: the pivot row travels by shuffles from the
+// (runtime) pivot lane instead of through the shared row.
+template <int N, bool BCAST_SHFL = false>
+__device__ __forceinline__ int warp_gj_inverse_la(const double *M, int ldm, double *Minv,
+                                                  int ldi, double *rowbuf, int *rowsel) {
+  static_assert(N <= 32 && N % 2 == 0, "warp_gj_inverse_la: even N <= 32");
+  const int lane = threadIdx.x & 31;
+  double a[N];
+  bool used = lane >= N;  // rows past the matrix never become pivots
+  int mystep = 0;
+  double dinv = 1.0;
+#pragma unroll
+  for (int j = 0; j < N; j++) a[j] = lane < N ? M[lane * ldm + j] : 0.0;
+  int flag = 0;
+  unsigned key = used ? 0u : (unsigned)__double2hiint(fabs(a[0]));
+  double myinv = fast_rcp(a[0]);
+  unsigned best = __reduce_max_sync(0xffffffffu, key);
+  unsigned ball = __ballot_sync(0xffffffffu, !used && key == best);
+#pragma unroll
+  for (int p = 0; p < N; p++) {
+    if (best == 0u) flag |= LQ_FLAG_SING;
+    const int rl = __ffs(ball) - 1;
+    const bool me = lane == rl;
+    double *rb = rowbuf + (p & 1) * (N + 2);
+    double inv;
+    if constexpr (BCAST_SHFL) {
+      inv = __shfl_sync(0xffffffffu, myinv, rl);
+      if (me) rowsel[p] = lane;
+    } else {
+      if (me) {
+#pragma unroll
+        for (int j = 0; j < N; j += 2)
+          *reinterpret_cast<double2 *>(rb + j) = make_double2(a[j], a[j + 1]);
+        rb[N] = myinv;
+        rowsel[p] = lane;
+      }
+      __syncwarp();
+      inv = rb[N];
+    }
+    const double m = me ? 0.0 : a[p] * inv;
+    if (me) { used = true; mystep = p; dinv = inv; }
+    // column p+1 first, then the selection of pivot p+1
+    if (p + 1 < N) {
+      const double prn = BCAST_SHFL ? __shfl_sync(0xffffffffu, a[p + 1], rl) : rb[p + 1];
+      a[p + 1] = fma(-m, prn, a[p + 1]);
+      key = used ? 0u : (unsigned)__double2hiint(fabs(a[p + 1]));
+      myinv = fast_rcp(a[p + 1]);
+      best = __reduce_max_sync(0xffffffffu, key);
+      ball = __ballot_sync(0xffffffffu, !used && key == best);
+    }
+    // the unit column of the right-hand identity takes the place of column p
+    if constexpr (BCAST_SHFL) {
+#pragma unroll
+      for (int j = 0; j < N; j++) {
+        if (j == p || j == p + 1) continue;
+        const double prj = __shfl_sync(0xffffffffu, a[j], rl);
+        a[j] = fma(-m, prj, a[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        const double2 prj = *reinterpret_cast<const double2 *>(rb + j);
+        if (j != p && j != p + 1) a[j] = fma(-m, prj.x, a[j]);
+        if (j + 1 != p && j + 1 != p + 1) a[j + 1] = fma(-m, prj.y, a[j + 1]);
+      }
+    }
+    a[p] = me ? 1.0 : -m;
+  }
+  __syncwarp();
+  // register a[q] / piv of the row chosen at step p is Minv[p][rowsel[q]]
+  if (lane < N) {
+#pragma unroll
+    for (int q = 0; q < N; q++) Minv[mystep * ldi + rowsel[q]] = a[q] * dinv;
   }
   return flag;
 }
@@ -884,7 +974,13 @@ __device__ __forceinline__ void cta_inverse_apply(double *M, int ldm, int nc, do
   __syncthreads();
   double *Minv = scratch, *rowbuf = scratch + NX * (NX + 1);
   if (warp_id_uniform() == 0) {
-    const int fl = warp_gj_inverse<NX>(M, ldm, Minv, NX + 1, rowbuf, rowsel);
+    int fl;
+    if constexpr (NX <= 32 && LQ_GJ_MODE == 1)
+      fl = warp_gj_inverse_la<NX, false>(M, ldm, Minv, NX + 1, rowbuf, rowsel);
+    else if constexpr (NX <= 32 && LQ_GJ_MODE == 2)
+      fl = warp_gj_inverse_la<NX, true>(M, ldm, Minv, NX + 1, rowbuf, rowsel);
+    else
+      fl = warp_gj_inverse<NX>(M, ldm, Minv, NX + 1, rowbuf, rowsel);
     if (fl && (threadIdx.x & 31) == 0) *st_s |= fl;
   }
   __syncthreads();

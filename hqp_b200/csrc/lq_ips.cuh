@@ -57,10 +57,21 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
   const int k = blockIdx.x;
   const int dk = (k < d.K) ? nm : nx;
   const size_t xo = (size_t)k * nm;
+  if (k == d.K && d.has_next) {
+    // horizon split: the trailing block duplicates the next range's x_0; its rows
+    // (and its share of every reduction) belong to that rank
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) r1[xo + i] = 0.0;
+    if (threadIdx.x < IPS_NQ) partial[(size_t)blockIdx.x * IPS_NQ + threadIdx.x] = 0.0;
+    return;
+  }
+  const double *xnext = (d.has_next && d.halo && k == d.K - 1)
+                            ? d.halo + (size_t)(d.rank + 1) * 2 * nx : nullptr;
+  const double *yprev = (d.has_prev && d.halo && k == 0)
+                            ? d.halo + (size_t)(d.rank - 1) * 2 * nx + nx : nullptr;
   for (int i = threadIdx.x; i < dk; i += blockDim.x) xs[i] = v.x[xo + i];
   if (k < d.K)
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      xn[i] = v.x[xo + nm + i];
+      xn[i] = xnext ? xnext[i] : v.x[xo + nm + i];
       yk[i] = v.y[(size_t)k * nx + i];
     }
   __syncthreads();
@@ -88,6 +99,7 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
     if (i < nx) {
       if (k > 0) s += v.y[(size_t)(k - 1) * nx + i];
       else if (d.fixed_x0) s -= v.y[(size_t)d.K * nx + i];
+      else if (yprev) s += yprev[i];
     }
     const int gv = k * nm + i;
     for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++)
@@ -296,6 +308,42 @@ __global__ void ips_gather_blocking_kernel(int m, const int *__restrict__ idx,
   out[7] = vz ? dw[iz] : 0.0;
   out[8] = (double)iz;
   out[9] = (double)iw;
+}
+
+// horizon split: local first-minimum indices -> indices on the whole horizon
+// (rows of the ranges are numbered range after range); out[0..1] as doubles
+// (exact below 2^53), 1e300 where this range has no candidate
+__global__ void ips_global_index_kernel(int m, long long row0, const int *__restrict__ idx,
+                                        double *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out[0] = idx[0] < m ? (double)(row0 + idx[0]) : 1.0e300;
+  out[1] = idx[1] < m ? (double)(row0 + idx[1]) : 1.0e300;
+}
+
+// as ips_gather_blocking_kernel with the winners given by their horizon-wide index
+// gidx[0..1] (after the min-all-reduce): only the owning range writes the entries,
+// so that a sum-all-reduce delivers them everywhere; out[8], out[9] = the indices
+__global__ void ips_gather_blocking_dist_kernel(int m, long long row0,
+                                                const double *__restrict__ gidx,
+                                                const double *__restrict__ z,
+                                                const double *__restrict__ dz,
+                                                const double *__restrict__ w,
+                                                const double *__restrict__ dw, double *out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const double gz = gidx[0], gw = gidx[1];
+  const long long iz = gz < 1.0e299 ? (long long)gz - row0 : -1;
+  const long long iw = gw < 1.0e299 ? (long long)gw - row0 : -1;
+  const bool vw = iw >= 0 && iw < m, vz = iz >= 0 && iz < m;
+  out[0] = vw ? z[iw] : 0.0;
+  out[1] = vw ? dz[iw] : 0.0;
+  out[2] = vw ? w[iw] : 0.0;
+  out[3] = vw ? dw[iw] : 0.0;
+  out[4] = vz ? z[iz] : 0.0;
+  out[5] = vz ? dz[iz] : 0.0;
+  out[6] = vz ? w[iz] : 0.0;
+  out[7] = vz ? dw[iz] : 0.0;
+  out[8] = gz;  // (not all-reduced: identical on every rank already)
+  out[9] = gw;
 }
 
 // corrector right-hand side r4 = -(z w + dza dwa - smm)  (:597-600, :616-619)

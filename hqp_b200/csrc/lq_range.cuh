@@ -115,9 +115,11 @@ __global__ void range_export_vec_kernel(LqDev d, const double *__restrict__ r2, 
 //   FWD : t = x_start(rank 0);   for r = 0 .. rank-1:       t = x0_r + Psi_r t;
 //         xstart = t  (rank > 0)
 // gv: [world][2][nx], gpsi: [world][nx*nx].  One CTA, nx <= blockDim.x.
+// psi_stride: doubles between the transitions of consecutive ranks in gpsi.
 template <bool BACK>
 __global__ void range_scan_vec_kernel(LqDev d, const double *__restrict__ gv,
-                                      const double *__restrict__ gpsi, int rank, int world) {
+                                      const double *__restrict__ gpsi, int rank, int world,
+                                      int psi_stride) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *t = reinterpret_cast<double *>(smem_raw);  // nx
   double *u = t + d.nx;
@@ -128,7 +130,7 @@ __global__ void range_scan_vec_kernel(LqDev d, const double *__restrict__ gv,
   __syncthreads();
   if (BACK) {
     for (int r = world - 1; r > rank; r--) {
-      const double *P = gpsi + (size_t)r * n2;
+      const double *P = gpsi + (size_t)r * psi_stride;
       if (i < nx) {
         double s = gv[(size_t)r * 2 * nx + i];
         for (int l = 0; l < nx; l++) s = fma(P[l * nx + i], t[l], s);
@@ -141,7 +143,7 @@ __global__ void range_scan_vec_kernel(LqDev d, const double *__restrict__ gv,
     if (rank < world - 1 && i < nx) d.v[(size_t)d.K * nx + i] += t[i];
   } else {
     for (int r = 0; r < rank; r++) {
-      const double *P = gpsi + (size_t)r * n2;
+      const double *P = gpsi + (size_t)r * psi_stride;
       if (i < nx) {
         double s = gv[(size_t)r * 2 * nx + i];
         for (int l = 0; l < nx; l++) s = fma(P[i * nx + l], t[l], s);
@@ -152,5 +154,19 @@ __global__ void range_scan_vec_kernel(LqDev d, const double *__restrict__ gv,
       __syncthreads();
     }
     if (rank > 0 && i < nx) d.xstart[i] = t[i];
+  }
+}
+
+// Status word of this range appended to its transition block (slot n2 of xpsi), and
+// the OR of all ranges' words back into d.status after the all-gather: every rank
+// then takes the same branch on a singular / non-PD block anywhere on the horizon.
+__global__ void range_status_pack_kernel(LqDev d, double *xpsi) {
+  if (threadIdx.x == 0) xpsi[d.nx * d.nx] = (double)*d.status;
+}
+__global__ void range_status_merge_kernel(LqDev d, const double *gpsi, int world, int psi_stride) {
+  if (threadIdx.x == 0) {
+    int st = 0;
+    for (int r = 0; r < world; r++) st |= (int)gpsi[(size_t)r * psi_stride + d.nx * d.nx];
+    *d.status = st;
   }
 }

@@ -721,6 +721,19 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
   const int dk = (k < d.K) ? nm : nx;
   const size_t xo = (size_t)b * d.N + (size_t)k * nm;
   const size_t yo = (size_t)b * d.me;
+  if (k == d.K && d.has_next) {
+    // horizon split: the trailing state block is the next range's x_0 -- its rows
+    // belong to that rank
+    if (t1)
+      for (int i = threadIdx.x; i < nx; i += blockDim.x) t1[xo + i] = 0.0;
+    return;
+  }
+  // state after the last local stage / multiplier before the first: from the
+  // neighbouring ranges when the horizon is split
+  const double *xnext = (d.has_next && d.halo && k == d.K - 1)
+                            ? d.halo + (size_t)(d.rank + 1) * 2 * nx : nullptr;
+  const double *yprev = (d.has_prev && d.halo && k == 0)
+                            ? d.halo + (size_t)(d.rank - 1) * 2 * nx + nx : nullptr;
   for (int i = threadIdx.x; i < dk; i += blockDim.x) xs[i] = dx[xo + i];
   if (k < d.K)
     for (int i = threadIdx.x; i < nx; i += blockDim.x) yk[i] = dy[yo + (size_t)k * nx + i];
@@ -749,6 +762,7 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
     if (i < nx) {
       if (k > 0) s += dy[yo + (size_t)(k - 1) * nx + i];  // -(-I)' dy_{k-1}
       else if (d.fixed_x0) s -= dy[yo + (size_t)d.K * nx + i];
+      else if (yprev) s += yprev[i];
     }
     const int gv = k * nm + i;
     for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++)
@@ -762,7 +776,7 @@ __global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
   if (k < d.K) {
     const double *fx = d.fx + ks * nx * nx, *fu = d.fu + ks * nx * nu;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = -dx[xo + nm + i];
+      double s = xnext ? -xnext[i] : -dx[xo + nm + i];
 #pragma unroll 10
       for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
 #pragma unroll 10

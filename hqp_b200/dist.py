@@ -243,3 +243,47 @@ class CudaRangeEngine:
 
     def close(self):
         self.eng.close()
+
+
+# --------------------------------------------------------------------------
+# the exchanges inside the library (hqpcu_comm_init): what bench.py and the
+# multi-process GPU tests use
+# --------------------------------------------------------------------------
+def exchange_unique_id(rank, group=None):
+    """NCCL unique id of a new library communicator: made on rank 0, broadcast over
+    the existing torch.distributed group (nccl or gloo)."""
+    import torch
+    import torch.distributed as dist
+    from . import ipcuda
+    if dist.get_world_size(group) == 1:
+        return None
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t.copy_(torch.frombuffer(bytearray(ipcuda.IpCuda.comm_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+class DistIpCuda:
+    """One rank's stage range of a horizon split over the GPUs of the process group.
+
+    Wraps an `IpCuda` handle created for the LOCAL problem and turned into rank
+    `rank` of `world` by `hqpcu_comm_init`: afterwards the handle's own methods
+    (update / factor / step / solve / residuum / mehrotra_solve and their `_dev`
+    flavours) run the split algorithm on the local slices, NCCL calls included, and
+    must be called by all ranks together."""
+
+    def __init__(self, local_prob: LQProblem, rank, world, device=0, nseg=0, group=None):
+        from . import ipcuda
+        self.rank, self.world = rank, world
+        self.eng = ipcuda.IpCuda(local_prob, device=device, nseg=nseg)
+        uid = exchange_unique_id(rank, group) if world > 1 else None
+        self.eng.comm_init(uid, rank, world)
+
+    def __getattr__(self, name):
+        return getattr(self.eng, name)
+
+    def close(self):
+        self.eng.close()

@@ -109,6 +109,23 @@ class IpCuda:
         except Exception:
             pass
 
+    # -- horizon split (hqpcu_comm_*): this handle = one rank's stage range ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (ctypes.c_ubyte * 128)()
+        _check(lib().hqpcu_comm_unique_id(buf), "hqpcu_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        buf = (ctypes.c_ubyte * 128).from_buffer_copy(uid) if uid is not None else None
+        _check(lib().hqpcu_comm_init(self.h, buf, rank, world), "hqpcu_comm_init")
+
+    def comm_info(self):
+        r, w, m = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_longlong(0)
+        _check(lib().hqpcu_comm_info(self.h, ctypes.byref(r), ctypes.byref(w), ctypes.byref(m)),
+               "hqpcu_comm_info")
+        return r.value, w.value, m.value
+
     def set_stream(self, cuda_stream: int):
         _check(lib().hqpcu_set_stream(self.h, ctypes.c_void_p(cuda_stream)), "set_stream")
 
@@ -237,6 +254,13 @@ class IpCuda:
     def update_dev(self, Q, fx, fu, ineq_val):
         _check(lib().hqpcu_update_dev(self.h, _vp(Q), _vp(fx), _vp(fu), _vp(ineq_val), None),
                "hqpcu_update_dev")
+
+    def update_stages_dev(self, k0, nq, Q, nf, fx, fu):
+        _check(lib().hqpcu_update_stages_dev(self.h, int(k0), int(nq), _vp(Q), int(nf), _vp(fx),
+                                             _vp(fu)), "hqpcu_update_stages_dev")
+
+    def update_ineq_dev(self, ineq_val):
+        _check(lib().hqpcu_update_ineq_dev(self.h, _vp(ineq_val)), "hqpcu_update_ineq_dev")
 
     def factor_dev(self, z, w):
         _check(lib().hqpcu_factor_dev(self.h, _vp(z), _vp(w)), "hqpcu_factor_dev")

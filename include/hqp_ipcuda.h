@@ -98,6 +98,14 @@ int hqpcu_update_dev(hqpcu_handle *h, const double *Q, const double *fx,
                      const double *fu, const double *ineq_val,
                      const double *eq_val);
 
+/* update of a stage window / of the inequality values from DEVICE memory (a host
+ * that builds its matrices on the GPU, or a 10^6-stage horizon produced chunk by
+ * chunk): nq blocks of Q for stages k0 .. k0+nq-1 (<= K), nf blocks of fx and fu
+ * for stages k0 .. k0+nf-1 (< K).  batch == 1.                                  */
+int hqpcu_update_stages_dev(hqpcu_handle *h, int k0, int nq, const double *Q, int nf,
+                            const double *fx, const double *fu);
+int hqpcu_update_ineq_dev(hqpcu_handle *h, const double *ineq_val);
+
 /* --- update from sparse values -----------------------------
  * Replaces the host-side walk that writes every SPMAT entry into a dense
  * stage block (sp_extract_mat_iter in Hqp_IpLQDOCP::update,
@@ -183,6 +191,30 @@ int hqpcu_range_step_mid(hqpcu_handle *h, const double *gv, const double *gpsi, 
                          int world, double *xx);
 int hqpcu_range_step_finish(hqpcu_handle *h, const double *gx, const double *gpsi, int rank,
                             int world, double *dx, double *dy, double *dz, double *dw);
+
+/* --- horizon split with the exchanges INSIDE the library.
+ *     hqpcu_comm_init turns the handle into rank `rank` of `world` contiguous stage
+ *     ranges (same local-K / local-row conventions as hqpcu_range_config) and
+ *     creates an NCCL communicator from a 128-byte unique id that the caller
+ *     distributes (rank 0: hqpcu_comm_unique_id, then MPI / torch.distributed /
+ *     a file).  NCCL is bound at run time (dlopen of libnccl.so.2; an NCCL already
+ *     in the process is shared); without it these two calls return
+ *     HQPCU_E_UNSUPPORTED and everything else keeps working on one GPU.
+ *     Afterwards EVERY entry point above (update, factor, step, solve, residuum,
+ *     mehrotra_solve, host or _dev flavour) works on the range's local slices and
+ *     must be called by all ranks together: the all-gathers of the boundary
+ *     elements / vectors and the all-reduces of the residual norm and of the IP
+ *     scalars (sum: mu, gap, dots; min: step lengths; max: norms --
+ *     hqp/Hqp_IpsMehrotra.C:425-465, 566-574, 627-681; hqp/Hqp_IpMatrix.C:131-178)
+ *     are issued on the handle's stream as nodes of the same CUDA graphs as the
+ *     kernels.  A singular / non-PD status is merged over the ranks, so all ranks
+ *     take the same branch.  world == 1 is allowed (no NCCL needed).
+ *     batch == 1, no general equality rows; a non-positive pivot at a segment end
+ *     returns HQPCU_E_NOTPD (no sequential fallback across ranks).              */
+int hqpcu_comm_unique_id(unsigned char *id128);
+int hqpcu_comm_init(hqpcu_handle *h, const unsigned char *id128, int rank, int world);
+/* rank, world and the number of inequality rows on the whole horizon (any may be NULL) */
+int hqpcu_comm_info(const hqpcu_handle *h, int *rank, int *world, long long *m_global);
 
 /* --- device-resident interior-point solve: Hqp_IpsMehrotra::cold_start + ::solve
  *     (hqp/Hqp_IpsMehrotra.C:209-327, 355-733; predictor-corrector with Terlaky's

@@ -45,6 +45,8 @@ EQ_CASES = {
     "eqstep_mid_and_terminal_n3m2K16": (3, 2, 16, True, 1, True, [16, 7], 1),
     "eqstep_free_x0_n4m3K9": (4, 3, 9, False, 0, False, [9, 0], 2),
     "eqstep_n20m10K60": (20, 10, 60, True, 0, True, [60], 6),
+    # 56 rows: above the 48 KB default shared-memory limit of the Schur inverse
+    "eqstep_56rows_n20m10K60": (20, 10, 60, True, 0, True, [60, 52, 44, 36, 28, 20, 12], 8),
 }
 
 
@@ -64,7 +66,10 @@ def make_problem(nx, nu, K, bounds, gen, fixed):
 
 
 def main():
+    only = sys.argv[1:]  # optional: regenerate just the named fixtures
     for name, cfg in STEP_CASES.items():
+        if only and name not in only:
+            continue
         p = make_problem(*cfg)
         z, w, r1, r2, r3, r4 = rhs_for(p, seed=99)
         qp = R.RefQP(p)
@@ -79,6 +84,8 @@ def main():
         M.close()
         qp.close()
     for name, cfg in EQ_CASES.items():
+        if only and name not in only:
+            continue
         p = make_eq_problem(*cfg)
         z, w, r1, r2, r3, r4 = rhs_for(p, seed=77)
         qp = R.RefQP(p)
@@ -90,6 +97,8 @@ def main():
         print(name, "res", res)
         M.close()
         qp.close()
+    if only:
+        return
     for name, (nx, nu, K) in {"ips_n5m3K40": (5, 3, 40), "ips_n20m10K200": (20, 10, 200)}.items():
         p = synth_lqdocp(nx, nu, K)
         qp = R.RefQP(p)

@@ -198,6 +198,67 @@ def test_c2_prefix_matches_oracle_on_truncated_horizon():
     e.close(); o.close()
 
 
+# ---- full BASELINE sizes against the live reference / the port oracle -----------
+def _ref_available():
+    from oracle import refharness
+    return refharness.available()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("shape", [(20, 10, 10000), (40, 10, 2500)])
+def test_full_size_step_and_solve_match_live_reference(shape):
+    """C2 at its full K = 10^4 and the C5 stage shape at K = 2500: factor, step and
+    the refined solve against the UNMODIFIED Hqp_IpLQDOCP (oracle/_ref) run here on
+    the same seeded inputs."""
+    from oracle import refharness
+    nx, nu, K = shape
+    p = synth_lqdocp(nx, nu, K)
+    z, w, r1, r2, r3, r4 = synth_rhs(p)
+    qp = refharness.RefQP(p)
+    M = refharness.RefMatrix("LQDOCP", qp)
+    M.factor(z, w)
+    ref = M.step(z, w, r1, r2, r3, r4)
+    rs = M.solve(z, w, r1, r2, r3, r4)
+    e = IpCuda(p)
+    assert e.nseg > 1
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b, key in zip(mine, ref, ("dx", "dy", "dz", "dw")):
+        assert relerr(a, b) < TOL, key
+    sx, sy, sz, sw, res, nsteps = e.solve(r1, r2, r3, r4)
+    for a, b, key in zip((sx, sy, sz, sw), rs[:4], ("sx", "sy", "sz", "sw")):
+        assert relerr(a, b) < TOL, key
+    assert res <= 1e-10 and rs[4] <= 1e-10
+    e.close(); M.close(); qp.close()
+
+
+def test_c3_full_batch_sampled_instances_match_oracle():
+    """config 3 at its full size: 4096 DIFFERENT instances nx=12 nu=4 K=50 in one
+    batch; sampled instances against the port oracle."""
+    nx, nu, K, B = 12, 4, 50, 4096
+    probs = [synth_lqdocp(nx, nu, K, seed=5000 + i) for i in range(B)]
+    p0 = probs[0]
+    rng = np.random.default_rng(3)
+    z = 0.5 + rng.uniform(0, 1, (B, p0.m)); w = 0.5 + rng.uniform(0, 1, (B, p0.m))
+    r1 = rng.uniform(-1, 1, (B, p0.N)); r2 = rng.uniform(-1, 1, (B, p0.me))
+    r3 = rng.uniform(-1, 1, (B, p0.m)); r4 = rng.uniform(-1, 1, (B, p0.m))
+    e = IpCuda(p0, batch=B)
+    e.update(Q=np.stack([p.Q for p in probs]), fx=np.stack([p.fx for p in probs]),
+             fu=np.stack([p.fu for p in probs]), ineq_val=np.stack([p.ineq_val for p in probs]))
+    e.factor(z.ravel(), w.ravel())
+    out = e.step(r1.ravel(), r2.ravel(), r3.ravel(), r4.ravel())
+    sizes = (p0.N, p0.me, p0.m, p0.m)
+    for i in (0, 1, 777, 2048, 4095):
+        o = PortOracle(probs[i])
+        o.factor(z[i], w[i])
+        ref = o.step(r1[i], r2[i], r3[i], r4[i])
+        for a, b, n in zip(out, ref, sizes):
+            assert relerr(a[i * n:(i + 1) * n], b) < TOL
+        o.close()
+    e.close()
+
+
 # ---- general stage equality rows (terminal constraints) ------------------------
 from common import dense_kkt_solve, eq_cases, make_eq_problem  # noqa: E402
 import os  # noqa: E402
