@@ -95,6 +95,7 @@ struct hqpcu_handle {
   long long n_solves = 0, n_solve_steps = 0;  // hqpcu_solve_stats
   int device = 0;
   int nseg_req = 0;       // segment count asked for (0 = automatic); hqpcu_set_nseg updates it
+  bool big = false;       // stage blocks exceed shared memory: global-workspace kernels (LqDev::gws)
   bool demoted = false;   // E_NOTPD fallback to the sequential sweep is in force until the next update
   std::vector<void *> allocs;
   // owned device copies
@@ -328,7 +329,7 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
       // (one resident CTA per SM at nx >= 32: two waves, the shorter solve chains
       //  pay for it -- measured at the C5 slice)
       const int wave = std::max(1, h->n_sm * std::max(1, h->k1_ctas_per_sm)) *
-                       (h->dims.nx >= 32 ? 2 : 1);
+                       (h->dims.nx >= 32 && !h->big ? 2 : 1);
       const int per_inst = std::max(1, wave / std::max(1, h->dims.batch));
       P = std::max(2, std::min(per_inst, K / 8));
     }
@@ -409,8 +410,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     g_err = "hqpcu_create: nu = 0 is not supported";
     return HQPCU_E_UNSUPPORTED;
   }
-  if (dims->nx > 64) {
-    g_err = "hqpcu_create: nx > 64 needs the tiled large-block kernels (not built yet)";
+  if (dims->nx > 256 || dims->nu > 256) {
+    g_err = "hqpcu_create: stage blocks larger than 256 are not supported";
     return HQPCU_E_UNSUPPORTED;
   }
   if (dims->n_eq > 0 && dims->batch != 1) {
@@ -471,6 +472,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, dims->device);
     // 3 was the measured optimum at nx=20 (4 fit by size but run in two waves)
     h->k1_ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (227 * 1024) / (k1 + 1024)));
+    h->big = k1 + 1024 > 227 * 1024;
   }
   choose_segments(h, dims->nseg);
 
@@ -580,7 +582,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_alloc(h, &d.LD, SB * K * nu * nu));
   TRY(dev_alloc(h, &d.Phi, SB * K * nx * nx));
   // bulk-copy (TMA) path needs every per-stage slab to be a 16-byte multiple
-  d.use_tma = (nx % 2 == 0 && nu % 2 == 0) ? 1 : 0;
+  d.use_tma = (nx % 2 == 0 && nu % 2 == 0 && !h->big) ? 1 : 0;
   TRY(dev_alloc(h, &d.hdiag, SB * d.N));
   // element arrays are sized for the hierarchy chosen here; hqpcu_set_nseg may
   // only shrink it
@@ -667,10 +669,32 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
                  2 * sizeof(uint64_t) + 16;
   const size_t smem_max = 227 * 1024;
   if (h->smem_k1 > smem_max || h->smem_k2 > smem_max || h->smem_k3 > smem_max ||
-      h->smem_cmp > smem_max || h->smem_psi > smem_max) {
-    g_err = "hqpcu_create: stage blocks too large for the shared-memory kernels";
-    hqpcu_destroy(h);
-    return HQPCU_E_UNSUPPORTED;
+      h->smem_cmp > smem_max || h->smem_psi > smem_max)
+    h->big = true;
+  if (h->big) {
+    // Large stage blocks: the CTA-internal blocks live in a per-CTA slice of a
+    // global workspace (LqDev::gws); shared memory holds barriers and flags only.
+    d.use_tma = 0;
+    const size_t need = std::max({h->smem_k1, h->smem_k2, h->smem_k3, h->smem_cmp, h->smem_psi,
+                                  nn * sizeof(double)}) + (size_t)(nx + 16) * sizeof(double);
+    d.gws_stride = pad2(need / sizeof(double) + 2);
+    TRY(dev_alloc(h, &d.gws, (size_t)std::max(d.P, 1) * B * d.gws_stride));
+    h->smem_k1 = h->smem_k2 = h->smem_k3 = h->smem_cmp = h->smem_psi = 0;
+    h->ring_chain = 0;   // the chains read their matrices from global memory directly
+    h->ring_scan = 0;
+    h->smem_chain = h->smem_scan = pad2((size_t)3 * nx) * sizeof(double) + 2 * sizeof(uint64_t) + 16;
+  }
+  // the middle pass keeps one LDL^T factor of Guu per warp in shared memory
+  {
+    const size_t sv = (size_t)LQ_WPB * 2 * (nx + nu + (size_t)nu * nu) * sizeof(double);
+    if (sv > smem_max) {
+      g_err = "hqpcu_create: nu too large for the stage-parallel solve pass";
+      hqpcu_destroy(h);
+      return HQPCU_E_UNSUPPORTED;
+    }
+    TRY(set_smem((const void *)(solve_mid_kernel<1, 32>), sv));
+    TRY(set_smem((const void *)(solve_mid_kernel<2, 32>), sv));
+    TRY(set_smem((const void *)(solve_mid_kernel<2, 16>), sv));
   }
 #define SET_A(NX_, NU_)                                                        \
   TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, 4>, h->smem_k1));   \
@@ -688,7 +712,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   LQ_DISPATCH_NX(nx, nu, SET_B);
 #undef SET_A
 #undef SET_B
-  TRY(set_smem((const void *)x0_factor_kernel, nn * sizeof(double)));
+  if (!h->big) TRY(set_smem((const void *)x0_factor_kernel, nn * sizeof(double)));
   if (h->smem_chain > smem_max) {
     g_err = "hqpcu_create: chain ring exceeds shared memory";
     hqpcu_destroy(h);
@@ -994,7 +1018,7 @@ static int launch_factor_down(hqpcu_handle *h) {
   }
   if (!d.fixed_x0 && !d.has_prev)
     LAUNCH(h, x0_factor_kernel,
-           <<<d.batch, 32, pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
+           <<<d.batch, 32, h->big ? 0 : pad2((size_t)d.nx * d.nx) * sizeof(double), s>>>(d));
   CUL(h);
   return HQPCU_OK;
 }

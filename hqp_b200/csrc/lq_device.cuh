@@ -41,6 +41,11 @@ struct LqDev {
   int has_next;       // a rank behind this one supplies the terminal value
   double *Vext;       // [nx*nx] value Hessian handed over from the ranks behind
   double *xstart;     // [nx]    state at stage 0 handed over from the ranks before
+  // Large stage blocks (nx > 64): the CTA-internal blocks of the factor kernels do
+  // not fit the 227 KB of shared memory; they then live in a per-CTA slice of this
+  // global workspace (L2-resident) and shared memory only stages GEMM panels
+  double *gws;          // NULL: blocks in shared memory
+  size_t gws_stride;    // doubles per CTA
   // halo of the residual passes: [world][2 nx] = (first state, last dynamics
   // multiplier) of every range, all-gathered before the pass (NULL: no split)
   const double *halo;
@@ -891,12 +896,21 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
     }
   }
   __syncthreads();
-  unsigned long long used = 0ull;  // rows already consumed as pivot rows
+  // rows already consumed as pivot rows (n <= 256: four 64-bit words)
+  unsigned long long used0 = 0ull, used1 = 0ull, used2 = 0ull, used3 = 0ull;
+  auto is_used = [&](int i) -> bool {
+    const unsigned long long wsel = i < 128 ? (i < 64 ? used0 : used1) : (i < 192 ? used2 : used3);
+    return (wsel >> (i & 63)) & 1ull;
+  };
   const int q = threadIdx.x & 3, jl = threadIdx.x >> 2, ncol = blockDim.x >> 2;
   for (int p = 0; p < n; p++) {
     const int r = piv_s[p];
     const double inv = inv_s[p & 1];
-    used |= 1ull << r;
+    {
+      const unsigned long long bit = 1ull << (r & 63);
+      if (r < 64) used0 |= bit; else if (r < 128) used1 |= bit;
+      else if (r < 192) used2 |= bit; else used3 |= bit;
+    }
     for (int j0 = p + 1; j0 < nc; j0 += ncol) {  // uniform trip count: shuffles below
       const int j = j0 + jl;
       const bool act = j < nc;
@@ -919,7 +933,7 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
             const int i = q + 4 * k;
             c[k] = fma(-f[k], prj, c[k]);
             if (i < NX && i != r) M[i * ldm + j] = c[k];
-            if (i < NX && !((used >> i) & 1ull) && fabs(c[k]) > best) {
+            if (i < NX && !is_used(i) && fabs(c[k]) > best) {
               best = fabs(c[k]); bv = c[k]; bi = i;
             }
           }
@@ -927,7 +941,7 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
           for (int i = q; i < n; i += 4) {
             const double v = fma(-M[i * ldm + p], prj, M[i * ldm + j]);
             if (i != r) M[i * ldm + j] = v;
-            if (!((used >> i) & 1ull) && fabs(v) > best) { best = fabs(v); bv = v; bi = i; }
+            if (!is_used(i) && fabs(v) > best) { best = fabs(v); bv = v; bi = i; }
           }
         }
       }
@@ -994,6 +1008,14 @@ __device__ __forceinline__ void atomic_max_nonneg(double *addr, double val) {
   // NaN (all-ones exponent, non-zero mantissa) compares above +inf and sticks.
   atomicMax(reinterpret_cast<unsigned long long *>(addr),
             static_cast<unsigned long long>(__double_as_longlong(fabs(val))));
+}
+
+// base of the CTA's block storage: dynamic shared memory, or its slice of the
+// global workspace when the stage blocks are too large for it
+__device__ __forceinline__ unsigned char *cta_workspace(const LqDev &d, unsigned char *smem_raw) {
+  if (!d.gws) return smem_raw;
+  const size_t cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+  return reinterpret_cast<unsigned char *>(d.gws + cta * d.gws_stride);
 }
 
 // shared-memory carve-up helper (16-byte granularity)

@@ -163,15 +163,17 @@ __device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
 }
 
 // set up pipe storage and barriers; returns after a CTA barrier
-__device__ __forceinline__ void stage_pipe_init(int nx, int nu, SmemCarver &sm, StagePipe &sp) {
+// (bars: two mbarriers in SHARED memory, used by the bulk-copy path only)
+__device__ __forceinline__ void stage_pipe_init(int nx, int nu, SmemCarver &sm, StagePipe &sp,
+                                                uint64_t *bars, bool use_tma) {
   const int nm = nx + nu;
   sp.o_fx = (nm * nm + 1) & ~1;
   sp.o_fu = sp.o_fx + ((nx * nx + 1) & ~1);
   sp.o_hd = sp.o_fu + ((nx * nu + 1) & ~1);
   sp.slot = sp.o_hd + ((nm + 1) & ~1);
   sp.base = sm.take(2 * sp.slot);
-  sp.bar = sm.take_bars(2);
-  if (threadIdx.x == 0) {
+  sp.bar = bars;
+  if (use_tma && threadIdx.x == 0) {
     mbar_init(&sp.bar[0], 1);
     mbar_init(&sp.bar[1], 1);
     mbar_fence_init();
@@ -312,9 +314,10 @@ seg_element_kernel(LqDev d) {
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
-  SmemCarver sm(smem_raw);
+  SmemCarver sm(cta_workspace(d, smem_raw));
   StagePipe sp;
-  stage_pipe_init(nx, nu, sm, sp);
+  __shared__ __align__(8) uint64_t pipe_bars[2];
+  stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
   double *fup = TC ? sm.take(nx * LU) : nullptr;
   double *J = sm.take(nx * LV), *A0 = sm.take(nx * LV), *A1 = sm.take(nx * LV);
   double *Cg = sm.take(nx * LV), *T = sm.take(nx * LT);
@@ -378,15 +381,16 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   const int ldm = NX > 0 ? n3 + 1 : n3;  // odd row stride for the warp inverse
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
-  SmemCarver sm(smem_raw);
+  SmemCarver sm(cta_workspace(d, smem_raw));
   const int ldx = NX > 0 ? 2 * nx + 4 : 2 * nx;  // = 4 (mod 8): conflict-free fragment reads
   double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
   double *Ai = sm.take(n2), *Ji = sm.take(n2);
   double *M = sm.take(nx * ldm), *T1 = sm.take(n2), *T2 = sm.take(n2), *T3 = sm.take(n2);
   double *X = sm.take(nx * ldx);  // [X_A | X_C]
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
-  __shared__ int st_s, piv_s[65];
+  __shared__ int st_s, piv_small[65];
   __shared__ double inv_s[2];
+  int *piv_s = nx <= 64 ? piv_small : reinterpret_cast<int *>(sm.take((nx + 2) / 2));
   constexpr int NWC = LQ_NT2 / 32;
   if (threadIdx.x == 0) st_s = 0;
   __syncthreads();  // (before any load: costs nothing on the critical path)
@@ -472,13 +476,14 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
-  SmemCarver sm(smem_raw);
+  SmemCarver sm(cta_workspace(d, smem_raw));
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm);
   double *X = sm.take(n2);
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
-  __shared__ int st_s, piv_s[65];
+  __shared__ int st_s, piv_small[65];
   __shared__ double inv_s[2];
+  int *piv_s = nx <= 64 ? piv_small : reinterpret_cast<int *>(sm.take((nx + 2) / 2));
   if (threadIdx.x == 0) st_s = 0;
   int c0, c1;
   if (top) {
@@ -559,9 +564,10 @@ seg_riccati_kernel(LqDev d) {
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
-  SmemCarver sm(smem_raw);
+  SmemCarver sm(cta_workspace(d, smem_raw));
   StagePipe sp;
-  stage_pipe_init(nx, nu, sm, sp);
+  __shared__ __align__(8) uint64_t pipe_bars[2];
+  stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
   double *fup = TC ? sm.take(nx * LU) : nullptr;
   double *V = sm.take(nx * LV), *T = sm.take(nx * LT);
   double *RuxA = sm.take(nu * LV), *RuxB = sm.take(nu * LV), *Phi = sm.take(nx * LV);
@@ -676,7 +682,7 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
-  double *bufA = reinterpret_cast<double *>(smem_raw);  // chunk blocks
+  double *bufA = reinterpret_cast<double *>(cta_workspace(d, smem_raw));  // chunk blocks
   double *bufB = bufA + (size_t)chunk * n2;             // ceil(chunk/2) blocks
   const size_t base = ((size_t)b * d.st.nel + d.st.off[lev]) * n2;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -756,7 +762,7 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
 __global__ void x0_factor_kernel(LqDev d) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, b = blockIdx.x;
-  double *A = reinterpret_cast<double *>(smem_raw);
+  double *A = reinterpret_cast<double *>(cta_workspace(d, smem_raw));
   const double *V0 = d.V + (size_t)b * (d.K + 1) * nx * nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) A[i] = V0[i];
   __syncthreads();

@@ -49,12 +49,13 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
-  SmemCarver sm(smem_raw);
+  SmemCarver sm(cta_workspace(d, smem_raw));
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm), *X = sm.take(n2);
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
-  __shared__ int st_s, piv_s[65];
+  __shared__ int st_s, piv_small[65];
   __shared__ double inv_s[2];
+  int *piv_s = nx <= 64 ? piv_small : reinterpret_cast<int *>(sm.take((nx + 2) / 2));
   if (threadIdx.x == 0) st_s = 0;
   const double *last = gathered + (size_t)(world - 1) * 4 * n2;
   for (int i = threadIdx.x; i < n2; i += blockDim.x) S[i] = last[3 * n2 + i];
