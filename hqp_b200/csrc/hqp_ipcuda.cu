@@ -680,8 +680,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     d.gws_stride = pad2(need / sizeof(double) + 2);
     TRY(dev_alloc(h, &d.gws, (size_t)std::max(d.P, 1) * B * d.gws_stride));
     h->smem_k1 = h->smem_k2 = h->smem_k3 = h->smem_cmp = h->smem_psi = 0;
-    h->ring_chain = 0;   // the chains read their matrices from global memory directly
-    h->ring_scan = 0;
+    // (the chains read their matrices from global memory directly: no ring)
     h->smem_chain = h->smem_scan = pad2((size_t)3 * nx) * sizeof(double) + 2 * sizeof(uint64_t) + 16;
   }
   // the middle pass keeps one LDL^T factor of Guu per warp in shared memory

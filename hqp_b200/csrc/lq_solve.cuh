@@ -124,10 +124,12 @@ struct ChainSmem {
   uint64_t *bars;
 };
 
-__device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH) {
+// (the ring only exists on the bulk-copy path; without it the chain reads its
+//  matrices from global memory and CH is just the loop blocking)
+__device__ __forceinline__ ChainSmem chain_smem_init(int n, void *raw, int CH, bool ring = true) {
   SmemCarver sm(raw);
   ChainSmem cs;
-  cs.ring = sm.take(2 * CH * (n * n + 2 * n));
+  cs.ring = ring ? sm.take(2 * CH * (n * n + 2 * n)) : nullptr;
   cs.tvec = sm.take(3 * n);
   cs.bars = sm.take_bars(2);
   if (threadIdx.x == 0) {
@@ -381,7 +383,7 @@ __global__ void solve_back_kernel(LqDev d, int mode, int ring_n) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n, NX > 0 || d.use_tma);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
@@ -419,7 +421,7 @@ __global__ void solve_fwd_kernel(LqDev d, int mode, int ring_n) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n, NX > 0 || d.use_tma);
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const size_t so = ((size_t)b * d.st.nel + s) * nx;
@@ -475,7 +477,7 @@ __global__ void solve_scan_kernel(LqDev d, int lev, int phase, const double *__r
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx;
-  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n);
+  ChainSmem cs = chain_smem_init(nx, smem_raw, ring_n, NX > 0 || d.use_tma);
   const int g = blockIdx.x, b = blockIdx.y;
   const size_t eb = (size_t)b * d.st.nel + d.st.off[lev];           // first element of level
   const size_t pb = (size_t)b * d.st.nel + (phase == 1 ? 0 : d.st.off[lev + 1]);

@@ -233,6 +233,52 @@ def test_full_size_step_and_solve_match_live_reference(shape):
     e.close(); M.close(); qp.close()
 
 
+# ---- large stage blocks (BASELINE config 4 shape): global-workspace kernels ------
+@pytest.mark.parametrize("cfg", [(70, 20, 24, 1, 0, 1, 0), (96, 32, 20, 1, 1, 0, 5),
+                                 (200, 50, 16, 1, 0, 1, 0), (130, 7, 12, 0, 0, 1, 1)])
+def test_large_blocks_match_cpu_oracle(cfg):
+    """nx > 64: the stage blocks do not fit shared memory (hqpcu_create used to
+    refuse them); FormGxx / BKP path of hqp/Hqp_IpLQDOCP.C:1077-1111, 1854-1882."""
+    *pc, nseg = cfg
+    p = make_problem(*pc)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=41)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < TOL
+    V, R = e.get_factor()
+    assert relerr(V[0], o.Vxx()) < TOL and relerr(R[0], o.Rux()) < TOL
+    sx, sy, sz, sw, res, nsteps = e.solve(r1, r2, r3, r4)
+    assert res <= 1e-10
+    e.close(); o.close()
+
+
+@pytest.mark.skipif(not _ref_available(), reason="compiled reference (oracle/_ref) not present")
+def test_c4_truncated_horizon_matches_live_reference():
+    """BASELINE config 4 (nx=200 nu=50) on a K=100 truncation against the
+    UNMODIFIED Hqp_IpLQDOCP, parallel in time (nseg chosen automatically)."""
+    from oracle import refharness
+    p = synth_lqdocp(200, 50, 100)
+    z, w, r1, r2, r3, r4 = synth_rhs(p)
+    qp = refharness.RefQP(p)
+    M = refharness.RefMatrix("LQDOCP", qp)
+    M.factor(z, w)
+    ref = M.step(z, w, r1, r2, r3, r4)
+    e = IpCuda(p)
+    assert e.nseg > 1
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b, key in zip(mine, ref, ("dx", "dy", "dz", "dw")):
+        assert relerr(a, b) < TOL, key
+    e.close(); M.close(); qp.close()
+
+
 def test_c3_full_batch_sampled_instances_match_oracle():
     """config 3 at its full size: 4096 DIFFERENT instances nx=12 nu=4 K=50 in one
     batch; sampled instances against the port oracle."""
