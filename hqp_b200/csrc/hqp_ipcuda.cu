@@ -679,7 +679,10 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
                                   nn * sizeof(double)}) + (size_t)(nx + 16) * sizeof(double);
     d.gws_stride = pad2(need / sizeof(double) + 2);
     TRY(dev_alloc(h, &d.gws, (size_t)std::max(d.P, 1) * B * d.gws_stride));
-    h->smem_k1 = h->smem_k2 = h->smem_k3 = h->smem_cmp = h->smem_psi = 0;
+    // shared memory = the private GEMM staging slices of the warps (cta_mm_big)
+    h->smem_k1 = h->smem_k3 = (big_ldlt_fits(nu, 128) ? big_seg_smem_doubles(nu, 128)
+                                                      : (size_t)4 * LQ_BIG_STAGE) * sizeof(double);
+    h->smem_k2 = h->smem_cmp = h->smem_psi = (size_t)(LQ_NT2 / 32) * LQ_BIG_STAGE * sizeof(double);
     // (the chains read their matrices from global memory directly: no ring)
     h->smem_chain = h->smem_scan = pad2((size_t)3 * nx) * sizeof(double) + 2 * sizeof(uint64_t) + 16;
   }

@@ -441,13 +441,154 @@ __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, 
   }
 }
 
+// ---------------------------------------------------------------------------
+// Large-block product (stage blocks that live in global memory, nx > 64):
+//   C (M x N) = beta * C0 + alpha * A * B,  same strided operands as cta_mm.
+// The output is cut into 40 x 40 blocks (5 x 5 DMMA tiles), dealt round-robin to
+// the warps; every warp is an independent GEMM worker: it stages its own A and B
+// panels, LQ_BIG_KC deep, in a PRIVATE double-buffered shared-memory slice with
+// cp.async (LDGSTS; zero-filled outside the matrix), so the only synchronisation
+// inside the product is __syncwarp -- no CTA barrier, no idle warps while another
+// one waits for memory.  Per k-step of 4 a warp loads 5 + 5 fragments for 25
+// DMMAs.  Panels are stored [row][k] with stride LQ_BIG_KC + 4 = 4 (mod 8):
+// conflict-free fragment reads (see lq_pad4).
+// stg: LQ_BIG_STAGE doubles of shared memory per PHYSICAL warp of the CTA.
+// ---------------------------------------------------------------------------
+#define LQ_BIG_KC 16
+#define LQ_BIG_BT 5                                   // DMMA tiles per block side
+#define LQ_BIG_LDS (LQ_BIG_KC + 4)
+#define LQ_BIG_PANEL (LQ_BIG_BT * 8 * LQ_BIG_LDS)     // one panel: 40 rows x 20
+#define LQ_BIG_STAGE (4 * LQ_BIG_PANEL)               // A, B panels, two buffers
+
+// shared memory of the large-block segment kernels: the staging slices of the
+// warps, then the LDL^T factor of Guu and one right-hand-side column per thread
+__host__ __device__ inline size_t big_seg_smem_doubles(int nu, int nthr) {
+  return (size_t)(nthr / 32) * LQ_BIG_STAGE + (size_t)nu * (nu + 1) + (size_t)nu * nthr + 2;
+}
+__host__ __device__ inline bool big_ldlt_fits(int nu, int nthr) {
+  return big_seg_smem_doubles(nu, nthr) * sizeof(double) <= (size_t)227 * 1024;
+}
+
+__device__ __forceinline__ void cp_async_f64(double *dst_smem, const double *src, bool valid) {
+  const int sz = valid ? 8 : 0;  // src-size 0: the destination is zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+               "r"(sz)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// panel[r][k] <- X(r0 + r, k0 + k), r < 40, k < KC;  X(i, l) = X[i * xr + l * xc]
+__device__ __forceinline__ void big_stage_panel(double *panel, const double *X, int xr, int xc,
+                                                int r0, int nrows, int k0, int Kd, int lane) {
+  constexpr int R = LQ_BIG_BT * 8, KC = LQ_BIG_KC;
+  if (xr == 1) {
+    // rows contiguous in memory: consecutive lanes take consecutive rows
+#pragma unroll 4
+    for (int e = lane; e < R * KC; e += 32) {
+      const int k = e / R, r = e - k * R;
+      const bool ok = r0 + r < nrows && k0 + k < Kd;
+      cp_async_f64(panel + r * LQ_BIG_LDS + k, X + (ok ? (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : 0), ok);
+    }
+  } else {
+    // (k contiguous, or a general stride pair): consecutive lanes take consecutive k
+#pragma unroll 4
+    for (int e = lane; e < R * KC; e += 32) {
+      const int r = e / KC, k = e - r * KC;
+      const bool ok = r0 + r < nrows && k0 + k < Kd;
+      cp_async_f64(panel + r * LQ_BIG_LDS + k, X + (ok ? (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : 0), ok);
+    }
+  }
+}
+
+__device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, const double *C0,
+                                           int ldc0, double beta, double alpha, const double *A,
+                                           int ar, int ac, const double *B, int br, int bc, int M,
+                                           int N, int Kd, int wofs, int warp_log, int nwarps) {
+  constexpr int BT = LQ_BIG_BT, BS = BT * 8, KC = LQ_BIG_KC;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  double *my = stg + (size_t)(threadIdx.x >> 5) * LQ_BIG_STAGE;
+  const int nbi = (M + BS - 1) / BS, nbj = (N + BS - 1) / BS, nb = nbi * nbj;
+  const int nchunk = (Kd + KC - 1) / KC;
+  for (int u = (warp_log + nwarps - (wofs % nwarps)) % nwarps; u < nb; u += nwarps) {
+    const int bi = u / nbj, bj = u - bi * nbj;
+    const int i0 = bi * BS, j0 = bj * BS;
+    // tiles of this block that hold any row / column of the result
+    const int nti = min(BT, (M - i0 + 7) >> 3), ntj = min(BT, (N - j0 + 7) >> 3);
+    double acc[BT][BT][2];
+#pragma unroll
+    for (int r = 0; r < BT; r++)
+#pragma unroll
+      for (int c = 0; c < BT; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
+    // B(l, j) = B[l * br + j * bc]: as a panel over "rows" j with k = l
+    big_stage_panel(my, A, ar, ac, i0, M, 0, Kd, lane);
+    big_stage_panel(my + LQ_BIG_PANEL, B, bc, br, j0, N, 0, Kd, lane);
+    cp_async_commit();
+    for (int c = 0; c < nchunk; c++) {
+      double *pa = my + (size_t)(c & 1) * 2 * LQ_BIG_PANEL, *pb = pa + LQ_BIG_PANEL;
+      cp_async_wait_all();
+      __syncwarp();
+      if (c + 1 < nchunk) {  // next chunk into the other buffer while this one is consumed
+        double *na = my + (size_t)((c + 1) & 1) * 2 * LQ_BIG_PANEL;
+        big_stage_panel(na, A, ar, ac, i0, M, (c + 1) * KC, Kd, lane);
+        big_stage_panel(na + LQ_BIG_PANEL, B, bc, br, j0, N, (c + 1) * KC, Kd, lane);
+        cp_async_commit();
+      }
+#pragma unroll
+      for (int kk = 0; kk < KC; kk += 4) {
+        double af[BT], bf[BT];
+#pragma unroll
+        for (int r = 0; r < BT; r++) af[r] = pa[(r * 8 + g) * LQ_BIG_LDS + kk + t];
+#pragma unroll
+        for (int q = 0; q < BT; q++) bf[q] = pb[(q * 8 + g) * LQ_BIG_LDS + kk + t];
+#pragma unroll
+        for (int r = 0; r < BT; r++) {
+          if (r < nti) {
+#pragma unroll
+            for (int q = 0; q < BT; q++)
+              if (q < ntj) dmma_m8n8k4(acc[r][q][0], acc[r][q][1], af[r], bf[q]);
+          }
+        }
+      }
+      __syncwarp();  // every lane is done with this buffer before it is refilled
+    }
+#pragma unroll
+    for (int r = 0; r < BT; r++) {
+      const int ic = i0 + r * 8 + g;
+      if (r >= nti || ic >= M) continue;
+#pragma unroll
+      for (int q = 0; q < BT; q++) {
+        const int jc = j0 + q * 8 + 2 * t;
+        if (q >= ntj) continue;
+        double r0 = alpha * acc[r][q][0], r1 = alpha * acc[r][q][1];
+        if (jc < N) {
+          if (C0) r0 = fma(beta, C0[(size_t)ic * ldc0 + jc], r0);
+          C[(size_t)ic * ldc + jc] = r0;
+        }
+        if (jc + 1 < N) {
+          if (C0) r1 = fma(beta, C0[(size_t)ic * ldc0 + jc + 1], r1);
+          C[(size_t)ic * ldc + jc + 1] = r1;
+        }
+      }
+    }
+  }
+}
+
 // compile-time choice between the tensor-core and the FMA product
+// stg != nullptr (large blocks in global memory, generic kernels only): cta_mm_big.
 template <bool TC, int NW = LQ_NT / 32>
-__device__ __forceinline__ void cta_mmx(double *C, int ldc, const double *C0, int ldc0,
-                                        double beta, double alpha, const double *A, int ar,
-                                        int ac, const double *B, int br, int bc, int M, int N,
-                                        int Kd, int wofs = 0, int warp_id = -1,
+__device__ __forceinline__ void cta_mmx(double *stg, double *C, int ldc, const double *C0,
+                                        int ldc0, double beta, double alpha, const double *A,
+                                        int ar, int ac, const double *B, int br, int bc, int M,
+                                        int N, int Kd, int wofs = 0, int warp_id = -1,
                                         bool lower = false) {
+  if constexpr (!TC) {
+    if (stg) {
+      cta_mm_big(stg, C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs,
+                 warp_id >= 0 ? warp_id : (int)(threadIdx.x >> 5), warp_id >= 0 ? NW : (int)(blockDim.x >> 5));
+      return;
+    }
+  }
   if constexpr (TC) {
     cta_mm_tc<NW>(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, wofs, warp_id,
                   lower);
@@ -970,6 +1111,107 @@ __device__ __forceinline__ void cta_gauss_jordan(double *M, int ldm, int n, int 
     const int p = e / nr, j = e - p * nr;
     X[e] = M[piv_s[p] * ldm + n + j];
   }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// In-place inverse of the n x n block M (ldm; global memory, large blocks) by the
+// whole CTA: Gauss-Jordan with partial pivoting and explicit row interchanges, the
+// pivot row and the multiplier column staged in shared memory (scr: 2 n doubles),
+// one rank-1 update of the whole block per pivot (coalesced along the rows), the
+// column permutation undone at the end.  piv_s: n ints.  Barriers on entry and exit.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cta_gj_inverse_big(double *M, int ldm, int n, int *piv_s,
+                                                   double *scr, int *st_s) {
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  __shared__ double piv_inv;
+  double *rowp = scr, *colp = scr + n;
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  for (int p = 0; p < n; p++) {
+    // pivot search in column p, rows p .. n-1 (ties: smaller row)
+    double best = -1.0;
+    int bi = p;
+    for (int i = p + tid; i < n; i += nthr) {
+      const double a = fabs(M[(size_t)i * ldm + p]);
+      if (a > best) { best = a; bi = i; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      const int nw = (nthr + 31) >> 5;
+      for (int w2 = 1; w2 < nw; w2++)
+        if (red_v[w2] > best || (red_v[w2] == best && red_i[w2] < bi)) { best = red_v[w2]; bi = red_i[w2]; }
+      piv_s[p] = bi;
+      if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
+      piv_inv = 1.0 / M[(size_t)bi * ldm + p];
+    }
+    __syncthreads();
+    const int r = piv_s[p];
+    const double inv = piv_inv;
+    // interchange rows p and r; the pivot row is scaled and staged
+    for (int j = tid; j < n; j += nthr) {
+      const double a = M[(size_t)r * ldm + j];
+      if (r != p) M[(size_t)r * ldm + j] = M[(size_t)p * ldm + j];
+      const double v = (j == p) ? inv : a * inv;
+      M[(size_t)p * ldm + j] = v;
+      rowp[j] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) colp[i] = (i == p) ? 0.0 : M[(size_t)i * ldm + p];
+    __syncthreads();
+    // rank-1 update of every other row; column p receives -f / pivot.  A thread
+    // owns a column (coalesced along the rows, no index arithmetic) and keeps 16
+    // independent loads in flight: the block lives in L2, not in shared memory
+    for (int j = tid; j < n; j += nthr) {
+      const double rj = rowp[j];
+      const bool isp = j == p;
+      double *col = M + j;
+#pragma unroll 1
+      for (int i0 = 0; i0 < n; i0 += 16) {
+        double cur[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const int i = i0 + q;
+          cur[q] = (i < n && !isp) ? col[(size_t)i * ldm] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const int i = i0 + q;
+          if (i < n && i != p) col[(size_t)i * ldm] = fma(-colp[i], rj, cur[q]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // (P A)^{-1} = A^{-1} P': undo the interchanges on the columns, last first
+  for (int p = n - 1; p >= 0; p--) {
+    const int r = piv_s[p];
+    if (r == p) continue;  // (uniform)
+    for (int i = tid; i < n; i += nthr) {
+      const double a = M[(size_t)i * ldm + p];
+      M[(size_t)i * ldm + p] = M[(size_t)i * ldm + r];
+      M[(size_t)i * ldm + r] = a;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+}
+
+// X = M0^{-1} R for the augmented M = [M0 | R] (n x nc, ldm), large blocks: M0 is
+// inverted in place, then applied to R on the tensor cores (cta_mm_big).
+__device__ __forceinline__ void cta_inverse_apply_big(double *stg, double *M, int ldm, int n,
+                                                      int nc, double *X, int ldx, int *piv_s,
+                                                      int *st_s) {
+  cta_gj_inverse_big(M, ldm, n, piv_s, stg, st_s);
+  cta_mm_big(stg, X, ldx, nullptr, 0, 0.0, 1.0, M, ldm, 1, M + n, ldm, 1, n, nc - n, n, 0,
+             (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5));
   __syncthreads();
 }
 

@@ -219,34 +219,92 @@ struct NoIdle {
   __device__ __forceinline__ void operator()(int, int) const {}
 };
 template <int NU, bool TC, int NW, class Idle = NoIdle>
-__device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, int LU, bool zero_V,
-                                              double *V, const double *fx, const double *fu,
-                                              double *G, double *T, double *Rux, double *Phi,
-                                              int *st_s, const ElemAcc *el, Idle idle = Idle()) {
+__device__ __forceinline__ void riccati_stage(double *stg, int nx, int nu, int LV, int LT, int LU,
+                                              bool zero_V, double *V, const double *fx,
+                                              const double *fu, double *G, double *T, double *Rux,
+                                              double *Phi, int *st_s, const ElemAcc *el,
+                                              Idle idle = Idle()) {
   const int nm = nx + nu;
   const int tid = threadIdx.x, nthr = blockDim.x;
   LQ_STAMP2(1);
   if (!zero_V) {
     // T = V [fx fu]   (V symmetric: read as V')
-    cta_mmx<TC, NW>(T, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fx, nx, 1, nx, nx, nx);
-    cta_mmx<TC, NW>(T + nx, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fu, LU, 1, nx, nu, nx, 3);
+    cta_mmx<TC, NW>(stg, T, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fx, nx, 1, nx, nx, nx);
+    cta_mmx<TC, NW>(stg, T + nx, LT, nullptr, 0, 0.0, 1.0, V, 1, LV, fu, LU, 1, nx, nu, nx, 3);
   }
   if (el)  // Wt = fu' At  (W = A fu)
-    cta_mmx<TC, NW>(el->Wt, LV, nullptr, 0, 0.0, 1.0, fu, 1, LU, el->At, LV, 1, nu, nx, nx, 2);
+    cta_mmx<TC, NW>(stg, el->Wt, LV, nullptr, 0, 0.0, 1.0, fu, 1, LU, el->At, LV, 1, nu, nx, nx, 2);
   if (!zero_V || el) __syncthreads();
   LQ_STAMP2(2);
   if (!zero_V) {
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
     // (Gxx and V are symmetric: tiles on and below the diagonal only, mirrored later)
-    cta_mmx<TC, NW>(G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx, 0, -1, TC);
-    cta_mmx<TC, NW>(G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
-    cta_mmx<TC, NW>(G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
+    cta_mmx<TC, NW>(stg, G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx, 0, -1, TC);
+    cta_mmx<TC, NW>(stg, G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
+    cta_mmx<TC, NW>(stg, G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
                 nu, nu, nx, 3);
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
   LQ_STAMP2(3);
-  if (el) {
+  // Large blocks: G lives in global memory, where a dependent substitution step
+  // costs an L2 round trip.  The factor of Guu and one right-hand-side column per
+  // thread are kept in the shared-memory area `lds` (nu (nu+1) + nu * nthr doubles
+  // behind the GEMM staging slices; NULL when it does not fit: the slow path).
+  double *lds = nullptr, *ybuf = nullptr;
+  if constexpr (!TC) {
+    if (stg && big_ldlt_fits(nu, nthr)) {
+      lds = stg + (size_t)(nthr >> 5) * LQ_BIG_STAGE;
+      ybuf = lds + nu * (nu + 1);
+    }
+  }
+  const int ldl = nu + 1;
+  auto big_ldlt = [&]() -> int {  // warp 0
+    const int lane = tid & 31;
+    for (int e = lane; e < nu * nu; e += 32) {
+      const int i = e / nu, j = e - i * nu;
+      if (j <= i) lds[i * ldl + j] = Guu[i * nm + j];
+    }
+    __syncwarp();
+    const int st = warp_ldlt(lds, ldl, nu);
+    for (int e = lane; e < nu * nu; e += 32) {
+      const int i = e / nu, j = e - i * nu;
+      if (j <= i) Guu[i * nm + j] = lds[i * ldl + j];
+    }
+    __syncwarp();
+    return st;
+  };
+  // dst(:, j) = Guu^{-1} src(:, j); thread t of nt works on columns t, t + nt, ...
+  auto big_solve = [&](const double *src, int sld, double *dst, int dld, int ncols, int t, int nt) {
+    double *y = ybuf + t;
+    for (int j = t; j < ncols; j += nt) {
+      for (int i = 0; i < nu; i++) y[i * nthr] = src[(size_t)i * sld + j];
+      thread_ldlt_solve(lds, ldl, nu, y, nthr);
+      for (int i = 0; i < nu; i++) dst[(size_t)i * dld + j] = y[i * nthr];
+    }
+  };
+  if (lds && el) {
+    if (warp_id_uniform() == 0) {
+      const int st = big_ldlt();
+      if (st && tid == 0) atomicOr(st_s, st);
+    }
+    __syncthreads();
+    big_solve(G + nx * nm, nm, Rux, LV, nx, tid, nthr);
+    big_solve(el->Wt, LV, el->Yt, LV, nx, tid, nthr);
+  } else if (lds) {
+    const int wu = warp_id_uniform();
+    if (wu == 0) {
+      const int st = big_ldlt();
+      if (st && tid == 0) atomicOr(st_s, st);
+      big_solve(G + nx * nm, nm, Rux, LV, nx, tid, 32);
+      if (NW == 1) {
+        __syncwarp();
+        idle(0, 1);
+      }
+    } else {
+      idle(wu - 1, NW - 1);
+    }
+  } else if (el) {
     // K1: LDL' by warp 0, then the 2 nx triangular solves spread over the CTA
     if (warp_id_uniform() == 0) {  // uniform branch: no WARPSYNC around the shuffles inside
       const int st = warp_ldlt_any<NU>(Guu, nm, nu);
@@ -290,10 +348,10 @@ __device__ __forceinline__ void riccati_stage(int nx, int nu, int LV, int LT, in
   __syncthreads();
   LQ_STAMP2(5);
   // V = Gxx - Gux' Rux ; Phi = fx - fu Rux ; K1: Cg += Y W' = Yt' Wt
-  cta_mmx<TC, NW>(V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu, 0, -1, TC);
-  cta_mmx<TC, NW>(Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
+  cta_mmx<TC, NW>(stg, V, LV, G, nm, 1.0, -1.0, G + nx * nm, 1, nm, Rux, LV, 1, nx, nx, nu, 0, -1, TC);
+  cta_mmx<TC, NW>(stg, Phi, LV, fx, nx, 1.0, -1.0, fu, LU, 1, Rux, LV, 1, nx, nx, nu);
   if (el)
-    cta_mmx<TC, NW>(el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu, 2,
+    cta_mmx<TC, NW>(stg, el->Cg, LV, el->Cg, LV, 1.0, 1.0, el->Yt, 1, LV, el->Wt, LV, 1, nx, nx, nu, 2,
                     -1, TC);
   __syncthreads();
 }
@@ -315,6 +373,8 @@ seg_element_kernel(LqDev d) {
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
   SmemCarver sm(cta_workspace(d, smem_raw));
+  // large blocks: shared memory is the GEMM staging area (cta_mm_big)
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   StagePipe sp;
   __shared__ __align__(8) uint64_t pipe_bars[2];
   stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
@@ -345,11 +405,11 @@ seg_element_kernel(LqDev d) {
     }
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
     ElemAcc el{At, Wt, Yt, Cg};
-    riccati_stage<NU, TC, NW>(nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
+    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
                           sp.G(buf), T, Rux, Phi, &st_s, &el);
     // J symmetrised ; A <- A Phi, i.e. At <- Phi' At
     if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx, true); else cta_symmetrize(J, LV, nx);
-    cta_mmx<TC, NW>(Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
+    cta_mmx<TC, NW>(stg, Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
     double *t = At; At = Atn; Atn = t;
     __syncthreads();
   }
@@ -382,6 +442,8 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
   SmemCarver sm(cta_workspace(d, smem_raw));
+  // large blocks: shared memory is the GEMM staging area (cta_mm_big)
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   const int ldx = NX > 0 ? 2 * nx + 4 : 2 * nx;  // = 4 (mod 8): conflict-free fragment reads
   double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
   double *Ai = sm.take(n2), *Ji = sm.take(n2);
@@ -419,23 +481,25 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
     }
     __syncthreads();
     LQ_STAMP(2);
-    cta_mmx<TC, NWC>(M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+    cta_mmx<TC, NWC>(stg, M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
     __syncthreads();
     LQ_STAMP(3);
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
     if constexpr (NX > 0)
       cta_inverse_apply<NX, NWC>(M, ldm, n3, X, inv_scr, piv_s, &st_s, ldx);
+    else if (stg)
+      cta_inverse_apply_big(stg, M, ldm, nx, n3, X, ldx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
     // T1 = A_j X_C ; T2 = J_j X_A ; T3 = A_j X_A (the new A)
-    cta_mmx<TC, NWC>(T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, ldx, 1, nx, nx, nx);
-    cta_mmx<TC, NWC>(T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, ldx, 1, nx, nx, nx, 4);
-    cta_mmx<TC, NWC>(T3, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, ldx, 1, nx, nx, nx, 2);
+    cta_mmx<TC, NWC>(stg, T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, ldx, 1, nx, nx, nx);
+    cta_mmx<TC, NWC>(stg, T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, ldx, 1, nx, nx, nx, 4);
+    cta_mmx<TC, NWC>(stg, T3, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, ldx, 1, nx, nx, nx, 2);
     __syncthreads();
     // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
-    cta_mmx<TC, NWC>(Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
-    cta_mmx<TC, NWC>(Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx, 4);
+    cta_mmx<TC, NWC>(stg, Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+    cta_mmx<TC, NWC>(stg, Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx, 4);
     __syncthreads();
     if constexpr (TC) {
       cta_symmetrize_tc<NWC>(Cj, nx, nx);
@@ -477,6 +541,8 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
   const int g = blockIdx.x, b = blockIdx.y;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
   SmemCarver sm(cta_workspace(d, smem_raw));
+  // large blocks: shared memory is the GEMM staging area (cta_mm_big)
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm);
   double *X = sm.take(n2);
@@ -534,16 +600,18 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
     }
     __syncthreads();
     // M = [I + S C | S A]
-    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
     if constexpr (NX > 0)
       cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
+    else if (stg)
+      cta_inverse_apply_big(stg, M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised
-    cta_mmx<TC, LQ_NT2 / 32>(S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     if constexpr (TC) cta_symmetrize_tc<LQ_NT2 / 32>(S, nx, nx); else cta_symmetrize(S, nx, nx);
     __syncthreads();
@@ -565,6 +633,8 @@ seg_riccati_kernel(LqDev d) {
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
   SmemCarver sm(cta_workspace(d, smem_raw));
+  // large blocks: shared memory is the GEMM staging area (cta_mm_big)
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   StagePipe sp;
   __shared__ __align__(8) uint64_t pipe_bars[2];
   stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
@@ -603,9 +673,9 @@ seg_riccati_kernel(LqDev d) {
     // needed when the segment is the whole horizon)
     if (need_psi) {
       if (nw == NW)
-        cta_mmx<TC, NW>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx, nx, nx);
+        cta_mmx<TC, NW>(stg, Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1, nx, nx, nx);
       else
-        cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1,
+        cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(stg, Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1,
                                           nx, nx, nx, 0, w);
     }
     for (int i = t0; i < nu * nx; i += nt) {
@@ -639,7 +709,7 @@ seg_riccati_kernel(LqDev d) {
     const bool have_prev = it > 0;
     const double *Rp = Rprev, *Ptc = Pt;
     double *Ptd = Ptn;
-    riccati_stage<NU, TC, NW>(nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T,
+    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T,
                               Rux, Phi, &st_s, nullptr, [&](int w, int nw) {
                                 if (have_prev) flush(k + 1, Rp, Ptc, Ptd, w, nw);
                               });
@@ -683,6 +753,7 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
   double *bufA = reinterpret_cast<double *>(cta_workspace(d, smem_raw));  // chunk blocks
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *bufB = bufA + (size_t)chunk * n2;             // ceil(chunk/2) blocks
   const size_t base = ((size_t)b * d.st.nel + d.st.off[lev]) * n2;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -737,8 +808,9 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
         }
       } else {
         for (int pr = 0; pr < half; pr++)
-          cta_mm(dst + (size_t)pr * n2, nx, nullptr, 0, 0.0, 1.0, src + (size_t)(2 * pr + 1) * n2,
-                 nx, 1, src + (size_t)(2 * pr) * n2, nx, 1, nx, nx, nx);
+          cta_mmx<false, LQ_NT2 / 32>(stg, dst + (size_t)pr * n2, nx, nullptr, 0, 0.0, 1.0,
+                                      src + (size_t)(2 * pr + 1) * n2, nx, 1,
+                                      src + (size_t)(2 * pr) * n2, nx, 1, nx, nx, nx);
       }
       if (odd)
         for (int i = threadIdx.x; i < n2; i += blockDim.x)

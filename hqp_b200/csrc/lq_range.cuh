@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
   SmemCarver sm(cta_workspace(d, smem_raw));
+  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm), *X = sm.take(n2);
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
@@ -67,15 +68,17 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
       Cg[i] = E[n2 + i];
     }
     __syncthreads();
-    cta_mmx<TC, LQ_NT2 / 32>(M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
-    cta_mmx<TC, LQ_NT2 / 32>(M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, M, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, Cg, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, M + nx, ldm, nullptr, 0, 0.0, 1.0, S, nx, 1, A, nx, 1, nx, nx, nx);
     __syncthreads();
     for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
     if constexpr (NX > 0)
       cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
+    else if (stg)
+      cta_inverse_apply_big(stg, M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
-    cta_mmx<TC, LQ_NT2 / 32>(S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
+    cta_mmx<TC, LQ_NT2 / 32>(stg, S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
     cta_symmetrize(S, nx, nx);
     __syncthreads();
