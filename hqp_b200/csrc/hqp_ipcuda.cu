@@ -129,6 +129,7 @@ struct hqpcu_handle {
   struct GraphEntry { std::vector<const void *> key; cudaGraphExec_t exec; long long launches; };
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
+  bool use_hs = true;    // factor tree as a one-sweep suffix scan (HQPCU_HS=0: up/down tree)
   // programmatic dependent launch inside the hot sequences: measured SLOWER at C2
   // (0.845 vs 0.794 ms per unit: early-scheduled dependents hold SM resources), so
   // off unless HQPCU_PDL=1
@@ -355,6 +356,8 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   }
   choose_seg_warps(h);
   build_tree(d.ft, P, 2);
+  d.ft.nel = std::max(d.ft.nel, 2 * P + 2);  // (two ping-pong regions of P+1 slots for the suffix scan)
+  d.hs = (h->use_hs && P > 1 && !h->ranged()) ? 1 : 0;
   // solve hierarchy: up (R steps) + top (P/R) + down (R) sequential chain steps,
   // shortest for R ~ sqrt(P) (measured at P = 435: R = 21 beats 32 by 5 % per step)
   int R = (int)std::ceil(std::sqrt((double)P));
@@ -441,6 +444,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     if (sw) h->seg_warps_req = atoi(sw) == 1 ? 1 : (atoi(sw) == 8 ? 8 : 4);
     const char *pe = getenv("HQPCU_PDL");
     h->use_pdl = pe && pe[0] == '1';
+    const char *hs = getenv("HQPCU_HS");
+    h->use_hs = !(hs && hs[0] == '0');
     const char *env = getenv("HQPCU_GRAPHS");  // "0": plain launches (debugging, ncu per-kernel lists)
     h->use_graphs = !(env && env[0] == '0');
     if (h->use_graphs &&
@@ -709,6 +714,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(set_smem((const void *)elem_scan_kernel<NX_>, h->smem_k2));             \
   TRY(set_smem((const void *)range_scan_factor_kernel<NX_>, h->smem_k2));     \
   TRY(set_smem((const void *)elem_compose_kernel<NX_>, h->smem_cmp));         \
+  TRY(set_smem((const void *)elem_hs_kernel<NX_>, h->smem_cmp));              \
   TRY(set_smem((const void *)psi_compose_kernel<NX_>, h->smem_psi));
   LQ_DISPATCH_NXNU(nx, nu, SET_A);
   LQ_DISPATCH_NX(nx, nu, SET_B);
@@ -977,6 +983,7 @@ static int launch_eq_factor(hqpcu_handle *h) {
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k3, s, d);        \
   } while (0)
 #define L_CMP(NX_) LAUNCHP(h, elem_compose_kernel<NX_>, gl, LQ_NT2, h->smem_cmp, s, d, l)
+#define L_HS(NX_) LAUNCHP(h, elem_hs_kernel<NX_>, gseg, LQ_NT2, h->smem_cmp, s, d, stride, src, dst, last)
 #define L_TOP(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, dim3(1, d.batch), LQ_NT2, h->smem_k2, s, d, h->ftop(), 1)
 #define L_DWN(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, gl, LQ_NT2, h->smem_k2, s, d, l, 0)
 #define L_PSI(NX_) LAUNCHP(h, psi_compose_kernel<NX_>, gl, LQ_NT2, h->smem_psi, s, d, l, h->psi_chunk)
@@ -994,9 +1001,20 @@ static int launch_factor_up(hqpcu_handle *h) {
   }
   if (d.P > 1 || h->ranged()) {
     LQ_DISPATCH_NXNU(d.nx, d.nu, L_K1);
-    for (int l = 0; l < h->ftop(); l++) {
-      const dim3 gl(d.ft.cnt[l + 1], d.batch);
-      LQ_DISPATCH_NX(d.nx, d.nu, L_CMP);
+    if (d.hs) {
+      // one sweep: ceil(log2 (P+1)) levels of P concurrent combines (elem_hs_kernel)
+      LAUNCHP(h, elem_terminal_kernel, d.batch, 128, 0, s, d);
+      int lev = 0;
+      for (int stride = 1; stride <= d.P; stride <<= 1, lev++) {
+        const int src = (lev & 1) * (d.P + 1), dst = ((lev + 1) & 1) * (d.P + 1);
+        const int last = (stride << 1) > d.P ? 1 : 0;
+        LQ_DISPATCH_NX(d.nx, d.nu, L_HS);
+      }
+    } else {
+      for (int l = 0; l < h->ftop(); l++) {
+        const dim3 gl(d.ft.cnt[l + 1], d.batch);
+        LQ_DISPATCH_NX(d.nx, d.nu, L_CMP);
+      }
     }
   }
   CUL(h);
@@ -1008,10 +1026,12 @@ static int launch_factor_down(hqpcu_handle *h) {
   const LqDev &d = h->d;
   cudaStream_t s = h->stream;
   const dim3 gseg(d.P, d.batch);
-  LQ_DISPATCH_NX(d.nx, d.nu, L_TOP);
-  for (int l = h->ftop() - 1; l >= 0; l--) {
-    const dim3 gl(d.ft.cnt[l + 1], d.batch);
-    LQ_DISPATCH_NX(d.nx, d.nu, L_DWN);
+  if (!d.hs) {  // (suffix-scan mode: every segment's end value is known already)
+    LQ_DISPATCH_NX(d.nx, d.nu, L_TOP);
+    for (int l = h->ftop() - 1; l >= 0; l--) {
+      const dim3 gl(d.ft.cnt[l + 1], d.batch);
+      LQ_DISPATCH_NX(d.nx, d.nu, L_DWN);
+    }
   }
   LQ_DISPATCH_NXNU(d.nx, d.nu, L_K3);
   for (int l = 0; l < h->stop(); l++) {
@@ -1027,6 +1047,7 @@ static int launch_factor_down(hqpcu_handle *h) {
 #undef L_K1
 #undef L_K3
 #undef L_CMP
+#undef L_HS
 #undef L_TOP
 #undef L_DWN
 #undef L_PSI
@@ -1462,6 +1483,7 @@ int hqpcu_range_config(hqpcu_handle *h, int has_prev, int has_next) {
   drop_graphs(h);  // the launch sequences depend on the range flags
   h->d.has_prev = has_prev ? 1 : 0;
   h->d.has_next = has_next ? 1 : 0;
+  h->d.hs = (h->use_hs && h->d.P > 1 && !h->ranged()) ? 1 : 0;
   h->factored = false;
   return HQPCU_OK;
 }

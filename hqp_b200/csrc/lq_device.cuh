@@ -35,6 +35,8 @@ struct LqDev {
   int use_tma;        // per-stage slabs are 16-byte multiples: bulk-copy path
   // horizon split across ranks (lq_range.cuh): this handle owns a contiguous
   // stage range of a longer horizon
+  int hs;             // factor tree as a one-sweep suffix scan (elem_hs_kernel): the last
+                      // segment carries the terminal value, log2(P) levels of P combines
   int spw;            // stages per warp of the stage-parallel solve passes
   int lgw;            // lanes per stage there (32, or 16: two stages side by side)
   int has_prev;       // a rank before this one supplies the state at stage 0

@@ -372,9 +372,9 @@ seg_element_kernel(LqDev d) {
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
-  SmemCarver sm(cta_workspace(d, smem_raw));
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
   // large blocks: shared memory is the GEMM staging area (cta_mm_big)
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   StagePipe sp;
   __shared__ __align__(8) uint64_t pipe_bars[2];
   stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
@@ -441,9 +441,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   const int ldm = NX > 0 ? n3 + 1 : n3;  // odd row stride for the warp inverse
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.ft.R, c1 = min(d.ft.cnt[lev], c0 + d.ft.R);
-  SmemCarver sm(cta_workspace(d, smem_raw));
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
   // large blocks: shared memory is the GEMM staging area (cta_mm_big)
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   const int ldx = NX > 0 ? 2 * nx + 4 : 2 * nx;  // = 4 (mod 8): conflict-free fragment reads
   double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
   double *Ai = sm.take(n2), *Ji = sm.take(n2);
@@ -522,6 +522,144 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
   LQ_STAMP(6);
 }
 
+// The virtual terminal element of the suffix scan, in slot P of both regions:
+// J = Vxx[K] = Q_K + C_K'(z/w)C_K (hqp/Hqp_IpLQDOCP.C:1800-1804), A = C = 0; also the
+// end value of the last segment for K3.  grid (batch), any block size.
+__global__ void elem_terminal_kernel(LqDev d) {
+  pdl_enter();
+  const int nx = d.nx, nm = d.nm, n2 = nx * nx, b = blockIdx.x;
+  const size_t eb = (size_t)b * d.ft.nel;
+  double *J0 = d.segJ + (eb + d.P) * n2, *J1 = d.segJ + (eb + 2 * d.P + 1) * n2;
+  const double *QK = d.Q + ((size_t)b * (d.K + 1) + d.K) * nm * nm;
+  const double *hk = d.hdiag + (size_t)b * d.N + (size_t)d.K * nm;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const int r = i / nx, c = i - r * nx;
+    J0[i] = QK[r * nm + c] + (r == c ? hk[r] : 0.0);
+    d.segA[(eb + d.P) * n2 + i] = 0.0;
+    d.segC[(eb + d.P) * n2 + i] = 0.0;
+    d.segA[(eb + 2 * d.P + 1) * n2 + i] = 0.0;
+    d.segC[(eb + 2 * d.P + 1) * n2 + i] = 0.0;
+  }
+  const double *cv = d.cval + (size_t)b * d.nnz;
+  for (int rr = d.grow_ptr[d.K]; rr < d.grow_ptr[d.K + 1]; rr++) {
+    __syncthreads();
+    const int r = d.grow[rr];
+    const int e0 = d.ineq_ptr[r], ne = d.ineq_ptr[r + 1] - e0;
+    const double wz = d.z[(size_t)b * d.m + r] / d.w[(size_t)b * d.m + r];
+    for (int e = threadIdx.x; e < ne * ne; e += blockDim.x) {
+      const int ea = e / ne, ebb = e - ea * ne;
+      J0[d.ineq_lcol[e0 + ea] * nx + d.ineq_lcol[e0 + ebb]] += wz * cv[e0 + ea] * cv[e0 + ebb];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const double v = J0[i];
+    J1[i] = v;
+    d.segVb[(eb + d.P - 1) * n2 + i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2 as ONE sweep (suffix scan over the segment elements).  The terminal value
+// Vxx[K] is a virtual element P = (A 0, C 0, J Vxx[K]) (elem_terminal_kernel);
+// level l replaces element s by the composition of s and s + 2^l (beyond the end:
+// unchanged).  Composing with a "complete" element (A = C = 0) is exactly the
+// Riccati map of element s applied to that value, so after ceil(log2 (P+1)) levels
+// the J of element s is the value Hessian at the START of segment s, i.e. the end
+// value of segment s-1 -- every segment boundary with log2 P dependent combines
+// instead of the 2 log2 P of the up- and down-sweep of a binary tree.  All P
+// combines of a level run concurrently (one wave); the extra arithmetic is free,
+// the machine idles during the tree anyway.
+// Elements ping-pong between two regions of P+1 slots (src, dst: slot offsets).
+// last != 0: also segVb[s-1] <- J.     grid (P, batch)
+// ---------------------------------------------------------------------------
+template <int NX>
+__global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, int src, int dst,
+                                                      int last) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
+  constexpr bool TC = LQ_USE_DMMA && NX > 0;
+  const int ldm = NX > 0 ? n3 + 1 : n3;  // odd row stride for the warp inverse
+  const int s = blockIdx.x, b = blockIdx.y;
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  const int ldx = NX > 0 ? 2 * nx + 4 : 2 * nx;
+  double *Aj = sm.take(n2), *Cj = sm.take(n2), *Jj = sm.take(n2);
+  double *Ai = sm.take(n2), *Ji = sm.take(n2);
+  double *M = sm.take(nx * ldm), *T1 = sm.take(n2), *T2 = sm.take(n2), *T3 = sm.take(n2);
+  double *X = sm.take(nx * ldx);  // [X_A | X_C]
+  double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;
+  __shared__ int st_s, piv_small[65];
+  __shared__ double inv_s[2];
+  int *piv_s = nx <= 64 ? piv_small : reinterpret_cast<int *>(sm.take((nx + 2) / 2));
+  constexpr int NWC = LQ_NT2 / 32;
+  if (threadIdx.x == 0) st_s = 0;
+  const size_t eb = (size_t)b * d.ft.nel;
+  const size_t oi = (eb + src + s) * n2, oo = (eb + dst + s) * n2;
+  const int j = s + stride;
+  if (j > d.P) {
+    // already the composition up to the end of the horizon
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      const double jv = d.segJ[oi + i];
+      d.segA[oo + i] = d.segA[oi + i];
+      d.segC[oo + i] = d.segC[oi + i];
+      d.segJ[oo + i] = jv;
+      if (last && s > 0) d.segVb[(eb + s - 1) * n2 + i] = jv;
+    }
+    return;
+  }
+  const size_t oj = (eb + src + j) * n2;
+  // M = [I + C_i J_j | A_i | C_i]
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const int r = i / nx, cc = i - r * nx;
+    Aj[i] = d.segA[oj + i];
+    Cj[i] = d.segC[oj + i];
+    Jj[i] = d.segJ[oj + i];
+    const double ai = d.segA[oi + i], ci = d.segC[oi + i];
+    Ai[i] = ai;
+    Ji[i] = d.segJ[oi + i];
+    M[r * ldm + nx + cc] = ai;
+    M[r * ldm + 2 * nx + cc] = ci;
+    T1[i] = ci;
+  }
+  __syncthreads();
+  cta_mmx<TC, NWC>(stg, M, ldm, nullptr, 0, 0.0, 1.0, T1, nx, 1, Jj, nx, 1, nx, nx, nx);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nx; i += blockDim.x) M[i * ldm + i] += 1.0;
+  if constexpr (NX > 0)
+    cta_inverse_apply<NX, NWC>(M, ldm, n3, X, inv_scr, piv_s, &st_s, ldx);
+  else if (stg)
+    cta_inverse_apply_big(stg, M, ldm, nx, n3, X, ldx, piv_s, &st_s);
+  else
+    cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
+  // T1 = A_j X_C ; T2 = J_j X_A ; T3 = A_j X_A (the new A)
+  cta_mmx<TC, NWC>(stg, T1, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X + nx, ldx, 1, nx, nx, nx);
+  cta_mmx<TC, NWC>(stg, T2, nx, nullptr, 0, 0.0, 1.0, Jj, nx, 1, X, ldx, 1, nx, nx, nx, 4);
+  cta_mmx<TC, NWC>(stg, T3, nx, nullptr, 0, 0.0, 1.0, Aj, nx, 1, X, ldx, 1, nx, nx, nx, 2);
+  __syncthreads();
+  // C = T1 A_j' + C_j ; J = A_i' T2 + J_i
+  cta_mmx<TC, NWC>(stg, Cj, nx, Cj, nx, 1.0, 1.0, T1, nx, 1, Aj, 1, nx, nx, nx, nx);
+  cta_mmx<TC, NWC>(stg, Jj, nx, Ji, nx, 1.0, 1.0, Ai, 1, nx, T2, nx, 1, nx, nx, nx, 4);
+  __syncthreads();
+  if constexpr (TC) {
+    cta_symmetrize_tc<NWC>(Cj, nx, nx);
+    cta_symmetrize_tc<NWC>(Jj, nx, nx);
+  } else {
+    cta_symmetrize(Cj, nx, nx);
+    cta_symmetrize(Jj, nx, nx);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    const double jv = Jj[i];
+    d.segA[oo + i] = T3[i];
+    d.segC[oo + i] = Cj[i];
+    d.segJ[oo + i] = jv;
+    if (last && s > 0) d.segVb[(eb + s - 1) * n2 + i] = jv;
+  }
+  if (threadIdx.x == 0 && st_s) atomicOr(d.status, st_s);
+}
+
 // ---------------------------------------------------------------------------
 // K2b: back-substitution of the value Hessian through the elements.
 //   top = 1: level `lev` is the top level; one CTA per instance starts from the
@@ -540,9 +678,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
-  SmemCarver sm(cta_workspace(d, smem_raw));
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
   // large blocks: shared memory is the GEMM staging area (cta_mm_big)
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm);
   double *X = sm.take(n2);
@@ -632,9 +770,9 @@ seg_riccati_kernel(LqDev d) {
   const int s = blockIdx.x, b = blockIdx.y;
   const int ka = s * d.L, kb = min(d.K, ka + d.L);
   const int LV = TC ? lq_pad4(nx) : nx, LT = TC ? lq_pad4(nm) : nm, LU = TC ? lq_pad4(nu) : nu;
-  SmemCarver sm(cta_workspace(d, smem_raw));
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
   // large blocks: shared memory is the GEMM staging area (cta_mm_big)
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   StagePipe sp;
   __shared__ __align__(8) uint64_t pipe_bars[2];
   stage_pipe_init(nx, nu, sm, sp, pipe_bars, d.use_tma);
@@ -752,8 +890,8 @@ __global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, i
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int g = blockIdx.x, b = blockIdx.y;
   const int c0 = g * d.st.R, c1 = min(d.st.cnt[lev], c0 + d.st.R);
-  double *bufA = reinterpret_cast<double *>(cta_workspace(d, smem_raw));  // chunk blocks
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  double *bufA = reinterpret_cast<double *>(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // chunk blocks
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *bufB = bufA + (size_t)chunk * n2;             // ceil(chunk/2) blocks
   const size_t base = ((size_t)b * d.st.nel + d.st.off[lev]) * n2;
   const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;

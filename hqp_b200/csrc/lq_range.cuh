@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, cons
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
   constexpr bool TC = LQ_USE_DMMA && NX > 0;
   const int ldm = NX > 0 ? 2 * nx + 1 : 2 * nx;  // odd row stride for the warp inverse
-  SmemCarver sm(cta_workspace(d, smem_raw));
-  double *const stg = d.gws ? reinterpret_cast<double *>(smem_raw) : nullptr;
+  SmemCarver sm(NX > 0 ? smem_raw : cta_workspace(d, smem_raw));  // (compiled sizes: provably shared memory)
+  double *const stg = (NX == 0 && d.gws) ? reinterpret_cast<double *>(smem_raw) : nullptr;
   double *S = sm.take(n2), *A = sm.take(n2), *Cg = sm.take(n2);
   double *M = sm.take(nx * ldm), *X = sm.take(n2);
   double *inv_scr = NX > 0 ? sm.take(nx * (nx + 1) + 2 * (nx + 2)) : nullptr;

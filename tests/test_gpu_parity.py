@@ -344,7 +344,7 @@ def test_equality_rows_match_dense_kkt():
 
 @pytest.mark.parametrize("env", [{"HQPCU_SEG_WARPS": "1"}, {"HQPCU_GRAPHS": "0"},
                                  {"HQPCU_PDL": "1"}, {"HQPCU_CHAIN_CHUNK": "7"},
-                                 {"HQPCU_LANE_GROUP": "16"}, {"HQPCU_SPW": "2"}])
+                                 {"HQPCU_LANE_GROUP": "16"}, {"HQPCU_SPW": "2"}, {"HQPCU_HS": "0"}])
 @pytest.mark.parametrize("cfg", [(20, 10, 131, 1, 0, 1, 9), (12, 4, 50, 1, 2, 0, 1),
                                  (40, 10, 64, 1, 0, 1, 4)])
 def test_launch_variants_match_cpu_oracle(cfg, env, monkeypatch):
