@@ -1661,3 +1661,4 @@ int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {
 }  // extern "C"
 
 #include "hqp_ips_host.inc"
+#include "hqp_franke_host.inc"

@@ -501,3 +501,53 @@ __global__ void ips_absmax_kernel(size_t n, const double *__restrict__ x, double
   a = block_reduce(a, true, red);
   if (threadIdx.x == 0) partial[blockIdx.x] = a;
 }
+
+// ---- Franke (hqp/Hqp_IpsFranke.C) ---------------------------------------------------
+// right-hand sides of one iteration (:293-299): r_i = -zeta a_i, r4 = z w - mu
+__global__ void ips_franke_rhs_kernel(int N, int me, int m, double zeta, double mu,
+                                      const double *__restrict__ a1, const double *__restrict__ a2,
+                                      const double *__restrict__ a3, const double *__restrict__ z,
+                                      const double *__restrict__ w, double *r1, double *r2,
+                                      double *r3, double *r4) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = t0; i < (size_t)N; i += stride) r1[i] = -zeta * a1[i];
+  for (size_t i = t0; i < (size_t)me; i += stride) r2[i] = -zeta * a2[i];
+  for (size_t i = t0; i < (size_t)m; i += stride) {
+    r3[i] = -zeta * a3[i];
+    r4[i] = z[i] * w[i] - mu;
+  }
+}
+
+// maximal feasible step (:316-334): out[0] = min over dz_i > 0 of z_i / dz_i and over
+// dw_i > 0 of w_i / dw_i (the step is x -= alpha dx); out[0] initialised to +inf.
+// (the reference's running test  z_i < val * dz_i  picks the same minimum)
+__global__ void ips_franke_ratio_kernel(int m, const double *__restrict__ z,
+                                        const double *__restrict__ w,
+                                        const double *__restrict__ dz,
+                                        const double *__restrict__ dw, double *out) {
+  double v = __longlong_as_double(0x7ff0000000000000LL);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)m;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double a = dz[i], b = dw[i];
+    if (a > 0.0) v = fmin(v, z[i] / a);
+    if (b > 0.0) v = fmin(v, w[i] / b);
+  }
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  if ((threadIdx.x & 31) == 0 && v >= 0.0) atomic_min_pos(out, v);
+}
+
+// cold start slacks (:184-188): w = (Ltilde + d) + 1e-10
+__global__ void ips_franke_w0_kernel(int m, double Ltilde, const double *__restrict__ dvec, double *w) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)m;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double t = Ltilde + dvec[i];
+    w[i] = t + 1e-10;
+  }
+}
+
+__global__ void ips_add_scalar_kernel(size_t n, double a, double *y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (size_t)gridDim.x * blockDim.x)
+    y[i] += a;
+}

@@ -18,16 +18,24 @@
 typedef If_Method<Hqp_IpsCuda> If_Cmd;
 
 IF_CLASS_DEFINE("CudaMehrotra", Hqp_IpsCuda, Hqp_Solver);
+IF_CLASS_DEFINE("CudaFranke", Hqp_IpsCudaFranke, Hqp_Solver);
 
 //--------------------------------------------------------------------------
-Hqp_IpsCuda::Hqp_IpsCuda()
+Hqp_IpsCuda::Hqp_IpsCuda(int franke)
 {
   _n = _me = _m = 0;
   _w = VNULL;
   _hot = 0;
-  _max_warm_iters = 25;  // hqp/Hqp_IpsMehrotra.C:111
+  _franke = franke;
+  _max_warm_iters = franke ? 15 : 25;  // hqp/Hqp_IpsFranke.C:82, hqp/Hqp_IpsMehrotra.C:111
+  _beta = 0.995;                       // hqp/Hqp_IpsFranke.C:79
+  _mu0 = 0.0;                          // :78
   _logging = 0;
   _gap = 0.0;
+  if (franke) {
+    _ifList.append(new If_Real("qp_beta", &_beta));
+    _ifList.append(new If_Real("qp_mu0", &_mu0));
+  }
 
   // the option names of Hqp_IpsMehrotra (:117-130) that apply here
   _ifList.append(new If_Int("qp_iter", &_iter));
@@ -115,7 +123,11 @@ void Hqp_IpsCuda::solve()
     y = &_yp[0];
   }
   int rc;
-  if (_hot)
+  if (_franke)
+    rc = hqpcu_franke_solve(_mat.handle(), _qp->c->ve, b, _m ? _qp->d->ve : none, _eps, _max_iters,
+                            _hot, _max_warm_iters, _beta, _mu0, _qp->x->ve, y, _m ? _z->ve : none,
+                            _m ? _w->ve : none, &iters, &res, &gap);
+  else if (_hot)
     rc = hqpcu_mehrotra_hot_solve(_mat.handle(), _qp->c->ve, b, _m ? _qp->d->ve : none, _eps,
                                   _max_iters, _max_warm_iters, _qp->x->ve, y,
                                   _m ? _z->ve : none, _m ? _w->ve : none, &iters, &res, &gap);

@@ -29,10 +29,12 @@ class Hqp_IpsCuda : public Hqp_Solver {
   int _max_warm_iters;
   int _logging;
   Real _gap;
+  int _franke;       ///< 0: Mehrotra predictor-corrector, 1: Franke (Hqp_IpsFranke)
+  Real _beta, _mu0;  ///< Franke: qp_beta, qp_mu0 (hqp/Hqp_IpsFranke.C:78-79)
   std::vector<double> _bp, _yp;  ///< b / y in the engine's equality row order
 
  public:
-  Hqp_IpsCuda();
+  Hqp_IpsCuda(int franke = 0);
   ~Hqp_IpsCuda();
 
   void init();
@@ -43,7 +45,14 @@ class Hqp_IpsCuda : public Hqp_Solver {
   void solve();
 
   Real gap() { return _gap; }
-  const char *name() { return "CudaMehrotra"; }
+  const char *name() { return _franke ? "CudaFranke" : "CudaMehrotra"; }
+};
+
+/** Hqp_IpsFranke (hqp/Hqp_IpsFranke.C, the solver docp ships with) with the whole
+ *  iteration on the device: sqp_qp_solver CudaFranke (hqpcu_franke_solve). */
+class Hqp_IpsCudaFranke : public Hqp_IpsCuda {
+ public:
+  Hqp_IpsCudaFranke() : Hqp_IpsCuda(1) {}
 };
 
 #endif

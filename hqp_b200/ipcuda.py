@@ -223,6 +223,29 @@ class IpCuda:
         return dict(x=x, y=y, z=z[:self.m], w=w[:self.m], iters=it.value,
                     result=names[res.value], gap=gap.value)
 
+    def franke_solve(self, c=None, b=None, d=None, eps=1e-9, max_iters=0, hot=None,
+                     max_warm_iters=0, beta=0.0, mu0=0.0):
+        """Hqp_IpsFranke cold_start (or hot_start from hot = (x, y, z, w)) + solve on
+        the device (hqpcu_franke_solve)."""
+        p = self.prob
+        c = np.ascontiguousarray(p.c if c is None else c, np.float64)
+        b = np.ascontiguousarray(p.b if b is None else b, np.float64)
+        d = np.ascontiguousarray(p.d if d is None else d, np.float64)
+        x, y = np.zeros(self.N), np.zeros(self.me)
+        z, w = np.zeros(max(self.m, 1)), np.zeros(max(self.m, 1))
+        if hot is not None:
+            x[:], y[:] = hot[0], hot[1]
+            z[:self.m], w[:self.m] = hot[2], hot[3]
+        it, res, gap = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_double(0)
+        _check(lib().hqpcu_franke_solve(self.h, _hp(c), _hp(b), _hp(d), ctypes.c_double(eps),
+                                        max_iters, int(hot is not None), max_warm_iters,
+                                        ctypes.c_double(beta), ctypes.c_double(mu0), _hp(x), _hp(y),
+                                        _hp(z), _hp(w), ctypes.byref(it), ctypes.byref(res),
+                                        ctypes.byref(gap)), "hqpcu_franke_solve")
+        names = ["optimal", "feasible", "infeasible", "suboptimal", "degenerate"]
+        return dict(x=x, y=y, z=z[:self.m], w=w[:self.m], iters=it.value,
+                    result=names[res.value], gap=gap.value)
+
     def set_value_map(self, dst, dst2):
         dst = np.ascontiguousarray(dst, np.int64)
         dst2 = np.ascontiguousarray(dst2, np.int64)

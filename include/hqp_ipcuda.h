@@ -243,6 +243,19 @@ int hqpcu_mehrotra_hot_solve(hqpcu_handle *h, const double *c, const double *b,
                              int max_warm_iters, double *x, double *y, double *z,
                              double *w, int *iters, int *result, double *gap);
 
+/* --- device-resident Franke interior-point solve: Hqp_IpsFranke::cold_start /
+ *     hot_start + ::solve (hqp/Hqp_IpsFranke.C:157-417), the default QP solver of
+ *     the shipped docp example (hqp/Hqp_SqpSolver.C:67).  Same problem and vector
+ *     conventions as hqpcu_mehrotra_solve.  hot = 0: cold start from x = y = 0;
+ *     hot != 0: x, y, z, w are IN/OUT (the previous iterate, :226-268), with the
+ *     reference's cold restarts when the gap grows.  beta <= 0: 0.995 (qp_beta),
+ *     mu0: qp_mu0 (0 = Wright's Ltilde), max_warm_iters <= 0: 15.  result:
+ *     Hqp_Result 0 optimal, 1 feasible, 2 infeasible, 3 suboptimal, 4 degenerate. */
+int hqpcu_franke_solve(hqpcu_handle *h, const double *c, const double *b, const double *d,
+                       double eps, int max_iters, int hot, int max_warm_iters, double beta,
+                       double mu0, double *x, double *y, double *z, double *w, int *iters,
+                       int *result, double *gap);
+
 /* --- per-kernel timing with CUDA events on the launching stream (bench.py's
  *     roofline section).  hqpcu_profile_read synchronises and writes a JSON
  *     object {"kernel": {"ms": total, "n": launches}, ...} for everything

@@ -97,3 +97,25 @@ def test_hot_started_sequence_matches_reference_golden(name, nseg, golden_dir):
         assert relerr(r["y"], g["y"][k]) < 1e-6
         prev = (r["x"], r["y"])
     e.close()
+
+
+@pytest.mark.skipif(not refharness.available(), reason="compiled reference not present")
+@pytest.mark.parametrize("dims", [(5, 3, 40), (20, 10, 200), (12, 4, 50)])
+@pytest.mark.parametrize("nseg", [1, 0])
+def test_franke_matches_live_reference(dims, nseg):
+    """hqpcu_franke_solve against a cold-started Hqp_IpsFranke + Hqp_IpLQDOCP solve of
+    the unmodified reference: identical iteration count, same solution."""
+    p = synth_lqdocp(*dims)
+    qp = refharness.RefQP(p)
+    ref = refharness.ips_solve(qp, "Franke", "LQDOCP", 1e-9)
+    e = IpCuda(p, nseg=nseg)
+    e.update()
+    r = e.franke_solve(eps=1e-9)
+    assert r["result"] == ref["result"] == "optimal"
+    assert r["iters"] == ref["iters"]
+    assert relerr(r["x"], ref["x"]) < 1e-7
+    assert relerr(r["z"], ref["z"]) < 1e-6
+    # hot start from the solution: converges again (cold restarts allowed), same x
+    r2 = e.franke_solve(eps=1e-9, hot=(r["x"], r["y"], r["z"], r["w"]))
+    assert r2["result"] == "optimal" and relerr(r2["x"], ref["x"]) < 1e-6
+    e.close(); qp.close()
