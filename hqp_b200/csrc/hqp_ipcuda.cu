@@ -585,6 +585,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(dev_alloc(h, &d.V, SB * (K + 1) * nx * nx));
   TRY(dev_alloc(h, &d.Rux, SB * K * nu * nx));
   TRY(dev_alloc(h, &d.LD, SB * K * nu * nu));
+  TRY(dev_alloc(h, &d.ldkind, SB * K));
   TRY(dev_alloc(h, &d.Phi, SB * K * nx * nx));
   // bulk-copy (TMA) path needs every per-stage slab to be a 16-byte multiple
   d.use_tma = (nx % 2 == 0 && nu % 2 == 0 && !h->big) ? 1 : 0;

@@ -70,6 +70,8 @@ struct LqDev {
   double *V;       // [batch][K+1][nx*nx]   value-function Hessians Vxx
   double *Rux;     // [batch][K][nu*nx]     feedback gains
   double *LD;      // [batch][K][nu*nu]     LDL^T of Guu: unit L below, 1/D on the diagonal
+  int *ldkind;     // [batch][K] 0: LD holds the LDL^T factor; 1: the explicit inverse of an
+                   //            indefinite Guu from the scaled, pivoted fallback
   double *Phi;     // [batch][K][nx*nx]     closed loop fx - fu Rux
   // factor hierarchy: element e of level l at [(b*ft.nel + ft.off[l] + e) * nx*nx]
   double *segA, *segC, *segJ;  // boundary elements (zero-terminal-cost condensation)
@@ -710,8 +712,10 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // Register-resident LDL^T for compile-time M <= 32: lane i keeps row i of the
 // block; per pivot the pivot column is broadcast with warp shuffles (no shared
 // memory traffic, no integer division, no barriers inside the sweep).
+// keep_on_fail: a block with a non-positive / zero pivot is left untouched (the
+// caller switches to the pivoted inverse, warp_pivoted_inverse).
 template <int M>
-__device__ __forceinline__ int warp_ldlt_reg(double *A, int lda) {
+__device__ __forceinline__ int warp_ldlt_reg(double *A, int lda, bool keep_on_fail = false) {
   const int lane = threadIdx.x & 31;
   const int row = lane < M ? lane : M - 1;
   double a[M];
@@ -732,7 +736,7 @@ __device__ __forceinline__ int warp_ldlt_reg(double *A, int lda) {
     a[p] = (lane == p) ? inv : li;
   }
   __syncwarp();  // lanes >= M read row M-1 above: order them before its write-back
-  if (lane < M) {
+  if (lane < M && !(keep_on_fail && st)) {
 #pragma unroll
     for (int j = 0; j < M; j++)
       if (j <= lane) A[lane * lda + j] = a[j];
@@ -742,9 +746,9 @@ __device__ __forceinline__ int warp_ldlt_reg(double *A, int lda) {
 }
 
 template <int M>
-__device__ __forceinline__ int warp_ldlt_any(double *A, int lda, int m) {
+__device__ __forceinline__ int warp_ldlt_any(double *A, int lda, int m, bool keep_on_fail = false) {
   if constexpr (M > 0 && M <= 32)
-    return warp_ldlt_reg<M>(A, lda);
+    return warp_ldlt_reg<M>(A, lda, keep_on_fail);
   else
     return warp_ldlt(A, lda, m);
 }
@@ -1002,6 +1006,65 @@ __device__ __forceinline__ int warp_gj_inverse_la(const double *M, int ldm, doub
     for (int q = 0; q < N; q++) Minv[mystep * ldi + rowsel[q]] = a[q] * dinv;
   }
   return flag;
+}
+
+// ---------------------------------------------------------------------------
+// Indefinite stage block (a16): the reference factors Guu with a diagonally
+// scaled Bunch-Kaufman (sc_i = 1/sqrt(g_ii) where g_ii > 1, BKPfactor;
+// hqp/Hqp_IpLQDOCP.C:1860-1879, meschach/bkpfacto.c:102-226).  Here LDL^T without
+// interchanges is tried first (positive definite blocks: the IP iterations of a
+// convex QP); a block with a non-positive pivot is redone by ONE warp as
+//     Guu^{-1} = S (S Guu S)^{-1} S,   S = diag(sc),
+// with the register-resident Gauss-Jordan whose pivot search is a warp redux over
+// magnitude keys (warp_gj_inverse: partial pivoting, stable for symmetric
+// indefinite blocks).  A (M x M, lda, full symmetric block) is replaced by the
+// explicit inverse; scr: M (M+1) + 2 (M+2) + M doubles, rowsel: 65 ints.
+// Returns LQ_FLAG_SING for a singular block.
+// ---------------------------------------------------------------------------
+template <int M>
+__device__ __forceinline__ int warp_pivoted_inverse(double *A, int lda, double *scr, int *rowsel) {
+  constexpr int ME = (M + 1) & ~1;  // warp_gj_inverse wants an even order: pad with an identity row
+  const int lane = threadIdx.x & 31;
+  double *Ms = scr, *rowbuf = scr + ME * (ME + 1), *sc = rowbuf + 2 * (ME + 2);
+  if (lane < M) {
+    const double g = A[lane * lda + lane];
+    sc[lane] = g > 1.0 ? rsqrt(g) : 1.0;
+  }
+  __syncwarp();
+  for (int e = lane; e < ME * ME; e += 32) {
+    const int i = e / ME, j = e - i * ME;
+    // (symmetrise from the lower triangle: the upper one may be stale)
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < M && j < M) v = sc[i] * sc[j] * (j <= i ? A[i * lda + j] : A[j * lda + i]);
+    Ms[i * (ME + 1) + j] = v;
+  }
+  __syncwarp();
+  const int fl = warp_gj_inverse<ME>(Ms, ME + 1, Ms, ME + 1, rowbuf, rowsel);
+  __syncwarp();
+  for (int e = lane; e < M * M; e += 32) {
+    const int i = e / M, j = e - i * M;
+    A[i * lda + j] = sc[i] * sc[j] * Ms[i * (ME + 1) + j];
+  }
+  __syncwarp();
+  return fl;
+}
+
+// y <- Ainv y for one right-hand side held at y[i*ys] by ONE thread (Ainv: the
+// explicit inverse left by warp_pivoted_inverse)
+template <int M>
+__device__ __forceinline__ void thread_inv_apply(const double *Ainv, int lda, double *y, int ys) {
+  double r[M], o[M];
+#pragma unroll
+  for (int i = 0; i < M; i++) r[i] = y[i * ys];
+#pragma unroll
+  for (int i = 0; i < M; i++) {
+    double s = 0.0;
+#pragma unroll
+    for (int l = 0; l < M; l++) s = fma(Ainv[i * lda + l], r[l], s);
+    o[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < M; i++) y[i * ys] = o[i];
 }
 
 // ---------------------------------------------------------------------------

@@ -223,7 +223,7 @@ __device__ __forceinline__ void riccati_stage(double *stg, int nx, int nu, int L
                                               bool zero_V, double *V, const double *fx,
                                               const double *fu, double *G, double *T, double *Rux,
                                               double *Phi, int *st_s, const ElemAcc *el,
-                                              Idle idle = Idle()) {
+                                              Idle idle = Idle(), int *kind_s = nullptr) {
   const int nm = nx + nu;
   const int tid = threadIdx.x, nthr = blockDim.x;
   LQ_STAMP2(1);
@@ -329,13 +329,31 @@ __device__ __forceinline__ void riccati_stage(double *stg, int nx, int nu, int L
     // the other warps run the deferred work of the previous stage meanwhile
     const int wu = warp_id_uniform();
     if (wu == 0) {
-      const int st = warp_ldlt_any<NU>(Guu, nm, nu);
+      // (a16) positive definite blocks: LDL^T without interchanges; a block with a
+      // non-positive pivot is left untouched and inverted with scaling and pivoting
+      constexpr bool PIV = NU > 0 && NU <= 32;
+      int st = warp_ldlt_any<NU>(Guu, nm, nu, PIV);
+      bool inv = false;
+      if constexpr (PIV) {
+        if (st) {  // (the same on every lane: pivots are broadcast by shuffles)
+          constexpr int ME = (NU + 1) & ~1;
+          st = warp_pivoted_inverse<NU>(Guu, nm, T,
+                                        reinterpret_cast<int *>(T + ME * (ME + 1) + 2 * (ME + 2) + ME + 2));
+          inv = true;
+        }
+      }
       if (st && tid == 0) atomicOr(st_s, st);
+      if (kind_s && tid == 0) *kind_s = inv ? 1 : 0;
       __syncwarp();
       LQ_STAMP2(4);
       for (int j = tid; j < nx; j += 32) {
         for (int i = 0; i < nu; i++) Rux[i * LV + j] = G[(nx + i) * nm + j];
-        ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+        if constexpr (PIV) {
+          if (inv) thread_inv_apply<NU>(Guu, nm, Rux + j, LV);
+          else ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+        } else {
+          ldlt_solve_any<NU>(Guu, nm, nu, Rux + j, LV);
+        }
       }
       if (NW == 1) {
         __syncwarp();
@@ -780,9 +798,10 @@ seg_riccati_kernel(LqDev d) {
   double *V = sm.take(nx * LV), *T = sm.take(nx * LT);
   double *RuxA = sm.take(nu * LV), *RuxB = sm.take(nu * LV), *Phi = sm.take(nx * LV);
   double *P0 = sm.take(nx * LV), *P1 = sm.take(nx * LV);
-  __shared__ int st_s;
+  __shared__ int st_s, kind_s;
   if (threadIdx.x == 0) {
     st_s = 0;
+    kind_s = 0;
     if (d.use_tma) stage_issue(d, nx, nu, sp, b, kb - 1, 0);
   }
   const size_t so = ((size_t)b * d.ft.nel + s) * n2;   // factor tree (segVb)
@@ -850,7 +869,8 @@ seg_riccati_kernel(LqDev d) {
     riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T,
                               Rux, Phi, &st_s, nullptr, [&](int w, int nw) {
                                 if (have_prev) flush(k + 1, Rp, Ptc, Ptd, w, nw);
-                              });
+                              }, &kind_s);
+    if (threadIdx.x == 0) d.ldkind[(size_t)b * d.K + k] = kind_s;
     if (have_prev) { double *t = Pt; Pt = Ptn; Ptn = t; }
     LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;

@@ -605,7 +605,20 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_mid_kernel(LqDev d, const d
         Gu[j] = a;
       }
     __syncwarp();
-    warp_ldlt_solve_g(LDs, nu, Gu, sl, W, on);
+    // LD holds the LDL^T factor of Guu or, for an indefinite block handled by the
+    // pivoted fallback of the factor, its explicit inverse (d.ldkind)
+    const bool expl = on && d.ldkind[ks] != 0;
+    warp_ldlt_solve_g(LDs, nu, Gu, sl, W, on && !expl);
+    if (__any_sync(0xffffffffu, expl)) {  // (rare: an indefinite block in this warp's stages)
+      // the pivoted fallback exists for nu <= W only (compiled sizes, nu <= 32 / 16):
+      // one lane per row, all of Gu read before any of it is overwritten
+      double a = 0.0;
+      if (expl && sl < nu)
+        for (int l = 0; l < nu; l++) a = fma(LDs[sl * nu + l], Gu[l], a);
+      __syncwarp();
+      if (expl && sl < nu) Gu[sl] = a;
+      __syncwarp();
+    }
     if (on) {
       for (int j = sl; j < nu; j += W) d.Ru[ks * nu + j] = Gu[j];
       for (int i = sl; i < nx; i += W) {

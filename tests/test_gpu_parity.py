@@ -415,3 +415,50 @@ def test_update_from_sparse_values_equals_dense_update():
     with pytest.raises(Exception):
         b.set_value_map(np.array([10 ** 12]), np.array([-1]))
     a.close(); b.close()
+
+
+# ---- indefinite stage blocks: scaled, pivoted factorisation of Guu (a16) ----------
+@pytest.mark.parametrize("dims", [(12, 4, 50), (20, 10, 96), (40, 10, 64)])
+@pytest.mark.parametrize("nseg", [1, 0])
+def test_indefinite_guu_matches_bunch_kaufman_oracle(dims, nseg):
+    """Huu made indefinite at a few stages (a non-convex Hessian block as BFGS can
+    deliver it before eigenvalue control): the reference factors Guu with a scaled
+    Bunch-Kaufman (hqp/Hqp_IpLQDOCP.C:1860-1879, meschach/bkpfacto.c:102-226) and
+    solves the KKT system all the same; the oracle restates that factorisation.
+    The device path must switch from LDL^T without interchanges to its scaled,
+    pivoted inverse for those blocks -- and, parallel in time, fall back to the
+    sequential sweep for THIS factor only (the next update restores the segments)."""
+    nx, nu, K = dims
+    p = synth_lqdocp(nx, nu, K, seed=21)
+    bad = [3, K // 2, K - 2]
+    for k in bad:
+        p.Q[k, nx:, nx:] -= 4.0 * np.eye(nu)       # Huu indefinite (eigenvalues ~ -3.9 .. -2)
+        p.Q[k, nx, nx + 1] += 0.7                   # and not diagonal
+        p.Q[k, nx + 1, nx] += 0.7
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=5)
+    z *= 0.05                                       # weak barrier terms: Guu stays indefinite
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, nseg=nseg)
+    nseg0 = e.nseg
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b, key in zip(mine, ref, ("dx", "dy", "dz", "dw")):
+        assert relerr(a, b) < 1e-9, (key, relerr(a, b))
+    sx, sy, sz, sw, res, nsteps = e.solve(r1, r2, r3, r4)
+    assert res <= 1e-10
+    if nseg == 0:
+        assert e.nseg == 1 and nseg0 > 1            # demoted for these matrix values ...
+        p2 = synth_lqdocp(nx, nu, K, seed=22)       # ... and restored by the next update
+        e.update(Q=p2.Q, fx=p2.fx, fu=p2.fu, ineq_val=p2.ineq_val)
+        assert e.nseg == nseg0
+        o2 = PortOracle(p2)
+        o2.factor(z, w)
+        ref2 = o2.step(r1, r2, r3, r4)
+        e.factor(z, w)
+        for a, b in zip(e.step(r1, r2, r3, r4), ref2):
+            assert relerr(a, b) < TOL
+        o2.close()
+    e.close(); o.close()
