@@ -16,6 +16,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <condition_variable>
+#include <functional>
+#include <thread>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -81,11 +84,13 @@ static thread_local std::string g_err;
 
 struct IpsState;
 struct DistState;
+struct MgState;
 
 struct hqpcu_handle {
   LqDev d;
   IpsState *ips = nullptr;           // device-resident IP solver state (lazy)
   DistState *dist = nullptr;         // horizon split over NCCL (hqp_dist_host.inc)
+  MgState *mg = nullptr;             // dispatcher over several GPUs of this process (hqp_mg_host.inc)
   std::vector<double> eq_rowsum;     // row sums |E| of the general equality rows
   std::vector<int> dims_eq_ptr;      // host copy of the equality CSR pointers
   hqpcu_dims dims;
@@ -390,6 +395,14 @@ static void ips_free(hqpcu_handle *h);
 // horizon split over NCCL (hqp_dist_host.inc): after hqpcu_comm_init the handle is
 // one rank's stage range and every entry point works on that range's slices
 extern "C" {  // (defined inside this file's extern "C" block)
+static int mg_create(const hqpcu_dims *dims, hqpcu_handle **out);
+static void mg_free(hqpcu_handle *h);
+static int mg_update(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
+                     const double *cv);
+static int mg_factor(hqpcu_handle *h, const double *z, const double *w);
+static int mg_apply(hqpcu_handle *h, int mode, double eps, const double *r1, const double *r2,
+                    const double *r3, const double *r4, double *dx, double *dy, double *dz,
+                    double *dw, double *res, int *nsteps);
 static void dist_free(hqpcu_handle *h);
 static bool dist_on(const hqpcu_handle *h);
 static int dist_launch_factor(hqpcu_handle *h);
@@ -413,6 +426,7 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     g_err = "hqpcu_create: nu = 0 is not supported";
     return HQPCU_E_UNSUPPORTED;
   }
+  if (dims->ngpu > 1) return mg_create(dims, out);  // dispatcher over several GPUs
   if (dims->nx > 256 || dims->nu > 256) {
     g_err = "hqpcu_create: stage blocks larger than 256 are not supported";
     return HQPCU_E_UNSUPPORTED;
@@ -743,6 +757,11 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
 
 int hqpcu_destroy(hqpcu_handle *h) {
   if (!h) return HQPCU_OK;
+  if (h->mg) {
+    mg_free(h);
+    delete h;
+    return HQPCU_OK;
+  }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   drop_graphs(h);
@@ -770,7 +789,7 @@ int hqpcu_solve_stats(const hqpcu_handle *h, long long *solves, long long *steps
   *steps = h->n_solve_steps;
   return HQPCU_OK;
 }
-int hqpcu_nseg(const hqpcu_handle *h) { return h ? h->d.P : 0; }
+int hqpcu_nseg(const hqpcu_handle *h);
 
 // ------------------------------------------------------------------ update --
 // new matrix values: a sequential-sweep fallback taken for the previous values
@@ -801,6 +820,10 @@ static int update_impl(hqpcu_handle *h, const double *Q, const double *fx, const
 
 int hqpcu_update(hqpcu_handle *h, const double *Q, const double *fx, const double *fu,
                  const double *ineq_val, const double *eq_val) {
+  if (h && h->mg) {
+    if (!Q || !fx || !fu || (h->d.m && !ineq_val)) return HQPCU_E_NULL;
+    return mg_update(h, Q, fx, fu, ineq_val);
+  }
   int rc = update_impl(h, Q, fx, fu, ineq_val, eq_val, cudaMemcpyHostToDevice);
   if (rc) return rc;
   h->eq_rowsum.assign(h->q.n_eq, 0.0);
@@ -1120,6 +1143,7 @@ static int finish_factor(hqpcu_handle *h) {
 }
 
 int hqpcu_factor(hqpcu_handle *h, const double *z, const double *w) {
+  if (h && h->mg) return mg_factor(h, z, w);
   int rc = factor_impl(h, z, w, cudaMemcpyHostToDevice);
   if (rc) return rc;
   return finish_factor(h);
@@ -1333,6 +1357,7 @@ int hqpcu_step(hqpcu_handle *h, const double *r1, const double *r2, const double
                const double *r4, double *dx, double *dy, double *dz, double *dw) {
   if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
   if (h->d.m && (!r3 || !r4 || !dz || !dw)) return HQPCU_E_NULL;
+  if (h->mg) return mg_apply(h, 0, 0.0, r1, r2, r3, r4, dx, dy, dz, dw, nullptr, nullptr);
   CU(cudaSetDevice(h->device));
   int rc = h2d_rhs(h, r1, r2, r3, r4);
   if (rc) return rc;
@@ -1385,6 +1410,9 @@ int hqpcu_residuum(hqpcu_handle *h, const double *r1, const double *r2, const do
                    const double *r4, const double *dx, const double *dy, const double *dz,
                    const double *dw, double *res) {
   if (!h || !res) return HQPCU_E_NULL;
+  if (h->mg)
+    return mg_apply(h, 2, 0.0, r1, r2, r3, r4, const_cast<double *>(dx), const_cast<double *>(dy),
+                    const_cast<double *>(dz), const_cast<double *>(dw), res, nullptr);
   CU(cudaSetDevice(h->device));
   const LqDev &d = h->d;
   const size_t B = d.batch;
@@ -1461,6 +1489,7 @@ int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
                 double *dw, double *res, int *nsteps) {
   if (!h || !r1 || !r2 || !dx || !dy) return HQPCU_E_NULL;
   if (h->d.m && (!r3 || !r4 || !dz || !dw)) return HQPCU_E_NULL;
+  if (h->mg) return mg_apply(h, 1, eps, r1, r2, r3, r4, dx, dy, dz, dw, res, nsteps);
   CU(cudaSetDevice(h->device));
   int rc = h2d_rhs(h, r1, r2, r3, r4);
   if (rc) return rc;
@@ -1663,3 +1692,10 @@ int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {
 
 #include "hqp_ips_host.inc"
 #include "hqp_franke_host.inc"
+extern "C" {
+#include "hqp_mg_host.inc"
+int hqpcu_nseg(const hqpcu_handle *h) {
+  if (h && h->mg) return h->mg->w[0]->part ? h->mg->w[0]->part->d.P : 0;
+  return h ? h->d.P : 0;
+}
+}

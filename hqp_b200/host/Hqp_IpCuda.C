@@ -33,6 +33,7 @@ Hqp_IpCuda::Hqp_IpCuda()
   _h = NULL;
   _nseg = 0;
   _device = 0;
+  _ngpu = 1;
   _dev_solve = 1;
   _sparse_update = 1;
   _K = _nx = _nu = _n = _me = _m = 0;
@@ -42,6 +43,7 @@ Hqp_IpCuda::Hqp_IpCuda()
 
   _ifList.append(new If_Int("mat_nseg", &_nseg));
   _ifList.append(new If_Int("mat_device", &_device));
+  _ifList.append(new If_Int("mat_ngpu", &_ngpu));
   _ifList.append(new If_Int("mat_dev_solve", &_dev_solve));
   _ifList.append(new If_Int("mat_sparse_update", &_sparse_update));
 }
@@ -230,6 +232,7 @@ void Hqp_IpCuda::init(const Hqp_Program *qp)
   dims.eq_lcol = _n_eq ? &eq_lcol[0] : NULL;
   dims.device = _device;
   dims.nseg = _nseg;
+  dims.ngpu = _ngpu > 1 ? _ngpu : 0;
   check(hqpcu_create(&dims, &_h), "Hqp_IpCuda::init");
 
   _Q.assign((size_t)(_K + 1) * nm * nm, 0.0);
@@ -240,6 +243,7 @@ void Hqp_IpCuda::init(const Hqp_Program *qp)
   _r2p.assign(_me > 0 ? _me : 1, 0.0);
   _dyp.assign(_me > 0 ? _me : 1, 0.0);
 
+  if (_ngpu > 1) _sparse_update = 0;  // (the dispatcher takes dense stage slabs)
   if (_sparse_update) build_value_map(qp);
   update(qp);
 }

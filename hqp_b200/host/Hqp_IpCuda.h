@@ -25,7 +25,8 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
   hqpcu_handle *_h;
   // interface options
   int _nseg;      ///< mat_nseg: horizon segments (0 = automatic, 1 = sequential)
-  int _device;    ///< mat_device: CUDA device ordinal
+  int _device;    ///< mat_device: CUDA device ordinal (the first one with mat_ngpu > 1)
+  int _ngpu;      ///< mat_ngpu: split the horizon over this many GPUs (hqpcu_dims::ngpu)
   int _dev_solve; ///< mat_dev_solve: run the refinement loop of solve() on the device
   int _sparse_update; ///< mat_sparse_update: upload SPMAT values + device-side scatter (row f1)
 

@@ -30,7 +30,8 @@ class HqpcuDims(ctypes.Structure):
                 ("n_ineq", ctypes.c_int), ("ineq_stage", _c_int_p),
                 ("ineq_ptr", _c_int_p), ("ineq_lcol", _c_int_p),
                 ("n_eq", ctypes.c_int), ("eq_stage", _c_int_p), ("eq_ptr", _c_int_p),
-                ("eq_lcol", _c_int_p), ("device", ctypes.c_int), ("nseg", ctypes.c_int)]
+                ("eq_lcol", _c_int_p), ("device", ctypes.c_int), ("nseg", ctypes.c_int),
+                ("ngpu", ctypes.c_int)]
 
 
 class SingularError(ArithmeticError):
@@ -82,7 +83,7 @@ class IpCuda:
     ``torch.Tensor.data_ptr()``) and enqueue on the handle's stream.
     """
 
-    def __init__(self, prob, batch=1, device=0, nseg=0):
+    def __init__(self, prob, batch=1, device=0, nseg=0, ngpu=0):
         self.prob = prob
         self.batch = batch
         stage, lcol = prob.ineq_stage_local()
@@ -92,7 +93,7 @@ class IpCuda:
         self._keep = (stage, lcol, ptr, estage, elcol, eptr)
         dims = HqpcuDims(prob.K, prob.nx, prob.nu, batch, int(prob.fixed_x0), prob.m,
                          _ip(stage), _ip(ptr), _ip(lcol), prob.n_eq, _ip(estage),
-                         _ip(eptr), _ip(elcol), device, nseg)
+                         _ip(eptr), _ip(elcol), device, nseg, ngpu)
         self.h = ctypes.c_void_p()
         _check(lib().hqpcu_create(ctypes.byref(dims), ctypes.byref(self.h)), "hqpcu_create")
         self.N, self.me, self.m = prob.N, prob.me, prob.m

@@ -68,6 +68,13 @@ typedef struct hqpcu_dims {
   int device;   /* CUDA device ordinal                                          */
   int nseg;     /* horizon segments per instance for the parallel-in-time
                    factor/solve; 0 = choose automatically, 1 = sequential sweep */
+  int ngpu;     /* 0 / 1: one GPU.  N > 1: the handle is a dispatcher over the N
+                   devices device .. device+N-1 of THIS process (Hqp_IpCuda's
+                   mat_ngpu): the horizon is split into N contiguous stage ranges,
+                   one worker thread and one NCCL rank per GPU; the host-pointer
+                   entry points (update, factor, step, solve, residuum,
+                   mehrotra_*, franke_solve) take and return FULL-length vectors.
+                   batch == 1, no general equality rows, dense update only.     */
 } hqpcu_dims;
 
 /* --- life cycle (Hqp_IpCuda ctor/dtor + init; If_Module deletes and re-creates

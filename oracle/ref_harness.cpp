@@ -362,6 +362,7 @@ int ref_ips_solve(void *qp_, const char *solver, const char *mat, double eps,
     delete s;
     return -2;
   }
+  if (getenv("HQP_MAT_NGPU")) If_SetInt("mat_ngpu", atoi(getenv("HQP_MAT_NGPU")));
   s->qp(qp);
   s->eps(eps);
   if (max_iters > 0) s->max_iters(max_iters);
@@ -442,6 +443,8 @@ int ref_docp_did(int kmax, const char *qp_solver, const char *mat_solver,
   // Franke instance runs with the 1e-9 of Hqp_SqpSolver's constructor -- tests that
   // compare a new module with the as-shipped run set it explicitly
   if (getenv("HQP_QP_EPS")) If_SetReal("qp_eps", atof(getenv("HQP_QP_EPS")));
+  // option of a plugged-in matrix module (Hqp_IpCuda: horizon split over GPUs)
+  if (getenv("HQP_MAT_NGPU")) If_SetInt("mat_ngpu", atoi(getenv("HQP_MAT_NGPU")));
   if (kmax > 0) If_SetInt("prg_kmax", kmax);
   If_SetInt("prg_with_cns", with_cns);
   int rc = 0;

@@ -129,3 +129,88 @@ def test_split_horizon_matches_oracle(world, cfg, graphs):
         pytest.skip(f"needs {world} CUDA devices")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(world, _free_port(), cfg, graphs), nprocs=world, join=True)
+
+
+# ---- several GPUs behind ONE handle of one process (hqpcu_dims::ngpu, mat_ngpu) ------
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 CUDA devices")
+@pytest.mark.parametrize("cfg", [(20, 10, 400, 0, 1), (12, 4, 230, 2, 0)])
+@pytest.mark.parametrize("ngpu", [2, 4])
+def test_single_process_dispatcher_matches_oracle(ngpu, cfg):
+    if _ngpu() < ngpu:
+        pytest.skip(f"needs {ngpu} CUDA devices")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import relerr
+    from hqp_b200.ipcuda import IpCuda
+    from hqp_b200.problem import add_random_stage_ineq, rhs_for, synth_lqdocp
+    from oracle.portoracle import PortOracle
+    nx, nu, K, gen, fixed = cfg
+    p = synth_lqdocp(nx, nu, K, seed=77)
+    if gen:
+        add_random_stage_ineq(p, rows_per_stage=gen, nnz_per_row=3, seed=5)
+    if not fixed:
+        p.fixed_x0 = False
+        p.b = p.b[:K * nx].copy()
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=9)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p, ngpu=ngpu)         # full-length vectors in and out
+    e.update()
+    for _ in range(2):
+        e.factor(z, w)
+        for a, b in zip(e.step(r1, r2, r3, r4), ref):
+            assert relerr(a, b) < 1e-10
+    sx, sy, sz, sw, res, nsteps = e.solve(r1, r2, r3, r4)
+    assert res <= 1e-10 and nsteps == 1 and relerr(sx, ref[0]) < 1e-10
+    rng = np.random.default_rng(3)
+    pert = [v + 1e-3 * rng.standard_normal(v.shape) for v in ref]
+    assert abs(e.residuum(r1, r2, r3, r4, *pert) - o.residuum(r1, r2, r3, r4, *pert)) <= 1e-11
+    one = IpCuda(p)
+    one.update()
+    for solver in ("mehrotra_solve", "franke_solve"):
+        a, b = getattr(e, solver)(), getattr(one, solver)()
+        assert a["iters"] == b["iters"] and a["result"] == b["result"] == "optimal", solver
+        assert relerr(a["x"], b["x"]) < 1e-9
+    one.close(); e.close(); o.close()
+
+
+def _plugin_worker(ngpu, q):
+    """the unmodified Hqp_IpsMehrotra of the reference driving Hqp_IpCuda (plugin) on a
+    synthetic QP, in a fresh process (mat_ngpu is read from the environment by the
+    test harness when the solver module is created)"""
+    sys.path.insert(0, ROOT)
+    if ngpu > 1:
+        os.environ["HQP_MAT_NGPU"] = str(ngpu)
+    from hqp_b200.problem import synth_lqdocp
+    from oracle import refharness
+    refharness.load_plugin(os.path.join(ROOT, "hqp_b200", "lib", "libhqp_ipcuda_plugin.so"))
+    p = synth_lqdocp(20, 10, 300)
+    r = refharness.ips_solve(refharness.RefQP(p), "Mehrotra", "Cuda", 1e-9)
+    q.put((r["iters"], r["result"], r["x"]))
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 CUDA devices")
+def test_reference_ip_solver_through_the_plugin_with_mat_ngpu():
+    """qp_mat_solver Cuda + mat_ngpu 2 under the UNMODIFIED Hqp_IpsMehrotra: same
+    iteration count and solution as with one GPU and as with Hqp_IpLQDOCP.  (The
+    docp example itself fixes its terminal state with general equality rows, which a
+    split horizon does not carry.)"""
+    import multiprocessing as mp
+    from oracle import refharness
+    if not refharness.available():
+        pytest.skip("compiled reference not present")
+    ctx = mp.get_context("spawn")
+    out = []
+    for ngpu in (1, 2):
+        q = ctx.Queue()
+        pr = ctx.Process(target=_plugin_worker, args=(ngpu, q))
+        pr.start()
+        out.append(q.get(timeout=300))
+        pr.join()
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import relerr
+    from hqp_b200.problem import synth_lqdocp
+    ref = refharness.ips_solve(refharness.RefQP(synth_lqdocp(20, 10, 300)), "Mehrotra", "LQDOCP", 1e-9)
+    for it, res, x in out:
+        assert it == ref["iters"] and res == ref["result"] == "optimal"
+        assert relerr(x, ref["x"]) < 1e-8
