@@ -135,6 +135,9 @@ struct hqpcu_handle {
   std::vector<GraphEntry> graphs;
   bool use_graphs = true;
   bool use_hs = true;    // factor tree as a one-sweep suffix scan (HQPCU_HS=0: up/down tree)
+  int hs_final = 0;      // slot offset of the region that holds the finished suffix elements
+  // slot of the element that condenses the whole stage range (exported by a split horizon)
+  int range_slot() const { return d.hs ? hs_final : d.ft.off[d.ft.nlev - 1]; }
   // programmatic dependent launch inside the hot sequences: measured SLOWER at C2
   // (0.845 vs 0.794 ms per unit: early-scheduled dependents hold SM resources), so
   // off unless HQPCU_PDL=1
@@ -362,7 +365,7 @@ static void choose_segments(hqpcu_handle *h, int nseg) {
   choose_seg_warps(h);
   build_tree(d.ft, P, 2);
   d.ft.nel = std::max(d.ft.nel, 2 * P + 2);  // (two ping-pong regions of P+1 slots for the suffix scan)
-  d.hs = (h->use_hs && P > 1 && !h->ranged()) ? 1 : 0;
+  d.hs = (h->use_hs && (P > 1 || h->ranged())) ? 1 : 0;
   // solve hierarchy: up (R steps) + top (P/R) + down (R) sequential chain steps,
   // shortest for R ~ sqrt(P) (measured at P = 435: R = 21 beats 32 by 5 % per step)
   int R = (int)std::ceil(std::sqrt((double)P));
@@ -1007,7 +1010,7 @@ static int launch_eq_factor(hqpcu_handle *h) {
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k3, s, d);        \
   } while (0)
 #define L_CMP(NX_) LAUNCHP(h, elem_compose_kernel<NX_>, gl, LQ_NT2, h->smem_cmp, s, d, l)
-#define L_HS(NX_) LAUNCHP(h, elem_hs_kernel<NX_>, gseg, LQ_NT2, h->smem_cmp, s, d, stride, src, dst, last)
+#define L_HS(NX_) LAUNCHP(h, elem_hs_kernel<NX_>, gseg, LQ_NT2, h->smem_cmp, s, d, stride, src, dst, last, jmax, jfix)
 #define L_TOP(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, dim3(1, d.batch), LQ_NT2, h->smem_k2, s, d, h->ftop(), 1)
 #define L_DWN(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, gl, LQ_NT2, h->smem_k2, s, d, l, 0)
 #define L_PSI(NX_) LAUNCHP(h, psi_compose_kernel<NX_>, gl, LQ_NT2, h->smem_psi, s, d, l, h->psi_chunk)
@@ -1025,15 +1028,26 @@ static int launch_factor_up(hqpcu_handle *h) {
   }
   if (d.P > 1 || h->ranged()) {
     LQ_DISPATCH_NXNU(d.nx, d.nu, L_K1);
-    if (d.hs) {
+    if (d.hs && !h->ranged()) {
       // one sweep: ceil(log2 (P+1)) levels of P concurrent combines (elem_hs_kernel)
       LAUNCHP(h, elem_terminal_kernel, d.batch, 128, 0, s, d);
+      const int jmax = d.P, jfix = -1;
       int lev = 0;
       for (int stride = 1; stride <= d.P; stride <<= 1, lev++) {
         const int src = (lev & 1) * (d.P + 1), dst = ((lev + 1) & 1) * (d.P + 1);
         const int last = (stride << 1) > d.P ? 1 : 0;
         LQ_DISPATCH_NX(d.nx, d.nu, L_HS);
       }
+    } else if (d.hs) {
+      // stage range of a split horizon: the scan without the terminal element (it is
+      // only known after the exchange); suffix 0 = the element of the whole range
+      const int jmax = d.P - 1, jfix = -1, last = 0;
+      int lev = 0;
+      for (int stride = 1; stride < d.P; stride <<= 1, lev++) {
+        const int src = (lev & 1) * (d.P + 1), dst = ((lev + 1) & 1) * (d.P + 1);
+        LQ_DISPATCH_NX(d.nx, d.nu, L_HS);
+      }
+      h->hs_final = (lev & 1) * (d.P + 1);
     } else {
       for (int l = 0; l < h->ftop(); l++) {
         const dim3 gl(d.ft.cnt[l + 1], d.batch);
@@ -1050,6 +1064,13 @@ static int launch_factor_down(hqpcu_handle *h) {
   const LqDev &d = h->d;
   cudaStream_t s = h->stream;
   const dim3 gseg(d.P, d.batch);
+  if (d.hs && h->ranged()) {
+    // the value behind this range is known now: terminal element into slot P, then
+    // ONE level applies it to every suffix -> all segment end values
+    LAUNCHP(h, elem_terminal_kernel, d.batch, 128, 0, s, d);
+    const int stride = 0, src = h->hs_final, dst = h->hs_final, last = 1, jmax = d.P, jfix = d.P;
+    LQ_DISPATCH_NX(d.nx, d.nu, L_HS);
+  }
   if (!d.hs) {  // (suffix-scan mode: every segment's end value is known already)
     LQ_DISPATCH_NX(d.nx, d.nu, L_TOP);
     for (int l = h->ftop() - 1; l >= 0; l--) {
@@ -1513,7 +1534,7 @@ int hqpcu_range_config(hqpcu_handle *h, int has_prev, int has_next) {
   drop_graphs(h);  // the launch sequences depend on the range flags
   h->d.has_prev = has_prev ? 1 : 0;
   h->d.has_next = has_next ? 1 : 0;
-  h->d.hs = (h->use_hs && h->d.P > 1 && !h->ranged()) ? 1 : 0;
+  h->d.hs = (h->use_hs && (h->d.P > 1 || h->ranged())) ? 1 : 0;
   h->factored = false;
   return HQPCU_OK;
 }
@@ -1530,7 +1551,7 @@ int hqpcu_range_factor_begin(hqpcu_handle *h, const double *z, const double *w, 
   return run_graphed(h, {(const void *)(uintptr_t)10, xf}, [&]() {
     int rc = launch_factor_up(h);
     if (rc) return rc;
-    LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(h->d, xf));
+    LAUNCH(h, range_export_factor_kernel, <<<1, 128, 0, h->stream>>>(h->d, xf, h->range_slot()));
     CUL(h);
     return (int)HQPCU_OK;
   });

@@ -460,8 +460,9 @@ __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, 
 // ---------------------------------------------------------------------------
 #define LQ_BIG_KC 16
 #define LQ_BIG_BT 5                                   // DMMA tiles per block side
-#define LQ_BIG_LDS (LQ_BIG_KC + 4)
-#define LQ_BIG_PANEL (LQ_BIG_BT * 8 * LQ_BIG_LDS)     // one panel: 40 rows x 20
+#define LQ_BIG_LDS (LQ_BIG_KC + 4)                    // [row][k] layout: 20 = 4 (mod 8)
+#define LQ_BIG_LDT (LQ_BIG_BT * 8 + 4)                // [k][row] layout: 44 = 12 (mod 16)
+#define LQ_BIG_PANEL (LQ_BIG_BT * 8 * LQ_BIG_LDS)     // one panel: 40 x 20 (>= 16 x 44)
 #define LQ_BIG_STAGE (4 * LQ_BIG_PANEL)               // A, B panels, two buffers
 
 // shared memory of the large-block segment kernels: the staging slices of the
@@ -482,25 +483,70 @@ __device__ __forceinline__ void cp_async_f64(double *dst_smem, const double *src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// panel[r][k] <- X(r0 + r, k0 + k), r < 40, k < KC;  X(i, l) = X[i * xr + l * xc]
+__device__ __forceinline__ void cp_async_f64x2(double *dst_smem, const double *src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+               "r"(sz)
+               : "memory");
+}
+
+// One 40 x KC panel of X(i, l) = X[i * xr + l * xc] (rows r0.., columns k0..) into
+// shared memory, zero-filled outside nrows x Kd.  Two layouts, chosen by the
+// operand's orientation so that the copies run along its contiguous direction:
+//   TR = false: panel[r][k], row stride LQ_BIG_LDS   (k contiguous in memory)
+//   TR = true : panel[k][r], row stride LQ_BIG_LDT   (rows contiguous in memory)
+// vec: 16-byte copies (even strides / extents, 16-byte aligned base); the index
+// arithmetic is incremental -- this loop was 70 % of the instructions of the first
+// version of the large-block kernels (profiles/r02_ncu_full_c4.md).
+template <bool TR>
 __device__ __forceinline__ void big_stage_panel(double *panel, const double *X, int xr, int xc,
-                                                int r0, int nrows, int k0, int Kd, int lane) {
+                                                int r0, int nrows, int k0, int Kd, int lane,
+                                                bool vec) {
   constexpr int R = LQ_BIG_BT * 8, KC = LQ_BIG_KC;
-  if (xr == 1) {
-    // rows contiguous in memory: consecutive lanes take consecutive rows
+  if constexpr (!TR) {
+    if (vec) {
+      // 8 x 16 bytes per row: lane -> (row = lane / 8 + 4 it, pair = lane % 8)
+      const int k = 2 * (lane & 7);
+      const bool kok = k0 + k < Kd;
+      const double *src = X + (size_t)(r0 + (lane >> 3)) * xr + (k0 + k);
+      double *dst = panel + (lane >> 3) * LQ_BIG_LDS + k;
+#pragma unroll
+      for (int it = 0; it < R / 4; it++) {
+        const bool ok = kok && r0 + (lane >> 3) + 4 * it < nrows;
+        cp_async_f64x2(dst, ok ? src : X, ok);
+        src += (size_t)4 * xr;
+        dst += 4 * LQ_BIG_LDS;
+      }
+    } else {
 #pragma unroll 4
-    for (int e = lane; e < R * KC; e += 32) {
-      const int k = e / R, r = e - k * R;
-      const bool ok = r0 + r < nrows && k0 + k < Kd;
-      cp_async_f64(panel + r * LQ_BIG_LDS + k, X + (ok ? (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : 0), ok);
+      for (int e = lane; e < R * KC; e += 32) {
+        const int r = e / KC, k = e % KC;  // (KC is a power of two)
+        const bool ok = r0 + r < nrows && k0 + k < Kd;
+        cp_async_f64(panel + r * LQ_BIG_LDS + k, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
+      }
     }
   } else {
-    // (k contiguous, or a general stride pair): consecutive lanes take consecutive k
+    if (vec) {
+      // 20 x 16 bytes per k: e = lane + 32 it -> (k = e / 20, pair = e % 20), incrementally
+      int k = lane / (R / 2), pr = lane % (R / 2);
+#pragma unroll
+      for (int it = 0; it < KC * (R / 2) / 32; it++) {
+        const bool ok = k0 + k < Kd && r0 + 2 * pr < nrows;
+        cp_async_f64x2(panel + k * LQ_BIG_LDT + 2 * pr,
+                       ok ? X + (size_t)(r0 + 2 * pr) + (size_t)(k0 + k) * xc : X, ok);
+        pr += 32 - (R / 2);  // (+32 elements = +1 k, +12 pairs)
+        k += 1;
+        if (pr >= R / 2) { pr -= R / 2; k += 1; }
+      }
+    } else {
+      int k = lane / R, r = lane % R;
 #pragma unroll 4
-    for (int e = lane; e < R * KC; e += 32) {
-      const int r = e / KC, k = e - r * KC;
-      const bool ok = r0 + r < nrows && k0 + k < Kd;
-      cp_async_f64(panel + r * LQ_BIG_LDS + k, X + (ok ? (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : 0), ok);
+      for (int it = 0; it < KC * R / 32; it++) {
+        const bool ok = k0 + k < Kd && r0 + r < nrows;
+        cp_async_f64(panel + k * LQ_BIG_LDT + r, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
+        r += 32;
+        if (r >= R) { r -= R; k += 1; }
+      }
     }
   }
 }
@@ -514,6 +560,18 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
   double *my = stg + (size_t)(threadIdx.x >> 5) * LQ_BIG_STAGE;
   const int nbi = (M + BS - 1) / BS, nbj = (N + BS - 1) / BS, nb = nbi * nbj;
   const int nchunk = (Kd + KC - 1) / KC;
+  // operand orientation -> panel layout; 16-byte copies where everything is even
+  const bool ta = ar == 1 && ac != 1, tb = bc == 1 && br != 1;
+  const bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  const bool va = al16 && (ta ? (ac % 2 == 0 && M % 2 == 0) : (ac == 1 && ar % 2 == 0 && Kd % 2 == 0));
+  const bool vb = al16 && (tb ? (br % 2 == 0 && N % 2 == 0) : (br == 1 && bc % 2 == 0 && Kd % 2 == 0));
+  auto stage = [&](double *pa_, double *pb_, int i0_, int j0_, int kc0) {
+    if (ta) big_stage_panel<true>(pa_, A, ar, ac, i0_, M, kc0, Kd, lane, va);
+    else big_stage_panel<false>(pa_, A, ar, ac, i0_, M, kc0, Kd, lane, va);
+    // B(l, j) = B[l * br + j * bc]: a panel over "rows" j with k = l
+    if (tb) big_stage_panel<true>(pb_, B, bc, br, j0_, N, kc0, Kd, lane, vb);
+    else big_stage_panel<false>(pb_, B, bc, br, j0_, N, kc0, Kd, lane, vb);
+  };
   for (int u = (warp_log + nwarps - (wofs % nwarps)) % nwarps; u < nb; u += nwarps) {
     const int bi = u / nbj, bj = u - bi * nbj;
     const int i0 = bi * BS, j0 = bj * BS;
@@ -524,9 +582,7 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
     for (int r = 0; r < BT; r++)
 #pragma unroll
       for (int c = 0; c < BT; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
-    // B(l, j) = B[l * br + j * bc]: as a panel over "rows" j with k = l
-    big_stage_panel(my, A, ar, ac, i0, M, 0, Kd, lane);
-    big_stage_panel(my + LQ_BIG_PANEL, B, bc, br, j0, N, 0, Kd, lane);
+    stage(my, my + LQ_BIG_PANEL, i0, j0, 0);
     cp_async_commit();
     for (int c = 0; c < nchunk; c++) {
       double *pa = my + (size_t)(c & 1) * 2 * LQ_BIG_PANEL, *pb = pa + LQ_BIG_PANEL;
@@ -534,17 +590,18 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
       __syncwarp();
       if (c + 1 < nchunk) {  // next chunk into the other buffer while this one is consumed
         double *na = my + (size_t)((c + 1) & 1) * 2 * LQ_BIG_PANEL;
-        big_stage_panel(na, A, ar, ac, i0, M, (c + 1) * KC, Kd, lane);
-        big_stage_panel(na + LQ_BIG_PANEL, B, bc, br, j0, N, (c + 1) * KC, Kd, lane);
+        stage(na, na + LQ_BIG_PANEL, i0, j0, (c + 1) * KC);
         cp_async_commit();
       }
 #pragma unroll
       for (int kk = 0; kk < KC; kk += 4) {
         double af[BT], bf[BT];
 #pragma unroll
-        for (int r = 0; r < BT; r++) af[r] = pa[(r * 8 + g) * LQ_BIG_LDS + kk + t];
+        for (int r = 0; r < BT; r++)
+          af[r] = ta ? pa[(kk + t) * LQ_BIG_LDT + r * 8 + g] : pa[(r * 8 + g) * LQ_BIG_LDS + kk + t];
 #pragma unroll
-        for (int q = 0; q < BT; q++) bf[q] = pb[(q * 8 + g) * LQ_BIG_LDS + kk + t];
+        for (int q = 0; q < BT; q++)
+          bf[q] = tb ? pb[(kk + t) * LQ_BIG_LDT + q * 8 + g] : pb[(q * 8 + g) * LQ_BIG_LDS + kk + t];
 #pragma unroll
         for (int r = 0; r < BT; r++) {
           if (r < nti) {

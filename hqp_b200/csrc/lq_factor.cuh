@@ -552,7 +552,8 @@ __global__ void elem_terminal_kernel(LqDev d) {
   const double *hk = d.hdiag + (size_t)b * d.N + (size_t)d.K * nm;
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     const int r = i / nx, c = i - r * nx;
-    J0[i] = QK[r * nm + c] + (r == c ? hk[r] : 0.0);
+    // (horizon split: plus the value of everything behind this range)
+    J0[i] = QK[r * nm + c] + (r == c ? hk[r] : 0.0) + (d.has_next ? d.Vext[i] : 0.0);
     d.segA[(eb + d.P) * n2 + i] = 0.0;
     d.segC[(eb + d.P) * n2 + i] = 0.0;
     d.segA[(eb + 2 * d.P + 1) * n2 + i] = 0.0;
@@ -591,9 +592,14 @@ __global__ void elem_terminal_kernel(LqDev d) {
 // Elements ping-pong between two regions of P+1 slots (src, dst: slot offsets).
 // last != 0: also segVb[s-1] <- J.     grid (P, batch)
 // ---------------------------------------------------------------------------
+// jmax: last slot that takes part (P with the terminal element in the scan, P-1
+// without); jfix >= 0: every element is combined with slot jfix instead of
+// s + stride (a stage range of a split horizon learns its terminal value only
+// after the exchange: the scan runs without it, then ONE more level applies the
+// terminal element in slot P to all suffixes at once).
 template <int NX>
 __global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, int src, int dst,
-                                                      int last) {
+                                                      int last, int jmax, int jfix) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx, n3 = 3 * nx;
@@ -615,8 +621,8 @@ __global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, in
   if (threadIdx.x == 0) st_s = 0;
   const size_t eb = (size_t)b * d.ft.nel;
   const size_t oi = (eb + src + s) * n2, oo = (eb + dst + s) * n2;
-  const int j = s + stride;
-  if (j > d.P) {
+  const int j = jfix >= 0 ? jfix : s + stride;
+  if (j > jmax) {
     // already the composition up to the end of the horizon
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
       const double jv = d.segJ[oi + i];

@@ -14,9 +14,11 @@
 // xf[0..3][nx*nx] <- A, C, J of the single top element of the factor tree and the
 // local terminal block Q_K + C_K'(z/w)C_K (zero when the caller passed none).
 // One CTA.
-__global__ void range_export_factor_kernel(LqDev d, double *xf) {
+// slot: where the element of the whole range lives (top of the binary tree, or
+// suffix 0 of the suffix scan).
+__global__ void range_export_factor_kernel(LqDev d, double *xf, int slot) {
   const int nx = d.nx, nm = d.nm, n2 = nx * nx;
-  const size_t o = (size_t)d.ft.off[d.ft.nlev - 1] * n2;  // batch == 1
+  const size_t o = (size_t)slot * n2;  // batch == 1
   for (int i = threadIdx.x; i < n2; i += blockDim.x) {
     xf[i] = d.segA[o + i];
     xf[n2 + i] = d.segC[o + i];

@@ -39,6 +39,9 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "sm__inst_executed_pipe_fp64.sum", "smsp__inst_executed_op_dmma.sum",
+        "sm__inst_executed_pipe_lsu.sum",
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
