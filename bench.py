@@ -21,7 +21,7 @@ Workloads (BASELINE.json configs):
        N > 1: strong scaling, the horizon split into N contiguous stage ranges
   c5s  nx=40 nu=10 K=100,000 host-generated slice of the same shape
 The default line (workload c2) carries the other configurations as sub-objects
-(`c5`, and at N = 1 `c3`) unless --no-extra is given.
+(`c5`, and at N = 1 `c4` and `c3`) unless --no-extra is given.
 
 Multi-GPU: one process per GPU (torchrun); the horizon split lives in
 libhqpcuda.so (hqpcu_comm_init): NCCL all-gathers of the boundary elements /
@@ -682,6 +682,13 @@ def run_ours(args):
                 raise
             extra["c5"] = {"error": str(ex)}
         if world == 1:
+            try:
+                sub = run_workload(args, "c4", 3, 3, group, extras=False)
+                cb = time_reference(WORKLOADS["c4"], 2, 1, max_stages=100)
+                sub["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                extra["c4"] = sub
+            except Exception as ex:
+                extra["c4"] = {"error": str(ex)}
             try:
                 sub = run_workload(args, "c3", max(3, min(args.steps, 10)), 3, group, extras=False)
                 cb = time_reference(WORKLOADS["c3"], 3, 1, max_stages=WORKLOADS["c3"]["K"])

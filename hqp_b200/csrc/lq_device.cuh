@@ -458,6 +458,9 @@ __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, 
 // conflict-free fragment reads (see lq_pad4).
 // stg: LQ_BIG_STAGE doubles of shared memory per PHYSICAL warp of the CTA.
 // ---------------------------------------------------------------------------
+#ifndef LQ_BIG_VEC
+#define LQ_BIG_VEC 0
+#endif
 #define LQ_BIG_KC 16
 #define LQ_BIG_BT 5                                   // DMMA tiles per block side
 #define LQ_BIG_LDS (LQ_BIG_KC + 4)                    // [row][k] layout: 20 = 4 (mod 8)
@@ -562,7 +565,10 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
   const int nchunk = (Kd + KC - 1) / KC;
   // operand orientation -> panel layout; 16-byte copies where everything is even
   const bool ta = ar == 1 && ac != 1, tb = bc == 1 && br != 1;
-  const bool al16 = ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
+  // (16-byte cp.async exists as .cg only: it bypasses L1, where the warps of a CTA
+  //  share each other's panels -- measured slower than 8-byte .ca copies at nx = 200,
+  //  K1 46 vs 38 ms; kept behind LQ_BIG_VEC for shapes without that reuse)
+  const bool al16 = LQ_BIG_VEC && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
   const bool va = al16 && (ta ? (ac % 2 == 0 && M % 2 == 0) : (ac == 1 && ar % 2 == 0 && Kd % 2 == 0));
   const bool vb = al16 && (tb ? (br % 2 == 0 && N % 2 == 0) : (br == 1 && bc % 2 == 0 && Kd % 2 == 0));
   auto stage = [&](double *pa_, double *pb_, int i0_, int j0_, int kc0) {
