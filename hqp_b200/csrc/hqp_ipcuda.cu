@@ -113,6 +113,7 @@ struct hqpcu_handle {
   double *res_dev = nullptr;
   double *res_host = nullptr;  // pinned
   int *status_host = nullptr;  // pinned
+  int status_seen = 0;         // status word as of the last residual read-back
   bool factored = false;
   // general stage equality rows (block elimination on top of the factor)
   LqEq q;
@@ -1414,8 +1415,12 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
     if (rc) return rc;
   }
   CU(cudaMemcpyAsync(h->res_host, h->res_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  // (the status word of the factor rides along: callers that enqueue factor + solve
+  //  back to back read both with this one synchronisation, factor_solve)
+  CU(cudaMemcpyAsync(h->status_host, h->d.status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   CU(cudaStreamSynchronize(h->stream));
   *res = *h->res_host;
+  h->status_seen = *h->status_host;
   return HQPCU_OK;
 }
 
@@ -1518,6 +1523,35 @@ int hqpcu_solve(hqpcu_handle *h, double eps, const double *r1, const double *r2,
                   h->u_dw, res, nsteps);
   if (rc) return rc;
   return d2h_sol(h, dx, dy, dz, dw);
+}
+
+// Factor with (z, w) already on the device, then one refined solve; the factor's
+// status is read with the solve's first residual -- one synchronisation for both
+// (the IP loops call this once per iteration).  Rare paths: a singular block
+// returns HQPCU_E_SING (the solve ran on garbage, harmlessly); a non-positive pivot
+// at a segment end repeats factor and solve as the sequential sweep.
+static int factor_solve(hqpcu_handle *h, const double *z, const double *w, double eps,
+                        const double *r1, const double *r2, const double *r3, const double *r4,
+                        double *dx, double *dy, double *dz, double *dw, double *res) {
+  int rc = factor_impl(h, z, w, cudaMemcpyDeviceToDevice);
+  if (rc) return rc;
+  rc = solve_core(h, eps, r1, r2, r3, r4, dx, dy, dz, dw, res, nullptr);
+  if (rc) return rc;
+  const int st = h->status_seen;
+  if (st & LQ_FLAG_SING) return HQPCU_E_SING;
+  if (st & LQ_FLAG_NOTPD) {
+    if (h->ranged()) return HQPCU_E_NOTPD;
+    if (h->d.P > 1) {
+      choose_segments(h, 1);
+      h->demoted = true;
+      if ((rc = launch_factor(h))) return rc;
+      rc = read_status(h);
+      if (rc == HQPCU_E_NOTPD) rc = HQPCU_OK;
+      if (rc) return rc;
+      return solve_core(h, eps, r1, r2, r3, r4, dx, dy, dz, dw, res, nullptr);
+    }
+  }
+  return HQPCU_OK;
 }
 
 // ------------------------------------------------------ horizon split (8e) --

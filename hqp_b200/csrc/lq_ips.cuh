@@ -254,22 +254,46 @@ __global__ void ips_ratio_kernel(int m, const double *__restrict__ z, const doub
                                  const double *__restrict__ dz, const double *__restrict__ dw,
                                  double *out) {
   double zmin = __longlong_as_double(0x7ff0000000000000LL), wmin = zmin, t = 0.0;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)m;
-       i += (size_t)gridDim.x * blockDim.x) {
-    const double zi = z[i], wi = w[i], a = dz[i], b = dw[i];
+  auto one = [&](double zi, double wi, double a, double b) {
     if (a < 0.0) zmin = fmin(zmin, -zi / a);
     if (b < 0.0) wmin = fmin(wmin, -wi / b);
     if (a * b > 0.0) t = fmax(t, a * b / zi / wi);
+  };
+  // 128-bit loads over the even part of the vectors (cudaMalloc'ed: 256-byte aligned)
+  const size_t m2 = (size_t)m >> 1;
+  const double2 *z2 = reinterpret_cast<const double2 *>(z), *w2 = reinterpret_cast<const double2 *>(w);
+  const double2 *a2 = reinterpret_cast<const double2 *>(dz), *b2 = reinterpret_cast<const double2 *>(dw);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m2;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const double2 zi = z2[i], wi = w2[i], a = a2[i], b = b2[i];
+    one(zi.x, wi.x, a.x, b.x);
+    one(zi.y, wi.y, a.y, b.y);
   }
+  if ((m & 1) && blockIdx.x == 0 && threadIdx.x == 0) one(z[m - 1], w[m - 1], dz[m - 1], dw[m - 1]);
   for (int o = 16; o > 0; o >>= 1) {
     zmin = fmin(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
     wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
     t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
   }
-  if ((threadIdx.x & 31) == 0) {
-    atomic_min_pos(out + 0, zmin);
-    atomic_min_pos(out + 1, wmin);
-    atomic_max_nonneg(out + 2, t);
+  // one set of atomics per CTA, not per warp (three hot addresses)
+  __shared__ double red[3][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) { red[0][warp] = zmin; red[1][warp] = wmin; red[2][warp] = t; }
+  __syncthreads();
+  if (warp == 0) {
+    zmin = lane < nw ? red[0][lane] : __longlong_as_double(0x7ff0000000000000LL);
+    wmin = lane < nw ? red[1][lane] : __longlong_as_double(0x7ff0000000000000LL);
+    t = lane < nw ? red[2][lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      zmin = fmin(zmin, __shfl_xor_sync(0xffffffffu, zmin, o));
+      wmin = fmin(wmin, __shfl_xor_sync(0xffffffffu, wmin, o));
+      t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    }
+    if (lane == 0) {
+      atomic_min_pos(out + 0, zmin);
+      atomic_min_pos(out + 1, wmin);
+      atomic_max_nonneg(out + 2, t);
+    }
   }
 }
 
@@ -358,10 +382,12 @@ __global__ void ips_corrector_rhs_kernel(int m, const double *__restrict__ z,
 }
 
 // partial[blk][0] = sum (z + a dz)(w + a dw)   (mu_pl, :651-653)
-__global__ void ips_mupl_kernel(int m, double alpha, const double *__restrict__ z,
+// alpha = min(mins[0], mins[1]) is read from the device scalars the ratio test left.
+__global__ void ips_mupl_kernel(int m, const double *__restrict__ mins, const double *__restrict__ z,
                                 const double *__restrict__ w, const double *__restrict__ dz,
                                 const double *__restrict__ dw, double *partial) {
   __shared__ double red[32];
+  const double alpha = fmin(mins[0], mins[1]);
   double s = 0.0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)m;
        i += (size_t)gridDim.x * blockDim.x)
