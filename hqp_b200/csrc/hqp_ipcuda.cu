@@ -1400,12 +1400,12 @@ static int launch_residuum(hqpcu_handle *h, const double *r1, const double *r2, 
     if (rc) return rc;
   }
   CU(cudaMemsetAsync(h->res_dev, 0, sizeof(double), h->stream));
-  const dim3 gall(d.K + 1, d.batch);
-  const size_t sv = (size_t)(d.nm + d.nx + 2) * sizeof(double);
+  const dim3 gall((d.K + LQ_RES_WPB) / LQ_RES_WPB, d.batch);
+  const size_t sv = (size_t)LQ_RES_WPB * (d.nm + d.nx) * sizeof(double);
   if (h->q.n_eq)
     LAUNCH(h, eq_residuum_kernel, <<<1, 256, 0, h->stream>>>(d, h->q, r2, dx, dy,
                                                               keep ? h->t2 : nullptr, h->res_dev));
-  LAUNCH(h, residuum_kernel, <<<gall, h->thr_stage, sv, h->stream>>>(
+  LAUNCH(h, residuum_kernel, <<<gall, 32 * LQ_RES_WPB, sv, h->stream>>>(
       d, r1, r2, r3, r4, dx, dy, dz, dw, keep ? h->t1 : nullptr, keep ? h->t2 : nullptr,
       keep ? h->t3 : nullptr, keep ? h->t4 : nullptr, h->res_dev,
       h->q.n_eq ? h->q.ety : nullptr));

@@ -43,42 +43,45 @@ __device__ __forceinline__ double block_reduce(double v, bool is_max, double *re
 //   r3 = -(C x + d - w)            r4 = -z w
 // partial[blk][0..7] = x'Qx, x'c, y'b, z'd, z'w, |r1|inf, |r2|inf, |r3|inf
 // ety = E' y|eq (general equality rows; NULL if none).
-// grid (K+1), block 64
+// grid ceil((K+1) / IPS_RES_WPB), block 32 * IPS_RES_WPB, smem IPS_RES_WPB (nm + 2 nx) doubles
 // ---------------------------------------------------------------------------
-__global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, double *r3,
-                                    double *r4, const double *__restrict__ ety,
-                                    double *partial) {
+#define IPS_RES_WPB 4  // stages (warps) per CTA of the residual pass
+__global__ void __launch_bounds__(32 * IPS_RES_WPB)
+ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, double *r3, double *r4,
+                    const double *__restrict__ ety, double *partial) {
+  // One WARP per stage (round 1: one 64-thread CTA per stage with eight block
+  // reductions, 16 CTA barriers -- 82 us at C2, launch- and barrier-bound): no CTA
+  // barrier at all, the eight partial sums / maxima of the stage by warp shuffles.
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
-  double *xs = reinterpret_cast<double *>(smem_raw);  // nm
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *xs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (nm + 2 * nx);  // nm
   double *xn = xs + nm;                                // nx : x_{k+1}
   double *yk = xn + nx;                                // nx : y dynamics rows k
-  __shared__ double red[32];
-  const int k = blockIdx.x;
+  const int k = blockIdx.x * IPS_RES_WPB + warp;
+  __shared__ double red[IPS_RES_WPB][IPS_NQ];
+  double xQx = 0, xc = 0, yb = 0, zd = 0, zw = 0, n1 = 0, n2 = 0, n3 = 0;
   const int dk = (k < d.K) ? nm : nx;
   const size_t xo = (size_t)k * nm;
   if (k == d.K && d.has_next) {
     // horizon split: the trailing block duplicates the next range's x_0; its rows
     // (and its share of every reduction) belong to that rank
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) r1[xo + i] = 0.0;
-    if (threadIdx.x < IPS_NQ) partial[(size_t)blockIdx.x * IPS_NQ + threadIdx.x] = 0.0;
-    return;
-  }
+    for (int i = lane; i < nx; i += 32) r1[xo + i] = 0.0;
+  } else if (k <= d.K) {
   const double *xnext = (d.has_next && d.halo && k == d.K - 1)
                             ? d.halo + (size_t)(d.rank + 1) * 2 * nx : nullptr;
   const double *yprev = (d.has_prev && d.halo && k == 0)
                             ? d.halo + (size_t)(d.rank - 1) * 2 * nx + nx : nullptr;
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) xs[i] = v.x[xo + i];
+  for (int i = lane; i < dk; i += 32) xs[i] = v.x[xo + i];
   if (k < d.K)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+    for (int i = lane; i < nx; i += 32) {
       xn[i] = xnext ? xnext[i] : v.x[xo + nm + i];
       yk[i] = v.y[(size_t)k * nx + i];
     }
-  __syncthreads();
-  double xQx = 0, xc = 0, yb = 0, zd = 0, zw = 0, n1 = 0, n2 = 0, n3 = 0;
+  __syncwarp();
   const double *Qk = d.Q + (size_t)k * nm * nm;
   const double *cv = d.cval;
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) {
+  for (int i = lane; i < dk; i += 32) {
     double qx = 0.0;
 #pragma unroll 10
     for (int l = 0; l < dk; l++) qx = fma(Qk[l * nm + i], xs[l], qx);
@@ -110,7 +113,7 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
   }
   if (k < d.K) {
     const double *fx = d.fx + (size_t)k * nx * nx, *fu = d.fu + (size_t)k * nx * nu;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+    for (int i = lane; i < nx; i += 32) {
       double s = -xn[i];
 #pragma unroll 10
       for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
@@ -124,14 +127,14 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
     }
   }
   if (k == 0 && d.fixed_x0)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
+    for (int i = lane; i < nx; i += 32) {
       const size_t ro = (size_t)d.K * nx + i;
       const double t = -(xs[i] + v.b[ro]);
       r2[ro] = t;
       yb = fma(v.y[ro], v.b[ro], yb);
       n2 = fmax(n2, fabs(t));
     }
-  for (int rr = d.srow_ptr[k] + threadIdx.x; rr < d.srow_ptr[k + 1]; rr += blockDim.x) {
+  for (int rr = d.srow_ptr[k] + lane; rr < d.srow_ptr[k + 1]; rr += 32) {
     const int r = d.srow[rr];
     double s = 0.0;
     for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
@@ -144,16 +147,29 @@ __global__ void ips_residual_kernel(LqDev d, IpsVec v, double *r1, double *r2, d
     zw = fma(zr, wr, zw);
     n3 = fmax(n3, fabs(t));
   }
-  double *out = partial + (size_t)blockIdx.x * IPS_NQ;
-  double q;
-  q = block_reduce(xQx, false, red); if (threadIdx.x == 0) out[0] = q;
-  q = block_reduce(xc, false, red);  if (threadIdx.x == 0) out[1] = q;
-  q = block_reduce(yb, false, red);  if (threadIdx.x == 0) out[2] = q;
-  q = block_reduce(zd, false, red);  if (threadIdx.x == 0) out[3] = q;
-  q = block_reduce(zw, false, red);  if (threadIdx.x == 0) out[4] = q;
-  q = block_reduce(n1, true, red);   if (threadIdx.x == 0) out[5] = q;
-  q = block_reduce(n2, true, red);   if (threadIdx.x == 0) out[6] = q;
-  q = block_reduce(n3, true, red);   if (threadIdx.x == 0) out[7] = q;
+  for (int o = 16; o > 0; o >>= 1) {
+    xQx += __shfl_xor_sync(0xffffffffu, xQx, o);
+    xc += __shfl_xor_sync(0xffffffffu, xc, o);
+    yb += __shfl_xor_sync(0xffffffffu, yb, o);
+    zd += __shfl_xor_sync(0xffffffffu, zd, o);
+    zw += __shfl_xor_sync(0xffffffffu, zw, o);
+    n1 = fmax(n1, __shfl_xor_sync(0xffffffffu, n1, o));
+    n2 = fmax(n2, __shfl_xor_sync(0xffffffffu, n2, o));
+    n3 = fmax(n3, __shfl_xor_sync(0xffffffffu, n3, o));
+  }
+  }  // (stage of this warp)
+  // one partial row per CTA: the stages of its warps combined in warp order
+  if (lane == 0) {
+    red[warp][0] = xQx; red[warp][1] = xc; red[warp][2] = yb; red[warp][3] = zd;
+    red[warp][4] = zw;  red[warp][5] = n1; red[warp][6] = n2; red[warp][7] = n3;
+  }
+  __syncthreads();
+  if (threadIdx.x < IPS_NQ) {
+    const int j = threadIdx.x;
+    double a = red[0][j];
+    for (int w2 = 1; w2 < IPS_RES_WPB; w2++) a = (j >= 5) ? fmax(a, red[w2][j]) : a + red[w2][j];
+    partial[(size_t)blockIdx.x * IPS_NQ + j] = a;
+  }
 }
 
 // general equality rows of the residual pass; one CTA.  Writes r2|eq, ety = E'y|eq

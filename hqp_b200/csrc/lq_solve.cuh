@@ -717,123 +717,128 @@ __global__ void __launch_bounds__(32 * LQ_WPB) solve_post_kernel(
 }
 
 // ---- residuum ----------------------------------------------------------------
-// Hqp_IpMatrix::residuum (hqp/Hqp_IpMatrix.C:131-178); grid (K+1, batch).
+// Hqp_IpMatrix::residuum (hqp/Hqp_IpMatrix.C:131-178);
+// grid (ceil((K+1)/LQ_RES_WPB), batch), block 32 * LQ_RES_WPB, smem LQ_RES_WPB (nm + nx) doubles.
 // Writes the four residual vectors to t1..t4 (may be NULL) and atomically
 // maxes their inf-norm into *res (must be zeroed before the launch).
-__global__ void residuum_kernel(LqDev d, const double *__restrict__ r1,
-                                const double *__restrict__ r2, const double *__restrict__ r3,
-                                const double *__restrict__ r4, const double *__restrict__ dx,
-                                const double *__restrict__ dy, const double *__restrict__ dz,
-                                const double *__restrict__ dw, double *t1, double *t2,
-                                double *t3, double *t4, double *res,
-                                const double *__restrict__ ety) {
+#define LQ_RES_WPB 4  // stages (warps) per CTA
+__global__ void __launch_bounds__(32 * LQ_RES_WPB)
+residuum_kernel(LqDev d, const double *__restrict__ r1, const double *__restrict__ r2,
+                const double *__restrict__ r3, const double *__restrict__ r4,
+                const double *__restrict__ dx, const double *__restrict__ dy,
+                const double *__restrict__ dz, const double *__restrict__ dw, double *t1,
+                double *t2, double *t3, double *t4, double *res, const double *__restrict__ ety) {
+  // one WARP per stage (round 1: one small CTA per stage -- CTA turnover, not
+  // bandwidth, set its 55 us at C2); one atomic max per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = d.nx, nu = d.nu, nm = d.nm;
-  double *xs = reinterpret_cast<double *>(smem_raw);  // nm: dx stage k
-  double *yk = xs + nm;                                // nx: dy dynamics rows k
-  __shared__ double red[32];
-  const int k = blockIdx.x, b = blockIdx.y;
-  const int dk = (k < d.K) ? nm : nx;
-  const size_t xo = (size_t)b * d.N + (size_t)k * nm;
-  const size_t yo = (size_t)b * d.me;
-  if (k == d.K && d.has_next) {
-    // horizon split: the trailing state block is the next range's x_0 -- its rows
-    // belong to that rank
-    if (t1)
-      for (int i = threadIdx.x; i < nx; i += blockDim.x) t1[xo + i] = 0.0;
-    return;
-  }
-  // state after the last local stage / multiplier before the first: from the
-  // neighbouring ranges when the horizon is split
-  const double *xnext = (d.has_next && d.halo && k == d.K - 1)
-                            ? d.halo + (size_t)(d.rank + 1) * 2 * nx : nullptr;
-  const double *yprev = (d.has_prev && d.halo && k == 0)
-                            ? d.halo + (size_t)(d.rank - 1) * 2 * nx + nx : nullptr;
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) xs[i] = dx[xo + i];
-  if (k < d.K)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) yk[i] = dy[yo + (size_t)k * nx + i];
-  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *xs = reinterpret_cast<double *>(smem_raw) + (size_t)warp * (nm + nx);  // nm: dx stage k
+  double *yk = xs + nm;                                                        // nx: dy dynamics rows k
+  __shared__ double red[LQ_RES_WPB];
+  const int k = blockIdx.x * LQ_RES_WPB + warp, b = blockIdx.y;
   double mx = 0.0;
   bool bad = false;  // NaN seen
-  const double *Qk = d.Q + ((size_t)b * (d.K + 1) + k) * nm * nm;
-  const double *cv = d.cval + (size_t)b * d.nnz;
-  const size_t ks = (size_t)b * d.K + k;
-  // t1 = r1 + Q dx - A' dy - C' dz, rows of stage k
-  for (int i = threadIdx.x; i < dk; i += blockDim.x) {
-    double s = r1[xo + i];
+  if (k <= d.K) {
+    const int dk = (k < d.K) ? nm : nx;
+    const size_t xo = (size_t)b * d.N + (size_t)k * nm;
+    const size_t yo = (size_t)b * d.me;
+    if (k == d.K && d.has_next) {
+      // horizon split: the trailing state block is the next range's x_0 -- its rows
+      // belong to that rank
+      if (t1)
+        for (int i = lane; i < nx; i += 32) t1[xo + i] = 0.0;
+    } else {
+      // state after the last local stage / multiplier before the first: from the
+      // neighbouring ranges when the horizon is split
+      const double *xnext = (d.has_next && d.halo && k == d.K - 1)
+                                ? d.halo + (size_t)(d.rank + 1) * 2 * nx : nullptr;
+      const double *yprev = (d.has_prev && d.halo && k == 0)
+                                ? d.halo + (size_t)(d.rank - 1) * 2 * nx + nx : nullptr;
+      for (int i = lane; i < dk; i += 32) xs[i] = dx[xo + i];
+      if (k < d.K)
+        for (int i = lane; i < nx; i += 32) yk[i] = dy[yo + (size_t)k * nx + i];
+      __syncwarp();
+      const double *Qk = d.Q + ((size_t)b * (d.K + 1) + k) * nm * nm;
+      const double *cv = d.cval + (size_t)b * d.nnz;
+      const size_t ks = (size_t)b * d.K + k;
+      // t1 = r1 + Q dx - A' dy - C' dz, rows of stage k
+      for (int i = lane; i < dk; i += 32) {
+        double s = r1[xo + i];
 #pragma unroll 10
-    for (int l = 0; l < dk; l++) s = fma(Qk[l * nm + i], xs[l], s);  // Q symmetric
-    if (k < d.K) {
-      if (i < nx) {
-        const double *fx = d.fx + ks * nx * nx;
+        for (int l = 0; l < dk; l++) s = fma(Qk[l * nm + i], xs[l], s);  // Q symmetric
+        if (k < d.K) {
+          if (i < nx) {
+            const double *fx = d.fx + ks * nx * nx;
 #pragma unroll 10
-        for (int l = 0; l < nx; l++) s = fma(-fx[l * nx + i], yk[l], s);
-      } else {
-        const double *fu = d.fu + ks * nx * nu;
+            for (int l = 0; l < nx; l++) s = fma(-fx[l * nx + i], yk[l], s);
+          } else {
+            const double *fu = d.fu + ks * nx * nu;
 #pragma unroll 10
-        for (int l = 0; l < nx; l++) s = fma(-fu[l * nu + (i - nx)], yk[l], s);
+            for (int l = 0; l < nx; l++) s = fma(-fu[l * nu + (i - nx)], yk[l], s);
+          }
+        }
+        if (i < nx) {
+          if (k > 0) s += dy[yo + (size_t)(k - 1) * nx + i];  // -(-I)' dy_{k-1}
+          else if (d.fixed_x0) s -= dy[yo + (size_t)d.K * nx + i];
+          else if (yprev) s += yprev[i];
+        }
+        const int gv = k * nm + i;
+        for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++)
+          s = fma(-cv[d.vcol_nz[e]], dz[(size_t)b * d.m + d.vcol_row[e]], s);
+        if (ety) s -= ety[xo + i];  // general equality rows (batch == 1)
+        if (t1) t1[xo + i] = s;
+        mx = fmax(mx, fabs(s));
+        bad |= (s != s);
+      }
+      // t2 = r2 - A dx, dynamics rows of stage k (+ x0 rows with stage 0)
+      if (k < d.K) {
+        const double *fx = d.fx + ks * nx * nx, *fu = d.fu + ks * nx * nu;
+        for (int i = lane; i < nx; i += 32) {
+          double s = xnext ? -xnext[i] : -dx[xo + nm + i];
+#pragma unroll 10
+          for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
+#pragma unroll 10
+          for (int l = 0; l < nu; l++) s = fma(fu[i * nu + l], xs[nx + l], s);
+          const double t = r2[yo + (size_t)k * nx + i] - s;
+          if (t2) t2[yo + (size_t)k * nx + i] = t;
+          mx = fmax(mx, fabs(t));
+          bad |= (t != t);
+        }
+      }
+      if (k == 0 && d.fixed_x0)
+        for (int i = lane; i < nx; i += 32) {
+          const double t = r2[yo + (size_t)d.K * nx + i] - xs[i];
+          if (t2) t2[yo + (size_t)d.K * nx + i] = t;
+          mx = fmax(mx, fabs(t));
+          bad |= (t != t);
+        }
+      // t3 = r3 - (C dx - dw) ; t4 = r4 - (z dw + w dz), rows of stage k
+      for (int rr = d.srow_ptr[k] + lane; rr < d.srow_ptr[k + 1]; rr += 32) {
+        const int r = d.srow[rr];
+        double s = 0.0;
+        for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
+          s = fma(cv[e], xs[d.ineq_lcol[e]], s);
+        const size_t ro = (size_t)b * d.m + r;
+        const double a3 = r3[ro] - (s - dw[ro]);
+        const double a4 = r4[ro] - (d.z[ro] * dw[ro] + d.w[ro] * dz[ro]);
+        if (t3) t3[ro] = a3;
+        if (t4) t4[ro] = a4;
+        mx = fmax(mx, fmax(fabs(a3), fabs(a4)));
+        bad |= (a3 != a3) | (a4 != a4);
       }
     }
-    if (i < nx) {
-      if (k > 0) s += dy[yo + (size_t)(k - 1) * nx + i];  // -(-I)' dy_{k-1}
-      else if (d.fixed_x0) s -= dy[yo + (size_t)d.K * nx + i];
-      else if (yprev) s += yprev[i];
-    }
-    const int gv = k * nm + i;
-    for (int e = d.vcol_ptr[gv]; e < d.vcol_ptr[gv + 1]; e++)
-      s = fma(-cv[d.vcol_nz[e]], dz[(size_t)b * d.m + d.vcol_row[e]], s);
-    if (ety) s -= ety[xo + i];  // general equality rows (batch == 1)
-    if (t1) t1[xo + i] = s;
-    mx = fmax(mx, fabs(s));
-    bad |= (s != s);
-  }
-  // t2 = r2 - A dx, dynamics rows of stage k (+ x0 rows with stage 0)
-  if (k < d.K) {
-    const double *fx = d.fx + ks * nx * nx, *fu = d.fu + ks * nx * nu;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      double s = xnext ? -xnext[i] : -dx[xo + nm + i];
-#pragma unroll 10
-      for (int l = 0; l < nx; l++) s = fma(fx[i * nx + l], xs[l], s);
-#pragma unroll 10
-      for (int l = 0; l < nu; l++) s = fma(fu[i * nu + l], xs[nx + l], s);
-      const double t = r2[yo + (size_t)k * nx + i] - s;
-      if (t2) t2[yo + (size_t)k * nx + i] = t;
-      mx = fmax(mx, fabs(t));
-      bad |= (t != t);
-    }
-  }
-  if (k == 0 && d.fixed_x0)
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) {
-      const double t = r2[yo + (size_t)d.K * nx + i] - xs[i];
-      if (t2) t2[yo + (size_t)d.K * nx + i] = t;
-      mx = fmax(mx, fabs(t));
-      bad |= (t != t);
-    }
-  // t3 = r3 - (C dx - dw) ; t4 = r4 - (z dw + w dz), rows of stage k
-  for (int rr = d.srow_ptr[k] + threadIdx.x; rr < d.srow_ptr[k + 1]; rr += blockDim.x) {
-    const int r = d.srow[rr];
-    double s = 0.0;
-    for (int e = d.ineq_ptr[r]; e < d.ineq_ptr[r + 1]; e++)
-      s = fma(cv[e], xs[d.ineq_lcol[e]], s);
-    const size_t ro = (size_t)b * d.m + r;
-    const double a3 = r3[ro] - (s - dw[ro]);
-    const double a4 = r4[ro] - (d.z[ro] * dw[ro] + d.w[ro] * dz[ro]);
-    if (t3) t3[ro] = a3;
-    if (t4) t4[ro] = a4;
-    mx = fmax(mx, fmax(fabs(a3), fabs(a4)));
-    bad |= (a3 != a3) | (a4 != a4);
   }
   if (bad) mx = __longlong_as_double(0x7ff8000000000000LL);
-  // block max; NaN is propagated explicitly (fmax would drop it)
+  // warp, then CTA max; NaN is propagated explicitly (fmax would drop it)
   for (int o = 16; o > 0; o >>= 1) {
     const double other = __shfl_xor_sync(0xffffffffu, mx, o);
     mx = (mx != mx) ? mx : ((other != other) ? other : fmax(mx, other));
   }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  if (lane == 0) red[warp] = mx;
   __syncthreads();
   if (threadIdx.x == 0) {
-    const int nw = (blockDim.x + 31) >> 5;
-    for (int i = 1; i < nw; i++) {
+    for (int i = 1; i < LQ_RES_WPB; i++) {
       const double other = red[i];
       mx = (mx != mx) ? mx : ((other != other) ? other : fmax(mx, other));
     }
