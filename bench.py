@@ -407,7 +407,14 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
         torch.cuda.synchronize()
 
     # ---- warm-up ---------------------------------------------------------
-    for _ in range(warmup):
+    # (clocks are sampled by rank 0 only, from before the warm-up until after the e2e
+    #  loops: the timed region of a 0.7 ms unit is shorter than nvidia-smi's period)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # a split horizon gets a few extra untimed units: the first replays of graphs
+    # that contain NCCL nodes still set up channels
+    for _ in range(warmup + (5 if world > 1 else 0)):
         flush.zero_()
         unit_dev()
     st = eng.sync_status()
@@ -415,8 +422,6 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
         raise RuntimeError(f"factor status {st}")
 
     # ---- timed region: device-resident inputs --------------------------------
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
     launches0 = eng.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -430,7 +435,6 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
     gpu_launches = eng.launches - launches0
     ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     ms_step = float(np.mean(ms))
-    clocks = sampler.stop()
 
     # ---- correctness of what was timed: refined solve, KKT residual (max over the
     # ranks, all-reduced inside the library) -- asserted before anything is printed
@@ -485,6 +489,7 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
         barrier()
         del hp, ho
 
+    clocks = sampler.stop() if sampler else None
     # ---- per-kernel CUDA-event times of the same unit (roofline section) ------
     eng.profile(True)
     nprof = min(steps, 5)

@@ -44,11 +44,23 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
   void build_value_map(const Hqp_Program *qp);
   std::vector<double> _r2p, _dyp; ///< permuted copies when _rowmap is not the identity
   bool _identity_rows;
+  // non-uniform stage dimensions (Hqp_IpLQDOCP::Get_Dim handles _nk[k], _mk[k] per
+  // stage, hqp/Hqp_IpLQDOCP.C:201-287): every stage is padded to the largest nx / nu
+  // with decoupled unit blocks (identity Hessian, zero dynamics), which leaves the
+  // solution of the original variables unchanged; _xmap: variable -> padded slot
+  bool _padded;
+  int _n_abi, _me_abi;            ///< vector lengths on the device side of the ABI
+  std::vector<int> _xmap;
+  std::vector<double> _r1p, _dxp; ///< padded copies of x-like vectors
+  std::vector<long long> _pad_diag; ///< slab positions of the padded diagonal entries of Q
+  std::vector<int> _xoff, _nxs, _dyn0, _vstage; ///< stage geometry of the QP's own layout
 
   void free_handle();
   void check(int status, const char *where);
   const double *pack_r2(const VEC *r2);
   void unpack_dy(VEC *dy);
+  const double *pack_r1(const VEC *r1);
+  void unpack_dx(VEC *dx);
 
  public:
   Hqp_IpCuda();
@@ -73,6 +85,14 @@ class Hqp_IpCuda : public Hqp_IpMatrix {
   hqpcu_handle *handle() { return _h; }
   bool identity_rows() const { return _identity_rows; }
   const std::vector<int> &rowmap() const { return _rowmap; }
+  // vectors of the QP <-> vectors of the (possibly padded / permuted) device layout
+  bool padded() const { return _padded; }
+  int n_abi() const { return _n_abi; }
+  int me_abi() const { return _me_abi; }
+  void to_abi_x(const double *user, double *abi) const;
+  void from_abi_x(const double *abi, double *user) const;
+  void to_abi_y(const double *user, double *abi) const;
+  void from_abi_y(const double *abi, double *user) const;
 };
 
 #endif

@@ -67,9 +67,11 @@ void Hqp_IpsCuda::init()
   _y = v_resize(_y, _me);
   _z = v_resize(_z, _m);
   _w = v_resize(_w, _m);
-  _bp.assign(_me > 0 ? _me : 1, 0.0);
-  _yp.assign(_me > 0 ? _me : 1, 0.0);
   _mat.init(_qp);  // structure detection + device engine (Hqp_IpCuda::init)
+  _bp.assign(_mat.me_abi() > 0 ? _mat.me_abi() : 1, 0.0);
+  _yp.assign(_mat.me_abi() > 0 ? _mat.me_abi() : 1, 0.0);
+  _cp.assign(_mat.n_abi() > 0 ? _mat.n_abi() : 1, 0.0);
+  _xp.assign(_mat.n_abi() > 0 ? _mat.n_abi() : 1, 0.0);
   _hot = 0;
 }
 
@@ -111,36 +113,42 @@ void Hqp_IpsCuda::solve()
   int i, iters = 0, res = (int)Hqp_Infeasible;
   double gap = 0.0;
 
-  // equality rows in the engine's order (dynamics, x0, general rows)
-  const double *b = _qp->b->ve;
-  double *y = _y->ve;
+  // equality rows in the engine's order (dynamics, x0, general rows); variables in
+  // the engine's (possibly padded) stage layout
+  const double *b = _qp->b->ve, *c = _qp->c->ve;
+  double *y = _y->ve, *x = _qp->x->ve;
   if (!ident) {
-    for (i = 0; i < _me; i++) {
-      _bp[i] = _qp->b->ve[rowmap[i]];
-      _yp[i] = _y->ve[rowmap[i]];
-    }
+    _mat.to_abi_y(_qp->b->ve, &_bp[0]);
+    _mat.to_abi_y(_y->ve, &_yp[0]);
     b = &_bp[0];
     y = &_yp[0];
   }
+  if (_mat.padded()) {
+    _mat.to_abi_x(_qp->c->ve, &_cp[0]);
+    _mat.to_abi_x(_qp->x->ve, &_xp[0]);
+    c = &_cp[0];
+    x = &_xp[0];
+  }
+  (void)rowmap;
   int rc;
   if (_franke)
-    rc = hqpcu_franke_solve(_mat.handle(), _qp->c->ve, b, _m ? _qp->d->ve : none, _eps, _max_iters,
-                            _hot, _max_warm_iters, _beta, _mu0, _qp->x->ve, y, _m ? _z->ve : none,
+    rc = hqpcu_franke_solve(_mat.handle(), c, b, _m ? _qp->d->ve : none, _eps, _max_iters,
+                            _hot, _max_warm_iters, _beta, _mu0, x, y, _m ? _z->ve : none,
                             _m ? _w->ve : none, &iters, &res, &gap);
   else if (_hot)
-    rc = hqpcu_mehrotra_hot_solve(_mat.handle(), _qp->c->ve, b, _m ? _qp->d->ve : none, _eps,
-                                  _max_iters, _max_warm_iters, _qp->x->ve, y,
+    rc = hqpcu_mehrotra_hot_solve(_mat.handle(), c, b, _m ? _qp->d->ve : none, _eps,
+                                  _max_iters, _max_warm_iters, x, y,
                                   _m ? _z->ve : none, _m ? _w->ve : none, &iters, &res, &gap);
   else
-    rc = hqpcu_mehrotra_solve(_mat.handle(), _qp->c->ve, b, _m ? _qp->d->ve : none, _eps,
-                              _max_iters, _qp->x->ve, y, _m ? _z->ve : none,
+    rc = hqpcu_mehrotra_solve(_mat.handle(), c, b, _m ? _qp->d->ve : none, _eps,
+                              _max_iters, x, y, _m ? _z->ve : none,
                               _m ? _w->ve : none, &iters, &res, &gap);
   if (rc != HQPCU_OK) {
     fprintf(stderr, "Hqp_IpsCuda::solve: %s\n", hqpcu_last_error());
     m_error(rc == HQPCU_E_SING ? E_SING : E_INTERN, "Hqp_IpsCuda::solve");
   }
-  if (!ident)
-    for (i = 0; i < _me; i++) _y->ve[rowmap[i]] = _yp[i];
+  if (!ident) _mat.from_abi_y(&_yp[0], _y->ve);
+  if (_mat.padded()) _mat.from_abi_x(&_xp[0], _qp->x->ve);
   _iter = iters;
   _gap = gap;
   _result = (Hqp_Result)res;

@@ -32,6 +32,7 @@ class Hqp_IpsCuda : public Hqp_Solver {
   int _franke;       ///< 0: Mehrotra predictor-corrector, 1: Franke (Hqp_IpsFranke)
   Real _beta, _mu0;  ///< Franke: qp_beta, qp_mu0 (hqp/Hqp_IpsFranke.C:78-79)
   std::vector<double> _bp, _yp;  ///< b / y in the engine's equality row order
+  std::vector<double> _cp, _xp;  ///< c / x in the engine's padded stage layout (non-uniform stages)
 
  public:
   Hqp_IpsCuda(int franke = 0);

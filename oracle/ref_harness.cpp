@@ -358,7 +358,9 @@ int ref_ips_solve(void *qp_, const char *solver, const char *mat, double eps,
   Hqp_Solver *s = list ? list->createObject(solver) : NULL;
   if (!s) return -1;
   int err = 0;
-  if (If_SetString("qp_mat_solver", mat) != IF_OK) {
+  // (a solver module without an exchangeable matrix solver -- "CudaMehrotra",
+  //  "CudaFranke" -- is selected with an empty mat)
+  if (mat && *mat && If_SetString("qp_mat_solver", mat) != IF_OK) {
     delete s;
     return -2;
   }

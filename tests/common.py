@@ -65,3 +65,67 @@ def dense_kkt_solve(p, z, w, r1, r2, r3, r4):
     Kmat[N + me + m:, N + me + m:] = np.diag(z)
     sol = np.linalg.solve(Kmat, np.concatenate([r1, r2, r3, r4]))
     return sol[:N], sol[N:N + me], sol[N + me:N + me + m], sol[N + me + m:]
+
+
+class VarDimQP:
+    """A DOCP-structured QP with stage-dependent nx_k / nu_k in the layout of
+    hqp/Hqp_Docp.C, as CSR for oracle/refharness.RefQP: what
+    Hqp_IpLQDOCP::Get_Dim handles with _nk[k], _mk[k] (hqp/Hqp_IpLQDOCP.C:201-287)."""
+
+    def __init__(self, nxs, nus, seed=0):
+        rng = np.random.default_rng(seed)
+        K = len(nus)
+        assert len(nxs) == K + 1 and nxs[0] == nxs[1] and min(nus) >= 1
+        xoff = np.concatenate([[0], np.cumsum([nxs[k] + nus[k] for k in range(K)])]).astype(int)
+        self.N = int(xoff[K] + nxs[K])
+        ndyn = int(sum(nxs[1:]))
+        self.me = ndyn + nxs[0]
+        qr, qc, qv = [], [], []
+        ar, ac, av = [], [], []
+        cr, cc, cv, d = [], [], [], []
+        self.c = rng.uniform(-1, 1, self.N)
+        b = []
+        row = 0
+        for k in range(K + 1):
+            dk = nxs[k] + (nus[k] if k < K else 0)
+            M = rng.uniform(-1, 1, (dk, dk))
+            H = M.T @ M / dk + 0.1 * np.eye(dk)
+            for i in range(dk):
+                for j in range(i, dk):
+                    qr.append(xoff[k] + i); qc.append(xoff[k] + j); qv.append(H[i, j])
+            if k < K:
+                fx = np.zeros((nxs[k + 1], nxs[k]))
+                mdim = min(nxs[k + 1], nxs[k])
+                fx[:mdim, :mdim] = np.eye(mdim)
+                fx += 0.1 * rng.uniform(-1, 1, fx.shape) / np.sqrt(max(nxs[k], 1))
+                fu = rng.uniform(-1, 1, (nxs[k + 1], nus[k]))
+                for i in range(nxs[k + 1]):
+                    for j in range(nxs[k]):
+                        ar.append(row); ac.append(xoff[k] + j); av.append(fx[i, j])
+                    for j in range(nus[k]):
+                        ar.append(row); ac.append(xoff[k] + nxs[k] + j); av.append(fu[i, j])
+                    ar.append(row); ac.append(xoff[k + 1] + i); av.append(-1.0)
+                    b.append(0.01 * rng.uniform(-1, 1))
+                    row += 1
+                for j in range(nus[k]):          # -1 <= u <= 1
+                    col = xoff[k] + nxs[k] + j
+                    cr.append(len(d)); cc.append(col); cv.append(1.0); d.append(1.0)
+                    cr.append(len(d)); cc.append(col); cv.append(-1.0); d.append(1.0)
+        for i in range(nxs[0]):                  # fixed x0, rows after the dynamics rows
+            ar.append(row); ac.append(i); av.append(1.0); b.append(-rng.uniform(-1, 1)); row += 1
+        self.b = np.asarray(b)
+        self.d = np.asarray(d)
+        self.m = len(d)
+        from hqp_b200.problem import _coo_to_csr
+        self._Q = _coo_to_csr(self.N, np.asarray(qr), np.asarray(qc), np.asarray(qv))
+        self._A = _coo_to_csr(self.me, np.asarray(ar), np.asarray(ac), np.asarray(av))
+        self._C = _coo_to_csr(self.m, np.asarray(cr), np.asarray(cc), np.asarray(cv))
+
+    def csr_Q_upper(self):
+        return self._Q
+
+    def csr_A(self):
+        return self._A
+
+    def csr_C(self):
+        return self._C

@@ -88,3 +88,43 @@ def test_docp_device_resident_franke_reproduces_as_shipped_run():
     assert r["sqp_iters"] == g["sqp_iters"]
     assert g["qp_iters"] == 57 and abs(r["qp_iters"] - 57) <= 1
     assert abs(r["objective"] - g["objective"]) <= 1e-8 * abs(g["objective"])
+
+
+def _vardim_worker(solver, mat, q):
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__))))
+    from common import VarDimQP
+    from oracle import refharness as R
+    if "Cuda" in solver + mat:
+        R.load_plugin(PLUGIN)
+    p = VarDimQP([3, 3, 5, 2, 4, 4, 6, 3, 5, 4, 4, 2, 3], [2, 1, 3, 2, 1, 4, 2, 3, 1, 2, 2, 3], seed=4)
+    r = R.ips_solve(R.RefQP(p), solver, mat, 1e-9)
+    q.put((r["iters"], r["result"], r["x"], r["y"], r["z"]))
+
+
+@needs_ref
+def test_non_uniform_stage_dimensions_through_the_plugin():
+    """stage-dependent nx_k / nu_k (Hqp_IpLQDOCP::Get_Dim's _nk[k], _mk[k],
+    hqp/Hqp_IpLQDOCP.C:201-287): Hqp_IpCuda pads every stage to the largest
+    dimensions with decoupled unit blocks.  Under the unmodified Hqp_IpsMehrotra and
+    as the device-resident solver modules: the reference's iteration count and
+    solution with Hqp_IpLQDOCP."""
+    import multiprocessing as mp
+    from common import relerr
+    ctx = mp.get_context("spawn")
+    out = {}
+    for solver, mat in (("Mehrotra", "LQDOCP"), ("Mehrotra", "Cuda"), ("CudaMehrotra", ""),
+                        ("Franke", "LQDOCP"), ("CudaFranke", "")):
+        q = ctx.Queue()
+        pr = ctx.Process(target=_vardim_worker, args=(solver, mat, q))
+        pr.start()
+        out[(solver, mat)] = q.get(timeout=300)
+        pr.join()
+    ref = out[("Mehrotra", "LQDOCP")]
+    for key in (("Mehrotra", "Cuda"), ("CudaMehrotra", "")):
+        it, res, x, y, z = out[key]
+        assert res == ref[1] == "optimal" and it == ref[0], key
+        assert relerr(x, ref[2]) < 1e-8 and relerr(y, ref[3]) < 1e-7 and relerr(z, ref[4]) < 1e-7, key
+    reff, fr = out[("Franke", "LQDOCP")], out[("CudaFranke", "")]
+    assert fr[1] == reff[1] == "optimal" and abs(fr[0] - reff[0]) <= 1
+    assert relerr(fr[2], reff[2]) < 1e-7
