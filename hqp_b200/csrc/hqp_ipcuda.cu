@@ -101,6 +101,7 @@ struct hqpcu_handle {
   int device = 0;
   int nseg_req = 0;       // segment count asked for (0 = automatic); hqpcu_set_nseg updates it
   bool big = false;       // stage blocks exceed shared memory: global-workspace kernels (LqDev::gws)
+  int nt2() const { return big ? LQ_BIG_NT : LQ_NT2; }  // threads per CTA of the tree kernels
   bool demoted = false;   // E_NOTPD fallback to the sequential sweep is in force until the next update
   std::vector<void *> allocs;
   // owned device copies
@@ -703,10 +704,11 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
                                   nn * sizeof(double)}) + (size_t)(nx + 16) * sizeof(double);
     d.gws_stride = pad2(need / sizeof(double) + 2);
     TRY(dev_alloc(h, &d.gws, (size_t)std::max(d.P, 1) * B * d.gws_stride));
-    // shared memory = the private GEMM staging slices of the warps (cta_mm_big)
-    h->smem_k1 = h->smem_k3 = (big_ldlt_fits(nu, 128) ? big_seg_smem_doubles(nu, 128)
-                                                      : (size_t)4 * LQ_BIG_STAGE) * sizeof(double);
-    h->smem_k2 = h->smem_cmp = h->smem_psi = (size_t)(LQ_NT2 / 32) * LQ_BIG_STAGE * sizeof(double);
+    // shared memory = the GEMM staging ring of the CTA (cta_mm_big), for K1/K3 followed by
+    // the LDL^T factor of Guu; LQ_BIG_NT threads per CTA
+    h->smem_k1 = h->smem_k3 = (big_ldlt_fits(nx, nu, LQ_BIG_NT) ? big_seg_smem_doubles(nx, nu, LQ_BIG_NT)
+                                                                : (size_t)LQ_BIG_STG) * sizeof(double);
+    h->smem_k2 = h->smem_cmp = h->smem_psi = (size_t)LQ_BIG_STG * sizeof(double);
     // (the chains read their matrices from global memory directly: no ring)
     h->smem_chain = h->smem_scan = pad2((size_t)3 * nx) * sizeof(double) + 2 * sizeof(uint64_t) + 16;
   }
@@ -728,7 +730,9 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
   TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>, h->smem_k1)); \
   TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>, h->smem_k3)); \
   TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k1)); \
-  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k3));
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>, h->smem_k3)); \
+  TRY(set_smem((const void *)seg_element_kernel<NX_, NU_, ((NX_) == 0 ? LQ_BIG_NT / 32 : 4)>, h->smem_k1)); \
+  TRY(set_smem((const void *)seg_riccati_kernel<NX_, NU_, ((NX_) == 0 ? LQ_BIG_NT / 32 : 4)>, h->smem_k3));
 #define SET_B(NX_)                                                             \
   TRY(set_smem((const void *)elem_scan_kernel<NX_>, h->smem_k2));             \
   TRY(set_smem((const void *)range_scan_factor_kernel<NX_>, h->smem_k2));     \
@@ -994,7 +998,9 @@ static int launch_eq_factor(hqpcu_handle *h) {
 
 #define L_K1(NX_, NU_)                                                                         \
   do {                                                                                         \
-    if ((NX_) >= 32 && h->seg_warps == 8)                                                      \
+    if ((NX_) == 0 && h->big)                                                                  \
+      LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) == 0 ? LQ_BIG_NT / 32 : 4)>), gseg, LQ_BIG_NT, h->smem_k1, s, d); \
+    else if ((NX_) >= 32 && h->seg_warps == 8)                                                 \
       LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>), gseg, 256, h->smem_k1, s, d); \
     else if ((NX_) > 0 && h->seg_warps == 1)                                                   \
       LAUNCHP(h, (seg_element_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k1, s, d); \
@@ -1003,18 +1009,20 @@ static int launch_eq_factor(hqpcu_handle *h) {
   } while (0)
 #define L_K3(NX_, NU_)                                                                         \
   do {                                                                                         \
-    if ((NX_) >= 32 && h->seg_warps == 8)                                                      \
+    if ((NX_) == 0 && h->big)                                                                  \
+      LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) == 0 ? LQ_BIG_NT / 32 : 4)>), gseg, LQ_BIG_NT, h->smem_k3, s, d); \
+    else if ((NX_) >= 32 && h->seg_warps == 8)                                                 \
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) >= 32 ? 8 : 4)>), gseg, 256, h->smem_k3, s, d); \
     else if ((NX_) > 0 && h->seg_warps == 1)                                                   \
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, ((NX_) > 0 ? 1 : 4)>), gseg, 32, h->smem_k3, s, d); \
     else                                                                                       \
       LAUNCHP(h, (seg_riccati_kernel<NX_, NU_, 4>), gseg, 128, h->smem_k3, s, d);        \
   } while (0)
-#define L_CMP(NX_) LAUNCHP(h, elem_compose_kernel<NX_>, gl, LQ_NT2, h->smem_cmp, s, d, l)
-#define L_HS(NX_) LAUNCHP(h, elem_hs_kernel<NX_>, gseg, LQ_NT2, h->smem_cmp, s, d, stride, src, dst, last, jmax, jfix)
-#define L_TOP(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, dim3(1, d.batch), LQ_NT2, h->smem_k2, s, d, h->ftop(), 1)
-#define L_DWN(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, gl, LQ_NT2, h->smem_k2, s, d, l, 0)
-#define L_PSI(NX_) LAUNCHP(h, psi_compose_kernel<NX_>, gl, LQ_NT2, h->smem_psi, s, d, l, h->psi_chunk)
+#define L_CMP(NX_) LAUNCHP(h, elem_compose_kernel<NX_>, gl, h->nt2(), h->smem_cmp, s, d, l)
+#define L_HS(NX_) LAUNCHP(h, elem_hs_kernel<NX_>, gseg, h->nt2(), h->smem_cmp, s, d, stride, src, dst, last, jmax, jfix)
+#define L_TOP(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, dim3(1, d.batch), h->nt2(), h->smem_k2, s, d, h->ftop(), 1)
+#define L_DWN(NX_) LAUNCHP(h, elem_scan_kernel<NX_>, gl, h->nt2(), h->smem_k2, s, d, l, 0)
+#define L_PSI(NX_) LAUNCHP(h, psi_compose_kernel<NX_>, gl, h->nt2(), h->smem_psi, s, d, l, h->psi_chunk)
 
 // factor, part 1: bound diagonal, segment elements, tree up-sweep
 static int launch_factor_up(hqpcu_handle *h) {
@@ -1601,7 +1609,7 @@ int hqpcu_range_factor_finish(hqpcu_handle *h, const double *gathered, int rank,
           (const void *)(uintptr_t)world},
       [&]() {
         cudaStream_t s = h->stream;
-#define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, LQ_NT2, h->smem_k2, s>>>(d, gathered, rank, world))
+#define L_RS(NX_) LAUNCH(h, range_scan_factor_kernel<NX_>, <<<1, h->nt2(), h->smem_k2, s>>>(d, gathered, rank, world))
         LQ_DISPATCH_NX(d.nx, d.nu, L_RS);
 #undef L_RS
         int rc = launch_factor_down(h);

@@ -448,33 +448,57 @@ __device__ __forceinline__ void cta_mm_tc(double *C, int ldc, const double *C0, 
 // ---------------------------------------------------------------------------
 // Large-block product (stage blocks that live in global memory, nx > 64):
 //   C (M x N) = beta * C0 + alpha * A * B,  same strided operands as cta_mm.
-// The output is cut into 40 x 40 blocks (5 x 5 DMMA tiles), dealt round-robin to
-// the warps; every warp is an independent GEMM worker: it stages its own A and B
-// panels, LQ_BIG_KC deep, in a PRIVATE double-buffered shared-memory slice with
-// cp.async (LDGSTS; zero-filled outside the matrix), so the only synchronisation
-// inside the product is __syncwarp -- no CTA barrier, no idle warps while another
-// one waits for memory.  Per k-step of 4 a warp loads 5 + 5 fragments for 25
-// DMMAs.  Panels are stored [row][k] with stride LQ_BIG_KC + 4 = 4 (mod 8):
-// conflict-free fragment reads (see lq_pad4).
-// stg: LQ_BIG_STAGE doubles of shared memory per PHYSICAL warp of the CTA.
+// CTA-cooperative tensor-core GEMM.  The output is cut into CTA tiles of
+// (wmb * 40) x (wnb * 24) elements (5 x 3 = 15 warp blocks of 5 x 3 DMMA tiles each:
+// 200 x 72; 2 x 7 blocks for products with few rows); the k-direction is streamed
+// in chunks of LQ_BIG_KC through a ring of LQ_BIG_NS shared-memory stages that ALL
+// warps read: the A panel of a chunk feeds every warp column and the B panel every
+// warp row, so a byte staged from L2 is used by 3 .. 7 warps (round 2's first
+// version staged private panels per warp and spent 97 % of its instructions in the
+// staging loop; profiles/r02_ncu_full_c4.md).
+// Staging: one bulk async copy (cp.async.bulk, SASS UBLKCP) per panel row -- 128 B
+// along k when k is the operand's contiguous direction, one copy per k otherwise --
+// completing on the stage's mbarrier, issued LQ_BIG_NS chunks ahead; one named
+// barrier per chunk recycles the stage.  Operands whose strides or base break the
+// 16-byte rules of the bulk copy take 8-byte cp.async copies (zero-filled) with
+// the same ring, two stages deep.
+// Panel layouts (conflict-free 64-bit fragment reads, see lq_pad4):
+//   [row][k], row stride LQ_BIG_KC + 4 = 20      (k contiguous in memory)
+//   [k][row], row stride rows + 4 = 4|12 (mod 16) (rows contiguous in memory)
+// stg: LQ_BIG_STG doubles of shared memory, 16-byte aligned.  Called by `nwarps`
+// warps numbered warp_log = 0 .. nwarps-1 (the whole CTA or a subset, e.g. all but
+// the warp that factors Guu); they synchronise on named barrier 1.
 // ---------------------------------------------------------------------------
-#ifndef LQ_BIG_VEC
-#define LQ_BIG_VEC 0
-#endif
 #define LQ_BIG_KC 16
-#define LQ_BIG_BT 5                                   // DMMA tiles per block side
-#define LQ_BIG_LDS (LQ_BIG_KC + 4)                    // [row][k] layout: 20 = 4 (mod 8)
-#define LQ_BIG_LDT (LQ_BIG_BT * 8 + 4)                // [k][row] layout: 44 = 12 (mod 16)
-#define LQ_BIG_PANEL (LQ_BIG_BT * 8 * LQ_BIG_LDS)     // one panel: 40 x 20 (>= 16 x 44)
-#define LQ_BIG_STAGE (4 * LQ_BIG_PANEL)               // A, B panels, two buffers
+#define LQ_BIG_NS 4
+#define LQ_BIG_LDS (LQ_BIG_KC + 4)
+#define LQ_BIG_RT 5                                    // DMMA tiles per warp block: rows
+#define LQ_BIG_CT 3                                    //                            columns
+#define LQ_BIG_ROWS (5 * 8 * LQ_BIG_RT + 3 * 8 * LQ_BIG_CT)  // panel rows of a stage: 200 + 72
+#define LQ_BIG_STAGE (LQ_BIG_ROWS * LQ_BIG_LDS)
+#define LQ_BIG_STG (LQ_BIG_NS * LQ_BIG_STAGE)          // doubles of staging per CTA (174 KB)
+#define LQ_BIG_NT 512                                  // threads per CTA of the large-block kernels
+#define LQ_BIG_SMEM_DOUBLES 27000                      // what a large-block kernel may use (216 KB)
 
-// shared memory of the large-block segment kernels: the staging slices of the
-// warps, then the LDL^T factor of Guu and one right-hand-side column per thread
-__host__ __device__ inline size_t big_seg_smem_doubles(int nu, int nthr) {
-  return (size_t)(nthr / 32) * LQ_BIG_STAGE + (size_t)nu * (nu + 1) + (size_t)nu * nthr + 2;
+// Large-block segment kernels: shared memory = [U | LDL^T factor of Guu], U = the
+// GEMM staging ring, which between the products doubles as the right-hand sides of
+// the substitutions (one column per thread, `big_ycols` columns at a time).
+__host__ __device__ inline int big_ycols(int nx, int nu, int nthr) {
+  const long avail = ((long)LQ_BIG_SMEM_DOUBLES - (long)nu * (nu + 1)) / (nu > 0 ? nu : 1);
+  long yc = nthr < 2 * nx ? nthr : 2 * nx;
+  if (yc > avail) yc = avail;
+  return (int)(yc & ~1L);
 }
-__host__ __device__ inline bool big_ldlt_fits(int nu, int nthr) {
-  return big_seg_smem_doubles(nu, nthr) * sizeof(double) <= (size_t)227 * 1024;
+__host__ __device__ inline size_t big_seg_union_doubles(int nx, int nu, int nthr) {
+  const size_t y = (size_t)nu * big_ycols(nx, nu, nthr);
+  return y > (size_t)LQ_BIG_STG ? y : (size_t)LQ_BIG_STG;
+}
+__host__ __device__ inline size_t big_seg_smem_doubles(int nx, int nu, int nthr) {
+  return big_seg_union_doubles(nx, nu, nthr) + (size_t)nu * (nu + 1) + 2;
+}
+__host__ __device__ inline bool big_ldlt_fits(int nx, int nu, int nthr) {
+  return (size_t)nu * (nu + 1) + LQ_BIG_STG + 2 <= (size_t)LQ_BIG_SMEM_DOUBLES &&
+         big_ycols(nx, nu, nthr) >= 32;
 }
 
 __device__ __forceinline__ void cp_async_f64(double *dst_smem, const double *src, bool valid) {
@@ -485,156 +509,353 @@ __device__ __forceinline__ void cp_async_f64(double *dst_smem, const double *src
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void big_bar(int nt) { asm volatile("bar.sync 1, %0;" ::"r"(nt) : "memory"); }
 
-__device__ __forceinline__ void cp_async_f64x2(double *dst_smem, const double *src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
-               "r"(sz)
-               : "memory");
-}
-
-// One 40 x KC panel of X(i, l) = X[i * xr + l * xc] (rows r0.., columns k0..) into
-// shared memory, zero-filled outside nrows x Kd.  Two layouts, chosen by the
-// operand's orientation so that the copies run along its contiguous direction:
-//   TR = false: panel[r][k], row stride LQ_BIG_LDS   (k contiguous in memory)
-//   TR = true : panel[k][r], row stride LQ_BIG_LDT   (rows contiguous in memory)
-// vec: 16-byte copies (even strides / extents, 16-byte aligned base); the index
-// arithmetic is incremental -- this loop was 70 % of the instructions of the first
-// version of the large-block kernels (profiles/r02_ncu_full_c4.md).
+// One operand panel of the chunk k0 .. of X(i, l) = X[i * xr + l * xc], rows r0 ..,
+// by the nt threads lt = 0 .. nt-1 (operands without 16-byte alignment).
+//   TR = false: panel[r][k] (stride LQ_BIG_LDS);  TR = true: panel[k][r] (stride ldt)
+// generic: 8-byte cp.async, zero-filled outside M x Kd; rows = panel rows to fill
 template <bool TR>
-__device__ __forceinline__ void big_stage_panel(double *panel, const double *X, int xr, int xc,
-                                                int r0, int nrows, int k0, int Kd, int lane,
-                                                bool vec) {
-  constexpr int R = LQ_BIG_BT * 8, KC = LQ_BIG_KC;
+__device__ __forceinline__ void big_fill_gen(double *panel, int ldt, const double *X, int xr,
+                                             int xc, int r0, int M, int rows, int k0, int Kd,
+                                             int lt, int nt) {
+  constexpr int KC = LQ_BIG_KC;
   if constexpr (!TR) {
-    if (vec) {
-      // 8 x 16 bytes per row: lane -> (row = lane / 8 + 4 it, pair = lane % 8)
-      const int k = 2 * (lane & 7);
-      const bool kok = k0 + k < Kd;
-      const double *src = X + (size_t)(r0 + (lane >> 3)) * xr + (k0 + k);
-      double *dst = panel + (lane >> 3) * LQ_BIG_LDS + k;
-#pragma unroll
-      for (int it = 0; it < R / 4; it++) {
-        const bool ok = kok && r0 + (lane >> 3) + 4 * it < nrows;
-        cp_async_f64x2(dst, ok ? src : X, ok);
-        src += (size_t)4 * xr;
-        dst += 4 * LQ_BIG_LDS;
-      }
-    } else {
-#pragma unroll 4
-      for (int e = lane; e < R * KC; e += 32) {
-        const int r = e / KC, k = e % KC;  // (KC is a power of two)
-        const bool ok = r0 + r < nrows && k0 + k < Kd;
-        cp_async_f64(panel + r * LQ_BIG_LDS + k, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
-      }
+    for (int e = lt; e < rows * KC; e += nt) {
+      const int r = e / KC, k = e % KC;
+      const bool ok = r0 + r < M && k0 + k < Kd;
+      cp_async_f64(panel + r * LQ_BIG_LDS + k, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
     }
   } else {
-    if (vec) {
-      // 20 x 16 bytes per k: e = lane + 32 it -> (k = e / 20, pair = e % 20), incrementally
-      int k = lane / (R / 2), pr = lane % (R / 2);
-#pragma unroll
-      for (int it = 0; it < KC * (R / 2) / 32; it++) {
-        const bool ok = k0 + k < Kd && r0 + 2 * pr < nrows;
-        cp_async_f64x2(panel + k * LQ_BIG_LDT + 2 * pr,
-                       ok ? X + (size_t)(r0 + 2 * pr) + (size_t)(k0 + k) * xc : X, ok);
-        pr += 32 - (R / 2);  // (+32 elements = +1 k, +12 pairs)
-        k += 1;
-        if (pr >= R / 2) { pr -= R / 2; k += 1; }
-      }
-    } else {
-      int k = lane / R, r = lane % R;
-#pragma unroll 4
-      for (int it = 0; it < KC * R / 32; it++) {
-        const bool ok = k0 + k < Kd && r0 + r < nrows;
-        cp_async_f64(panel + k * LQ_BIG_LDT + r, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
-        r += 32;
-        if (r >= R) { r -= R; k += 1; }
-      }
+    for (int e = lt; e < rows * KC; e += nt) {
+      const int k = e / rows, r = e - k * rows;
+      const bool ok = r0 + r < M && k0 + k < Kd;
+      cp_async_f64(panel + k * ldt + r, ok ? X + (size_t)(r0 + r) * xr + (size_t)(k0 + k) * xc : X, ok);
     }
   }
+}
+
+__device__ __forceinline__ void mbar_add_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_inval(uint64_t *bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, const double *C0,
                                            int ldc0, double beta, double alpha, const double *A,
                                            int ar, int ac, const double *B, int br, int bc, int M,
                                            int N, int Kd, int wofs, int warp_log, int nwarps) {
-  constexpr int BT = LQ_BIG_BT, BS = BT * 8, KC = LQ_BIG_KC;
+  (void)wofs;
+  constexpr int KC = LQ_BIG_KC, NS = LQ_BIG_NS, LDS = LQ_BIG_LDS, RT = LQ_BIG_RT, CT = LQ_BIG_CT;
+  constexpr int WR = 8 * RT, WC = 8 * CT;  // rows / columns of a warp block
+  __shared__ __align__(8) uint64_t bars[2 * NS];  // full[NS] (bytes landed), empty[NS] (warps done)
+  uint64_t *full = bars, *empty = bars + NS;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  double *my = stg + (size_t)(threadIdx.x >> 5) * LQ_BIG_STAGE;
-  const int nbi = (M + BS - 1) / BS, nbj = (N + BS - 1) / BS, nb = nbi * nbj;
-  const int nchunk = (Kd + KC - 1) / KC;
-  // operand orientation -> panel layout; 16-byte copies where everything is even
+  const int lt = warp_log * 32 + lane, nt = nwarps * 32;
+  // a product with few rows is computed as C' = B' A' (the CTA tile is tall): the
+  // operands swap roles and the result is stored through transposed strides
+  int crs = ldc, ccs = 1, c0rs = ldc0, c0cs = 1;
+  if (M <= 2 * WR && N > M) {
+    const double *tp = A; A = B; B = tp;
+    int ti = ar; ar = bc; bc = ti;
+    ti = ac; ac = br; br = ti;
+    ti = M; M = N; N = ti;
+    crs = 1; ccs = ldc; c0rs = 1; c0cs = ldc0;
+  }
+  // warp grid of a CTA tile
+  int wnb = nwarps >= 15 ? 3 : (nwarps >= 8 ? 2 : 1);
+  int wmb = nwarps / wnb < 5 ? nwarps / wnb : 5;
+  if (M <= 2 * WR && nwarps >= 14) { wmb = 2; wnb = 7; }
+  const int BM = wmb * WR, BN = wnb * WC, ncw = wmb * wnb;
+  const int wr = warp_log / wnb, wc = warp_log - wr * wnb;
+  const bool cw = warp_log < ncw;  // this warp computes
+  // operand orientation -> panel layout; bulk copies where the 16-byte rules hold
   const bool ta = ar == 1 && ac != 1, tb = bc == 1 && br != 1;
-  // (16-byte cp.async exists as .cg only: it bypasses L1, where the warps of a CTA
-  //  share each other's panels -- measured slower than 8-byte .ca copies at nx = 200,
-  //  K1 46 vs 38 ms; kept behind LQ_BIG_VEC for shapes without that reuse)
-  const bool al16 = LQ_BIG_VEC && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0;
-  const bool va = al16 && (ta ? (ac % 2 == 0 && M % 2 == 0) : (ac == 1 && ar % 2 == 0 && Kd % 2 == 0));
-  const bool vb = al16 && (tb ? (br % 2 == 0 && N % 2 == 0) : (br == 1 && bc % 2 == 0 && Kd % 2 == 0));
-  auto stage = [&](double *pa_, double *pb_, int i0_, int j0_, int kc0) {
-    if (ta) big_stage_panel<true>(pa_, A, ar, ac, i0_, M, kc0, Kd, lane, va);
-    else big_stage_panel<false>(pa_, A, ar, ac, i0_, M, kc0, Kd, lane, va);
-    // B(l, j) = B[l * br + j * bc]: a panel over "rows" j with k = l
-    if (tb) big_stage_panel<true>(pb_, B, bc, br, j0_, N, kc0, Kd, lane, vb);
-    else big_stage_panel<false>(pb_, B, bc, br, j0_, N, kc0, Kd, lane, vb);
-  };
-  for (int u = (warp_log + nwarps - (wofs % nwarps)) % nwarps; u < nb; u += nwarps) {
-    const int bi = u / nbj, bj = u - bi * nbj;
-    const int i0 = bi * BS, j0 = bj * BS;
-    // tiles of this block that hold any row / column of the result
-    const int nti = min(BT, (M - i0 + 7) >> 3), ntj = min(BT, (N - j0 + 7) >> 3);
-    double acc[BT][BT][2];
+  // (a subset of the CTA's warps takes the plain path as well)
+#ifndef LQ_BIG_SUBFAST
+#define LQ_BIG_SUBFAST 0
+#endif
+  const bool fast =
+      (LQ_BIG_SUBFAST || nt == (int)blockDim.x) &&
+      ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0 && (Kd & 1) == 0 &&
+      (ta ? ((ac & 1) == 0 && (M & 1) == 0) : (ac == 1 && (ar & 1) == 0)) &&
+      (tb ? ((br & 1) == 0 && (N & 1) == 0) : (br == 1 && (bc & 1) == 0));
+  const bool solo = fast && ta && tb && ncw < nwarps;  // one spare warp stages everything
+  const int ldtA = BM + 4, ldtB = BN + 4;
+  const int nchunk = (Kd + KC - 1) / KC;
+  const int ntj_t = (N + BN - 1) / BN;
+  const int total = ((M + BM - 1) / BM) * ntj_t * nchunk;
+  // fragment addressing: element (row, k) of a panel at row * rs + k * ks
+  const int a_rs = ta ? 1 : LDS, a_ks = ta ? ldtA : 1;
+  const int b_rs = tb ? 1 : LDS, b_ks = tb ? ldtB : 1;
+  const int a_off = (wr * WR + g) * a_rs + t * a_ks, b_off = BM * LDS + (wc * WC + g) * b_rs + t * b_ks;
+  // The operands were written by this CTA a moment ago with ordinary stores (generic
+  // proxy); the bulk copies below read them through the async proxy, and overwrite a
+  // staging area that held right-hand sides / scratch.  Every thread orders its own
+  // writes -- global and shared -- before the barrier that precedes the first copy.
+#ifndef LQ_BIG_FENCE
+#define LQ_BIG_FENCE 2
+#endif
+#if LQ_BIG_FENCE == 0
+  fence_proxy_async();
+#elif LQ_BIG_FENCE == 1
+  __threadfence();
+  fence_proxy_async();
+#elif LQ_BIG_FENCE == 2
+  __threadfence();
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  fence_proxy_async();
+#else
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+#endif
+  if (fast && lt == 0) {
 #pragma unroll
-    for (int r = 0; r < BT; r++)
-#pragma unroll
-      for (int c = 0; c < BT; c++) acc[r][c][0] = acc[r][c][1] = 0.0;
-    stage(my, my + LQ_BIG_PANEL, i0, j0, 0);
-    cp_async_commit();
-    for (int c = 0; c < nchunk; c++) {
-      double *pa = my + (size_t)(c & 1) * 2 * LQ_BIG_PANEL, *pb = pa + LQ_BIG_PANEL;
-      cp_async_wait_all();
-      __syncwarp();
-      if (c + 1 < nchunk) {  // next chunk into the other buffer while this one is consumed
-        double *na = my + (size_t)((c + 1) & 1) * 2 * LQ_BIG_PANEL;
-        stage(na, na + LQ_BIG_PANEL, i0, j0, (c + 1) * KC);
-        cp_async_commit();
+    for (int s = 0; s < NS; s++) {
+      mbar_init(&full[s], solo ? 1 : nwarps);
+      mbar_init(&empty[s], ncw);
+    }
+    mbar_fence_init();
+  }
+  big_bar(nt);
+  if (fast) {
+    // ---- bulk-copy ring.  The (tile, chunk) pairs form ONE stream q = 0 .. total-1
+    // (slot q % NS, phase (q / NS) & 1).  Every warp stages its share of chunk q + D
+    // (D = NS - 2) at the top of its iteration q: it waits until the ncw computing
+    // warps have released that slot (`empty`; they did so two chunks ago, so the wait
+    // is normally over already), issues at most one bulk copy per lane and arrives on
+    // the slot's `full` barrier with the byte count of its copies.  The computing
+    // warps then only wait for data, not for each other: no CTA barrier inside the
+    // product, and the first chunks of the next CTA tile are in flight while the last
+    // ones of the current tile are consumed.  (One staging warp alone cannot issue
+    // the ~270 row copies of a k-contiguous operand fast enough: 47 cycles per copy.)
+    // When both panels arrive as a few long copies (rows contiguous in memory: 2 x 16
+    // copies per chunk) and the warp grid leaves a warp without a block, that warp alone
+    // stages, a full ring ahead, and the computing warps do not touch the copies at all.
+    constexpr int D = NS - 2;
+    auto issue = [&](int q, int lt, int nt) {
+      if (q >= total) return;
+      const int s = q % NS;
+      if (q >= NS) {
+        mbar_wait(&empty[s], ((q / NS) - 1) & 1);
+        __syncwarp();
       }
+      const int tile = q / nchunk, c = q - tile * nchunk;
+      const int i0 = (tile / ntj_t) * BM, j0 = (tile % ntj_t) * BN;
+      const int mt = M - i0 < BM ? M - i0 : BM, nc = N - j0 < BN ? N - j0 : BN;
+      const int k0 = c * KC, kc = Kd - k0 < KC ? Kd - k0 : KC;
+      double *pa = stg + (size_t)s * LQ_BIG_STAGE, *pb = pa + BM * LDS;
+      // copies lt, lt + nt, .. of the chunk (A copies first, then B copies): normally
+      // at most one per thread
+      const int na = ta ? kc : mt, nb = tb ? kc : nc;
+      auto copy_of = [&](int e, const double *&src, double *&dst) -> uint32_t {
+        if (e < na) {
+          if (ta) { src = A + (size_t)(k0 + e) * ac + i0; dst = pa + e * ldtA; return (uint32_t)mt * 8; }
+          src = A + (size_t)(i0 + e) * ar + k0; dst = pa + e * LDS; return (uint32_t)kc * 8;
+        }
+        e -= na;
+        if (tb) { src = B + (size_t)(k0 + e) * br + j0; dst = pb + e * ldtB; return (uint32_t)nc * 8; }
+        src = B + (size_t)(j0 + e) * bc + k0; dst = pb + e * LDS; return (uint32_t)kc * 8;
+      };
+      if (kc & 3) {  // zero-filled k-tail (plain stores, published by the arrive below)
+        const int kc4 = (kc + 3) & ~3;
+        for (int e = lt; e < (kc4 - kc) * mt; e += nt) {
+          const int k = kc + e / mt, r = e % mt;
+          pa[ta ? k * ldtA + r : r * LDS + k] = 0.0;
+        }
+        for (int e = lt; e < (kc4 - kc) * nc; e += nt) {
+          const int k = kc + e / nc, r = e % nc;
+          pb[tb ? k * ldtB + r : r * LDS + k] = 0.0;
+        }
+        __syncwarp();
+      }
+      // every thread announces the bytes of its own copies, then lane 0 arrives for the
+      // warp.  (Uniform trip count, predicated body, and the warp reconverges before it
+      // goes on: what follows -- mma.sync, the next wait -- needs all 32 lanes together.)
+      for (int e0 = 0; e0 < na + nb; e0 += nt) {
+        const int e = e0 + lt;
+        if (e < na + nb) {
+          const double *src;
+          double *dst;
+          const uint32_t b = copy_of(e, src, dst);
+          mbar_add_tx(&full[s], b);
+          tma_load_1d(dst, src, b, &full[s]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) mbar_arrive(&full[s]);
+      __syncwarp();
+    };
+    if (solo) {
+      if (warp_log == ncw)
+        for (int q = 0; q < total; q++) issue(q, lane, 32);
+    } else {
+      for (int q = 0; q < D; q++) issue(q, lt, nt);
+      if (!cw)
+        for (int q = 0; q < total; q++) issue(q + D, lt, nt);
+    }
+    if (cw) {
+      int q = 0;
+      for (int i0 = 0; i0 < M; i0 += BM) {
+        for (int j0 = 0; j0 < N; j0 += BN) {
+          const int mt = M - i0 < BM ? M - i0 : BM, nc = N - j0 < BN ? N - j0 : BN;
+          int nti = (mt - wr * WR + 7) >> 3, ntj = (nc - wc * WC + 7) >> 3;
+          nti = nti < 0 ? 0 : (nti > RT ? RT : nti);
+          ntj = ntj < 0 ? 0 : (ntj > CT ? CT : ntj);
+          if (nti == 0 || ntj == 0) nti = ntj = 0;
+          double acc[RT][CT][2];
 #pragma unroll
-      for (int kk = 0; kk < KC; kk += 4) {
-        double af[BT], bf[BT];
+          for (int r = 0; r < RT; r++)
 #pragma unroll
-        for (int r = 0; r < BT; r++)
-          af[r] = ta ? pa[(kk + t) * LQ_BIG_LDT + r * 8 + g] : pa[(r * 8 + g) * LQ_BIG_LDS + kk + t];
+            for (int qq = 0; qq < CT; qq++) acc[r][qq][0] = acc[r][qq][1] = 0.0;
+          for (int c = 0; c < nchunk; c++, q++) {
+            if (!solo) issue(q + D, lt, nt);
+            const int s = q % NS;
+            mbar_wait(&full[s], (q / NS) & 1);
+            __syncwarp();
+            const double *ap = stg + (size_t)s * LQ_BIG_STAGE + a_off;
+            const double *bp = stg + (size_t)s * LQ_BIG_STAGE + b_off;
+            const int kc = Kd - c * KC < KC ? Kd - c * KC : KC;
+            const int kc4 = (kc + 3) & ~3;
+            if (nti == RT && ntj == CT) {
+#pragma unroll 4
+              for (int kk = 0; kk < kc4; kk += 4) {
+                double af[RT], bf[CT];
 #pragma unroll
-        for (int q = 0; q < BT; q++)
-          bf[q] = tb ? pb[(kk + t) * LQ_BIG_LDT + q * 8 + g] : pb[(q * 8 + g) * LQ_BIG_LDS + kk + t];
+                for (int r = 0; r < RT; r++) af[r] = ap[r * 8 * a_rs + kk * a_ks];
 #pragma unroll
-        for (int r = 0; r < BT; r++) {
-          if (r < nti) {
+                for (int qq = 0; qq < CT; qq++) bf[qq] = bp[qq * 8 * b_rs + kk * b_ks];
 #pragma unroll
-            for (int q = 0; q < BT; q++)
-              if (q < ntj) dmma_m8n8k4(acc[r][q][0], acc[r][q][1], af[r], bf[q]);
+                for (int r = 0; r < RT; r++)
+#pragma unroll
+                  for (int qq = 0; qq < CT; qq++) dmma_m8n8k4(acc[r][qq][0], acc[r][qq][1], af[r], bf[qq]);
+              }
+            } else if (nti > 0) {
+              for (int kk = 0; kk < kc4; kk += 4) {
+                double af[RT], bf[CT];
+#pragma unroll
+                for (int r = 0; r < RT; r++) af[r] = ap[r * 8 * a_rs + kk * a_ks];
+#pragma unroll
+                for (int qq = 0; qq < CT; qq++) bf[qq] = bp[qq * 8 * b_rs + kk * b_ks];
+#pragma unroll
+                for (int r = 0; r < RT; r++) {
+                  if (r < nti) {
+#pragma unroll
+                    for (int qq = 0; qq < CT; qq++)
+                      if (qq < ntj) dmma_m8n8k4(acc[r][qq][0], acc[r][qq][1], af[r], bf[qq]);
+                  }
+                }
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with slot s
+          }
+#pragma unroll
+          for (int r = 0; r < RT; r++) {
+            const int ic = i0 + wr * WR + r * 8 + g;
+            if (r >= nti || ic >= M) continue;
+#pragma unroll
+            for (int qq = 0; qq < CT; qq++) {
+              const int jc = j0 + wc * WC + qq * 8 + 2 * t;
+              if (qq >= ntj) continue;
+              double r0 = alpha * acc[r][qq][0], r1 = alpha * acc[r][qq][1];
+              if (jc < N) {
+                if (C0) r0 = fma(beta, C0[(size_t)ic * c0rs + (size_t)jc * c0cs], r0);
+                C[(size_t)ic * crs + (size_t)jc * ccs] = r0;
+              }
+              if (jc + 1 < N) {
+                if (C0) r1 = fma(beta, C0[(size_t)ic * c0rs + (size_t)(jc + 1) * c0cs], r1);
+                C[(size_t)ic * crs + (size_t)(jc + 1) * ccs] = r1;
+              }
+            }
           }
         }
       }
-      __syncwarp();  // every lane is done with this buffer before it is refilled
     }
+    big_bar(nt);  // the ring and its barriers are free again
+    // (the next product arms the barriers with other counts: re-initialising a live
+    //  mbarrier is undefined, it has to be invalidated first)
+    if (lt == 0) {
 #pragma unroll
-    for (int r = 0; r < BT; r++) {
-      const int ic = i0 + r * 8 + g;
-      if (r >= nti || ic >= M) continue;
+      for (int s = 0; s < 2 * NS; s++) mbar_inval(&bars[s]);
+    }
+    return;
+  }
+  // ---- operands that break the 16-byte rules: 8-byte cp.async copies by all threads,
+  // two slots, one CTA-wide barrier per chunk
+  for (int i0 = 0; i0 < M; i0 += BM) {
+    for (int j0 = 0; j0 < N; j0 += BN) {
+      const int mt = M - i0 < BM ? M - i0 : BM, nc = N - j0 < BN ? N - j0 : BN;
+      int nti = 0, ntj = 0;
+      if (cw) {
+        nti = (mt - wr * WR + 7) >> 3;
+        nti = nti < 0 ? 0 : (nti > RT ? RT : nti);
+        ntj = (nc - wc * WC + 7) >> 3;
+        ntj = ntj < 0 ? 0 : (ntj > CT ? CT : ntj);
+        if (nti == 0 || ntj == 0) nti = ntj = 0;
+      }
+      double acc[RT][CT][2];
 #pragma unroll
-      for (int q = 0; q < BT; q++) {
-        const int jc = j0 + q * 8 + 2 * t;
-        if (q >= ntj) continue;
-        double r0 = alpha * acc[r][q][0], r1 = alpha * acc[r][q][1];
-        if (jc < N) {
-          if (C0) r0 = fma(beta, C0[(size_t)ic * ldc0 + jc], r0);
-          C[(size_t)ic * ldc + jc] = r0;
+      for (int r = 0; r < RT; r++)
+#pragma unroll
+        for (int qq = 0; qq < CT; qq++) acc[r][qq][0] = acc[r][qq][1] = 0.0;
+      auto fill = [&](int c, int s) {
+        double *pa = stg + (size_t)s * LQ_BIG_STAGE, *pb = pa + BM * LDS;
+        const int ra = (mt + 7) & ~7, rb = (nc + 7) & ~7;
+        if (ta) big_fill_gen<true>(pa, ldtA, A, ar, ac, i0, M, ra, c * KC, Kd, lt, nt);
+        else big_fill_gen<false>(pa, ldtA, A, ar, ac, i0, M, ra, c * KC, Kd, lt, nt);
+        if (tb) big_fill_gen<true>(pb, ldtB, B, bc, br, j0, N, rb, c * KC, Kd, lt, nt);
+        else big_fill_gen<false>(pb, ldtB, B, bc, br, j0, N, rb, c * KC, Kd, lt, nt);
+        cp_async_commit();
+      };
+      fill(0, 0);
+      for (int c = 0; c < nchunk; c++) {
+        cp_async_wait_all();
+        big_bar(nt);  // chunk c has landed for every thread; chunk c-1 is consumed
+        if (c + 1 < nchunk) fill(c + 1, (c + 1) & 1);
+        const double *ap = stg + (size_t)(c & 1) * LQ_BIG_STAGE + a_off;
+        const double *bp = stg + (size_t)(c & 1) * LQ_BIG_STAGE + b_off;
+        if (nti > 0) {
+          for (int kk = 0; kk < KC; kk += 4) {
+            double af[RT], bf[CT];
+#pragma unroll
+            for (int r = 0; r < RT; r++) af[r] = ap[r * 8 * a_rs + kk * a_ks];
+#pragma unroll
+            for (int qq = 0; qq < CT; qq++) bf[qq] = bp[qq * 8 * b_rs + kk * b_ks];
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+              if (r < nti) {
+#pragma unroll
+                for (int qq = 0; qq < CT; qq++)
+                  if (qq < ntj) dmma_m8n8k4(acc[r][qq][0], acc[r][qq][1], af[r], bf[qq]);
+              }
+            }
+          }
         }
-        if (jc + 1 < N) {
-          if (C0) r1 = fma(beta, C0[(size_t)ic * ldc0 + jc + 1], r1);
-          C[(size_t)ic * ldc + jc + 1] = r1;
+      }
+      big_bar(nt);  // before the next tile refills slot 0
+#pragma unroll
+      for (int r = 0; r < RT; r++) {
+        const int ic = i0 + wr * WR + r * 8 + g;
+        if (r >= nti || ic >= M) continue;
+#pragma unroll
+        for (int qq = 0; qq < CT; qq++) {
+          const int jc = j0 + wc * WC + qq * 8 + 2 * t;
+          if (qq >= ntj) continue;
+          double r0 = alpha * acc[r][qq][0], r1 = alpha * acc[r][qq][1];
+          if (jc < N) {
+            if (C0) r0 = fma(beta, C0[(size_t)ic * c0rs + (size_t)jc * c0cs], r0);
+            C[(size_t)ic * crs + (size_t)jc * ccs] = r0;
+          }
+          if (jc + 1 < N) {
+            if (C0) r1 = fma(beta, C0[(size_t)ic * c0rs + (size_t)(jc + 1) * c0cs], r1);
+            C[(size_t)ic * crs + (size_t)(jc + 1) * ccs] = r1;
+          }
         }
       }
     }
@@ -665,6 +886,71 @@ __device__ __forceinline__ void cta_mmx(double *stg, double *C, int ldc, const d
              warp_id * 32 + (int)(threadIdx.x & 31), NW * 32);
     else
       cta_mm(C, ldc, C0, ldc0, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd);
+  }
+}
+
+// dst[0..n) = src[0..n) by the whole CTA (global -> global, large blocks): 16-byte
+// accesses when both ends allow it, four independent loads in flight per thread
+__device__ __forceinline__ void cta_copy_big(double *dst, const double *src, int n, int tid, int nthr) {
+  if ((((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) && (n & 1) == 0) {
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+    double2 *d2 = reinterpret_cast<double2 *>(dst);
+    const int n2 = n >> 1;
+    int i = tid;
+    for (; i + 3 * nthr < n2; i += 4 * nthr) {
+      const double2 a = s2[i], b = s2[i + nthr], c = s2[i + 2 * nthr], e = s2[i + 3 * nthr];
+      d2[i] = a; d2[i + nthr] = b; d2[i + 2 * nthr] = c; d2[i + 3 * nthr] = e;
+    }
+    for (; i < n2; i += nthr) d2[i] = s2[i];
+  } else {
+    int i = tid;
+    for (; i + 3 * nthr < n; i += 4 * nthr) {
+      const double a = src[i], b = src[i + nthr], c = src[i + 2 * nthr], e = src[i + 3 * nthr];
+      dst[i] = a; dst[i + nthr] = b; dst[i + 2 * nthr] = c; dst[i + 3 * nthr] = e;
+    }
+    for (; i < n; i += nthr) dst[i] = src[i];
+  }
+}
+
+// A <- 0.5 (A + A') for a block in global memory (large blocks): 32 x 32 tile pairs
+// (I, J), I <= J, one pair per warp at a time; both tiles are read along their rows
+// and exchanged through a padded shared-memory tile (scr: 33 * 32 doubles per warp),
+// where cta_symmetrize reads one of every two elements down a column.
+__device__ __forceinline__ void cta_symmetrize_big(double *scr, double *A, int lda, int n) {
+  // (at most 15 warps: 15 padded tiles fit the GEMM staging ring, LQ_BIG_STG doubles)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (int)(blockDim.x >> 5) < 15 ? (int)(blockDim.x >> 5) : 15;
+  if (warp >= nw) return;
+  double *tile = scr + (size_t)warp * (33 * 32);
+  const int nt = (n + 31) >> 5;
+  for (int pr = warp; pr < nt * (nt + 1) / 2; pr += nw) {
+    // pair index -> (I, J), I <= J
+    int I = 0, rem = pr;
+    while (rem >= nt - I) { rem -= nt - I; I++; }
+    const int J = I + rem;
+    const int i0 = I << 5, j0 = J << 5;
+    // tile (J, I) into shared memory, transposed access later
+    for (int r = 0; r < 32; r++) {
+      const int gi = j0 + r, gj = i0 + lane;
+      tile[r * 33 + lane] = (gi < n && gj < n) ? A[(size_t)gi * lda + gj] : 0.0;
+    }
+    __syncwarp();
+    for (int r = 0; r < 32; r++) {
+      const int gi = i0 + r, gj = j0 + lane;
+      if (gi < n && gj < n) {
+        const double v = 0.5 * (A[(size_t)gi * lda + gj] + tile[lane * 33 + r]);
+        A[(size_t)gi * lda + gj] = v;
+        tile[lane * 33 + r] = v;
+      }
+    }
+    __syncwarp();
+    if (I != J) {
+      for (int r = 0; r < 32; r++) {
+        const int gi = j0 + r, gj = i0 + lane;
+        if (gi < n && gj < n) A[(size_t)gi * lda + gj] = tile[r * 33 + lane];
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -757,6 +1043,36 @@ __device__ __forceinline__ int warp_ldlt(double *A, int lda, int m) {
     __syncwarp();
   }
   return st;
+}
+
+// The same factorisation by the whole CTA (large blocks, m up to a few hundred, A in
+// shared memory): per pivot the trailing update is spread over all threads.  Returns
+// the flag word to every thread; `flag_s`: one int of shared memory.  Ends with a barrier.
+__device__ __forceinline__ int cta_ldlt(double *A, int lda, int m, int *flag_s) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (tid == 0) *flag_s = 0;
+  __syncthreads();
+  for (int p = 0; p < m; p++) {
+    const double d = A[p * lda + p];
+    const double inv = 1.0 / d;
+    const int r = m - p - 1;  // trailing size
+    // trailing update A[i][j] -= A[i][p] A[j][p] / d, p < j <= i  (column p is still unscaled)
+    for (int e = tid; e < r * r; e += nthr) {
+      const int ii = e / r, jj = e - ii * r;
+      if (jj <= ii) {
+        const int i = p + 1 + ii, j = p + 1 + jj;
+        A[i * lda + j] = fma(-A[i * lda + p] * inv, A[j * lda + p], A[i * lda + j]);
+      }
+    }
+    __syncthreads();
+    for (int i = p + 1 + tid; i < m; i += nthr) A[i * lda + p] *= inv;
+    if (tid == 0) {
+      A[p * lda + p] = inv;
+      if (!(d > 0.0)) *flag_s |= (d == 0.0 || d != d) ? LQ_FLAG_SING : LQ_FLAG_NOTPD;
+    }
+    __syncthreads();
+  }
+  return *flag_s;
 }
 
 // fast FP64 reciprocal: hardware seed (MUFU.RCP64H) + two Newton steps; full

@@ -123,8 +123,9 @@ __device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
     mbar_wait(&sp.bar[buf], parity);
   } else {
     const double *Qk = d.Q + ((size_t)b * (d.K + 1) + k) * nm * nm;
-    for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) G[i] = Qk[i];
-    if (k < d.K) {
+    if (d.gws) cta_copy_big(G, Qk, nm * nm, threadIdx.x, blockDim.x);
+    else for (int i = threadIdx.x; i < nm * nm; i += blockDim.x) G[i] = Qk[i];
+    if (k < d.K && !d.gws) {  // (large blocks: fx, fu are read where they lie, stage_fx / stage_fu)
       const double *fx = d.fx + ((size_t)b * d.K + k) * nx * nx;
       const double *fu = d.fu + ((size_t)b * d.K + k) * nx * nu;
       for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) sp.fx(buf)[i] = fx[i];
@@ -160,6 +161,16 @@ __device__ __forceinline__ void stage_acquire(const LqDev &d, int nx, int nu,
     }
   }
   __syncthreads();
+}
+
+// fx / fu of stage k as the stage kernels read them: the pipe's buffer, or (large
+// blocks, whose products stage their operands themselves) the HBM slab directly
+__device__ __forceinline__ const double *stage_fx(const LqDev &d, const StagePipe &sp, int nx, int b, int k, int buf) {
+  return d.gws ? d.fx + ((size_t)b * d.K + k) * nx * nx : sp.fx(buf);
+}
+__device__ __forceinline__ const double *stage_fu(const LqDev &d, const StagePipe &sp, int nx, int nu, int b, int k,
+                                                  int buf) {
+  return d.gws ? d.fu + ((size_t)b * d.K + k) * nx * nu : sp.fu(buf);
 }
 
 // set up pipe storage and barriers; returns after a CTA barrier
@@ -240,69 +251,59 @@ __device__ __forceinline__ void riccati_stage(double *stg, int nx, int nu, int L
     // Gxx += fx' Tx ; Gux += fu' Tx ; Guu += fu' Tu  (lower blocks only)
     // (Gxx and V are symmetric: tiles on and below the diagonal only, mirrored later)
     cta_mmx<TC, NW>(stg, G, nm, G, nm, 1.0, 1.0, fx, 1, nx, T, LT, 1, nx, nx, nx, 0, -1, TC);
-    cta_mmx<TC, NW>(stg, G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
-    cta_mmx<TC, NW>(stg, G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
-                nu, nu, nx, 3);
+    if (!TC && stg) {  // (large blocks: [Gux Guu] += fu' [Tx Tu] as one product)
+      cta_mmx<TC, NW>(stg, G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nm, nx);
+    } else {
+      cta_mmx<TC, NW>(stg, G + nx * nm, nm, G + nx * nm, nm, 1.0, 1.0, fu, 1, LU, T, LT, 1, nu, nx, nx);
+      cta_mmx<TC, NW>(stg, G + nx * nm + nx, nm, G + nx * nm + nx, nm, 1.0, 1.0, fu, 1, LU, T + nx, LT, 1,
+                  nu, nu, nx, 3);
+    }
     __syncthreads();
   }
   double *Guu = G + nx * nm + nx;
   LQ_STAMP2(3);
   // Large blocks: G lives in global memory, where a dependent substitution step
-  // costs an L2 round trip.  The factor of Guu and one right-hand-side column per
-  // thread are kept in the shared-memory area `lds` (nu (nu+1) + nu * nthr doubles
-  // behind the GEMM staging slices; NULL when it does not fit: the slow path).
+  // costs an L2 round trip.  The factor of Guu is kept in the shared-memory area
+  // `lds` behind the GEMM staging ring, and the ring itself holds the right-hand
+  // sides of the substitutions, one column per thread, `yc` columns at a time
+  // (NULL when it does not fit: the slow path).
   double *lds = nullptr, *ybuf = nullptr;
+  int yc = 0;
   if constexpr (!TC) {
-    if (stg && big_ldlt_fits(nu, nthr)) {
-      lds = stg + (size_t)(nthr >> 5) * LQ_BIG_STAGE;
-      ybuf = lds + nu * (nu + 1);
+    if (stg && big_ldlt_fits(nx, nu, nthr)) {
+      lds = stg + big_seg_union_doubles(nx, nu, nthr);
+      ybuf = stg;
+      yc = big_ycols(nx, nu, nthr);
     }
   }
   const int ldl = nu + 1;
-  auto big_ldlt = [&]() -> int {  // warp 0
-    const int lane = tid & 31;
-    for (int e = lane; e < nu * nu; e += 32) {
+  if (lds) {
+    // the deferred work of the previous stage first (K3: copy-outs and the Psi product
+    // on the tensor cores, by the whole CTA), then LDL^T of Guu in shared memory
+    idle((int)(tid >> 5), NW);
+    __shared__ int ldlt_flag;
+    for (int e = tid; e < nu * nu; e += nthr) {
       const int i = e / nu, j = e - i * nu;
       if (j <= i) lds[i * ldl + j] = Guu[i * nm + j];
     }
-    __syncwarp();
-    const int st = warp_ldlt(lds, ldl, nu);
-    for (int e = lane; e < nu * nu; e += 32) {
+    const int st = cta_ldlt(lds, ldl, nu, &ldlt_flag);  // (barriers on entry and exit)
+    if (st && tid == 0) atomicOr(st_s, st);
+    for (int e = tid; e < nu * nu; e += nthr) {
       const int i = e / nu, j = e - i * nu;
       if (j <= i) Guu[i * nm + j] = lds[i * ldl + j];
     }
-    __syncwarp();
-    return st;
-  };
-  // dst(:, j) = Guu^{-1} src(:, j); thread t of nt works on columns t, t + nt, ...
-  auto big_solve = [&](const double *src, int sld, double *dst, int dld, int ncols, int t, int nt) {
-    double *y = ybuf + t;
-    for (int j = t; j < ncols; j += nt) {
-      for (int i = 0; i < nu; i++) y[i * nthr] = src[(size_t)i * sld + j];
-      thread_ldlt_solve(lds, ldl, nu, y, nthr);
-      for (int i = 0; i < nu; i++) dst[(size_t)i * dld + j] = y[i * nthr];
-    }
-  };
-  if (lds && el) {
-    if (warp_id_uniform() == 0) {
-      const int st = big_ldlt();
-      if (st && tid == 0) atomicOr(st_s, st);
-    }
-    __syncthreads();
-    big_solve(G + nx * nm, nm, Rux, LV, nx, tid, nthr);
-    big_solve(el->Wt, LV, el->Yt, LV, nx, tid, nthr);
-  } else if (lds) {
-    const int wu = warp_id_uniform();
-    if (wu == 0) {
-      const int st = big_ldlt();
-      if (st && tid == 0) atomicOr(st_s, st);
-      big_solve(G + nx * nm, nm, Rux, LV, nx, tid, 32);
-      if (NW == 1) {
-        __syncwarp();
-        idle(0, 1);
+    // Rux = Guu^{-1} Gux and (K1) Yt = Guu^{-1} Wt: one right-hand side per thread
+    if (tid < yc) {
+      double *y = ybuf + tid;
+      const int ncols = el ? 2 * nx : nx;
+      for (int j = tid; j < ncols; j += yc) {
+        const double *src = j < nx ? G + nx * nm + j : el->Wt + (j - nx);
+        double *dst = j < nx ? Rux + j : el->Yt + (j - nx);
+        const int sld = j < nx ? nm : LV;
+        for (int i = 0; i < nu; i++) y[i * yc] = src[(size_t)i * sld];
+        thread_ldlt_solve(lds, ldl, nu, y, yc);
+        for (int i = 0; i < nu; i++) dst[(size_t)i * LV] = y[i * yc];
       }
-    } else {
-      idle(wu - 1, NW - 1);
     }
   } else if (el) {
     // K1: LDL' by warp 0, then the 2 nx triangular solves spread over the CTA
@@ -423,15 +424,19 @@ seg_element_kernel(LqDev d) {
     }
     stage_acquire(d, nx, nu, sp, b, k, buf, (it >> 1) & 1, fup, LU);
     ElemAcc el{At, Wt, Yt, Cg};
-    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, k == kb - 1, J, sp.fx(buf), TC ? fup : sp.fu(buf),
-                          sp.G(buf), T, Rux, Phi, &st_s, &el);
+    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, k == kb - 1, J, stage_fx(d, sp, nx, b, k, buf),
+                          TC ? fup : stage_fu(d, sp, nx, nu, b, k, buf), sp.G(buf), T, Rux, Phi, &st_s, &el);
     // J symmetrised ; A <- A Phi, i.e. At <- Phi' At
-    if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx, true); else cta_symmetrize(J, LV, nx);
+    if constexpr (TC) cta_symmetrize_tc<NW>(J, LV, nx, true);
+    else if (stg) cta_symmetrize_big(stg, J, LV, nx);
+    else cta_symmetrize(J, LV, nx);
     cta_mmx<TC, NW>(stg, Atn, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, At, LV, 1, nx, nx, nx);
     double *t = At; At = Atn; Atn = t;
     __syncthreads();
   }
-  if constexpr (TC) cta_symmetrize_tc<NW>(Cg, LV, nx, true); else cta_symmetrize(Cg, LV, nx);
+  if constexpr (TC) cta_symmetrize_tc<NW>(Cg, LV, nx, true);
+  else if (stg) cta_symmetrize_big(stg, Cg, LV, nx);
+  else cta_symmetrize(Cg, LV, nx);
   __syncthreads();
   const size_t o = ((size_t)b * d.ft.nel + s) * nx * nx;
   for (int i = threadIdx.x; i < nx * nx; i += blockDim.x) {
@@ -450,7 +455,7 @@ seg_element_kernel(LqDev d) {
 // ---------------------------------------------------------------------------
 
 template <int NX>
-__global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) {
+__global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_compose_kernel(LqDev d, int lev) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   LQ_STAMP(0);
@@ -522,6 +527,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_compose_kernel(LqDev d, int lev) 
     if constexpr (TC) {
       cta_symmetrize_tc<NWC>(Cj, nx, nx);
       cta_symmetrize_tc<NWC>(Jj, nx, nx);
+    } else if (stg) {
+      cta_symmetrize_big(stg, Cj, nx, nx);
+      cta_symmetrize_big(stg, Jj, nx, nx);
     } else {
       cta_symmetrize(Cj, nx, nx);
       cta_symmetrize(Jj, nx, nx);
@@ -598,7 +606,7 @@ __global__ void elem_terminal_kernel(LqDev d) {
 // after the exchange: the scan runs without it, then ONE more level applies the
 // terminal element in slot P to all suffixes at once).
 template <int NX>
-__global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, int src, int dst,
+__global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_hs_kernel(LqDev d, int stride, int src, int dst,
                                                       int last, int jmax, int jfix) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -669,6 +677,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, in
   if constexpr (TC) {
     cta_symmetrize_tc<NWC>(Cj, nx, nx);
     cta_symmetrize_tc<NWC>(Jj, nx, nx);
+  } else if (stg) {
+    cta_symmetrize_big(stg, Cj, nx, nx);
+    cta_symmetrize_big(stg, Jj, nx, nx);
   } else {
     cta_symmetrize(Cj, nx, nx);
     cta_symmetrize(Jj, nx, nx);
@@ -695,7 +706,7 @@ __global__ void __launch_bounds__(LQ_NT2) elem_hs_kernel(LqDev d, int stride, in
 //   S <- J + A' (I + S C)^{-1} S A.
 // ---------------------------------------------------------------------------
 template <int NX>
-__global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int top) {
+__global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_scan_kernel(LqDev d, int lev, int top) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, nm = d.nm, n2 = nx * nx;
@@ -775,7 +786,9 @@ __global__ void __launch_bounds__(LQ_NT2) elem_scan_kernel(LqDev d, int lev, int
     // S <- J + A' X, symmetrised
     cta_mmx<TC, LQ_NT2 / 32>(stg, S, nx, d.segJ + o, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
     __syncthreads();
-    if constexpr (TC) cta_symmetrize_tc<LQ_NT2 / 32>(S, nx, nx); else cta_symmetrize(S, nx, nx);
+    if constexpr (TC) cta_symmetrize_tc<LQ_NT2 / 32>(S, nx, nx);
+    else if (stg) cta_symmetrize_big(stg, S, nx, nx);
+    else cta_symmetrize(S, nx, nx);
     __syncthreads();
   }
   if (threadIdx.x == 0 && st_s) atomicOr(d.status, st_s);
@@ -841,6 +854,12 @@ seg_riccati_kernel(LqDev d) {
         cta_mmx<TC, (NW > 1 ? NW - 1 : 1)>(stg, Ptd, LV, nullptr, 0, 0.0, 1.0, Phi, 1, LV, Ptc, LV, 1,
                                           nx, nx, nx, 0, w);
     }
+    if (stg) {  // (large blocks: LV == nx, plain copies out of the workspace)
+      cta_copy_big(Rk, Rp, nu * nx, t0, nt);
+      cta_copy_big(Pk, Phi, n2, t0, nt);
+      if (kp > ka || s == 0) cta_copy_big(d.V + ((size_t)b * (d.K + 1) + kp) * n2, V, n2, t0, nt);
+      return;
+    }
     for (int i = t0; i < nu * nx; i += nt) {
       const int r = i / nx, c = i - r * nx;
       Rk[i] = Rp[r * LV + c];
@@ -872,7 +891,8 @@ seg_riccati_kernel(LqDev d) {
     const bool have_prev = it > 0;
     const double *Rp = Rprev, *Ptc = Pt;
     double *Ptd = Ptn;
-    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, false, V, sp.fx(buf), TC ? fup : sp.fu(buf), G, T,
+    riccati_stage<NU, TC, NW>(stg, nx, nu, LV, LT, LU, false, V, stage_fx(d, sp, nx, b, k, buf),
+                              TC ? fup : stage_fu(d, sp, nx, nu, b, k, buf), G, T,
                               Rux, Phi, &st_s, nullptr, [&](int w, int nw) {
                                 if (have_prev) flush(k + 1, Rp, Ptc, Ptd, w, nw);
                               }, &kind_s);
@@ -881,7 +901,9 @@ seg_riccati_kernel(LqDev d) {
     LQ_STAMP2(6);
     const size_t ks = (size_t)b * d.K + k;
     double *Lk = d.LD + ks * nu * nu;
-    if constexpr (TC) cta_symmetrize_tc<NW>(V, LV, nx, true); else cta_symmetrize(V, LV, nx);
+    if constexpr (TC) cta_symmetrize_tc<NW>(V, LV, nx, true);
+    else if (stg) cta_symmetrize_big(stg, V, LV, nx);
+    else cta_symmetrize(V, LV, nx);
     for (int i = threadIdx.x; i < nu * nu; i += blockDim.x) {
       const int r = i / nu, c = i - r * nu;
       Lk[i] = G[(nx + r) * nm + nx + c];
@@ -909,7 +931,7 @@ seg_riccati_kernel(LqDev d) {
 // chunk as its first (rightmost) factor.  grid (cnt_{lev+1}, batch), LQ_NT2
 // threads, smem: (chunk + ceil(chunk/2)) * nx*nx doubles.
 template <int NX>
-__global__ void __launch_bounds__(LQ_NT2) psi_compose_kernel(LqDev d, int lev, int chunk) {
+__global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) psi_compose_kernel(LqDev d, int lev, int chunk) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;

@@ -45,7 +45,7 @@ __global__ void range_export_factor_kernel(LqDev d, double *xf, int slot) {
 // of the last rank and apply the elements of the ranks world-1 .. rank+1
 // (V_start = J + A'(I + S C)^{-1} S A).  gathered: [world][4][nx*nx].  One CTA.
 template <int NX>
-__global__ void __launch_bounds__(LQ_NT2) range_scan_factor_kernel(LqDev d, const double *gathered,
+__global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) range_scan_factor_kernel(LqDev d, const double *gathered,
                                                                 int rank, int world) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nx = NX > 0 ? NX : d.nx, n2 = nx * nx;
