@@ -701,7 +701,8 @@ int hqpcu_create(const hqpcu_dims *dims, hqpcu_handle **out) {
     // global workspace (LqDev::gws); shared memory holds barriers and flags only.
     d.use_tma = 0;
     const size_t need = std::max({h->smem_k1, h->smem_k2, h->smem_k3, h->smem_cmp, h->smem_psi,
-                                  nn * sizeof(double)}) + (size_t)(nx + 16) * sizeof(double);
+                                  nn * sizeof(double)}) + (size_t)(nx + 16) * sizeof(double) +
+                        big_gj_scratch_doubles(nx) * sizeof(double);  // (tail: scratch of the blocked elimination)
     d.gws_stride = pad2(need / sizeof(double) + 2);
     TRY(dev_alloc(h, &d.gws, (size_t)std::max(d.P, 1) * B * d.gws_stride));
     // shared memory = the GEMM staging ring of the CTA (cta_mm_big), for K1/K3 followed by

@@ -755,6 +755,42 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with slot s
           }
+          // (C0 may alias C: all loads of the tile first, then all stores -- interleaved,
+          //  every load would wait for the store before it, one L2 round trip each; the
+          //  two adjacent columns of a lane move as one 16-byte access where they can)
+          const bool vec = ccs == 1 && (crs & 1) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0 &&
+                           (N & 1) == 0 &&
+                           (!C0 || (c0cs == 1 && (c0rs & 1) == 0 && (reinterpret_cast<uintptr_t>(C0) & 15) == 0));
+          if (C0) {
+            // (no branches around the loads: every load is issued from a valid address,
+            //  so that several of them are in flight at once -- with a branch per element
+            //  each one waits out its own L2 round trip, 15 in a row per tile)
+#pragma unroll
+            for (int r = 0; r < RT; r++) {
+              const int ic = i0 + wr * WR + r * 8 + g;
+              double c0a[CT], c0b[CT];
+#pragma unroll
+              for (int qq = 0; qq < CT; qq++) {
+                const int jc = j0 + wc * WC + qq * 8 + 2 * t;
+                const bool ok = r < nti && qq < ntj && ic < M && jc < N;
+                if (vec) {
+                  const double2 c2 = *reinterpret_cast<const double2 *>(ok ? C0 + (size_t)ic * c0rs + jc : C0);
+                  c0a[qq] = c2.x;
+                  c0b[qq] = c2.y;
+                } else {
+                  const bool ok1 = ok && jc + 1 < N;
+                  c0a[qq] = *(ok ? C0 + (size_t)ic * c0rs + (size_t)jc * c0cs : C0);
+                  c0b[qq] = *(ok1 ? C0 + (size_t)ic * c0rs + (size_t)(jc + 1) * c0cs : C0);
+                }
+              }
+#pragma unroll
+              for (int qq = 0; qq < CT; qq++) {
+                acc[r][qq][0] = fma(beta, c0a[qq], alpha * acc[r][qq][0]);
+                acc[r][qq][1] = fma(beta, c0b[qq], alpha * acc[r][qq][1]);
+              }
+            }
+          }
+          const double asc = C0 ? 1.0 : alpha;
 #pragma unroll
           for (int r = 0; r < RT; r++) {
             const int ic = i0 + wr * WR + r * 8 + g;
@@ -763,14 +799,13 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
             for (int qq = 0; qq < CT; qq++) {
               const int jc = j0 + wc * WC + qq * 8 + 2 * t;
               if (qq >= ntj) continue;
-              double r0 = alpha * acc[r][qq][0], r1 = alpha * acc[r][qq][1];
-              if (jc < N) {
-                if (C0) r0 = fma(beta, C0[(size_t)ic * c0rs + (size_t)jc * c0cs], r0);
-                C[(size_t)ic * crs + (size_t)jc * ccs] = r0;
-              }
-              if (jc + 1 < N) {
-                if (C0) r1 = fma(beta, C0[(size_t)ic * c0rs + (size_t)(jc + 1) * c0cs], r1);
-                C[(size_t)ic * crs + (size_t)(jc + 1) * ccs] = r1;
+              if (vec) {
+                if (jc < N)
+                  *reinterpret_cast<double2 *>(C + (size_t)ic * crs + jc) =
+                      make_double2(asc * acc[r][qq][0], asc * acc[r][qq][1]);
+              } else {
+                if (jc < N) C[(size_t)ic * crs + (size_t)jc * ccs] = asc * acc[r][qq][0];
+                if (jc + 1 < N) C[(size_t)ic * crs + (size_t)(jc + 1) * ccs] = asc * acc[r][qq][1];
               }
             }
           }
@@ -1648,11 +1683,183 @@ __device__ __forceinline__ void cta_gj_inverse_big(double *M, int ldm, int n, in
   __syncthreads();
 }
 
-// X = M0^{-1} R for the augmented M = [M0 | R] (n x nc, ldm), large blocks: M0 is
-// inverted in place, then applied to R on the tensor cores (cta_mm_big).
-__device__ __forceinline__ void cta_inverse_apply_big(double *stg, double *M, int ldm, int n,
+// ---------------------------------------------------------------------------
+// X = M0^{-1} R for the augmented W = [M0 | R] (n x nc, ldm; global memory, large
+// blocks) by the whole CTA: BLOCKED Gauss-Jordan elimination with partial pivoting.
+// Round 2's first version inverted M0 with one rank-1 update of the whole block per
+// pivot -- 200 dependent passes over L2, 3.4 of the 4.5 ms of a tree level at nx =
+// 200.  Here LQ_GJ_W pivots are taken at a time:
+//   1. the panel W[:, k0 .. k0+w) is eliminated in shared memory, pivot by pivot
+//      (search over the rows not used yet, implicit row pivoting: no interchanges in
+//      memory); its columns keep the multipliers F;
+//   2. the w "effective" pivot rows Y of all columns to the right follow from a small
+//      triangular recurrence (one column per thread);
+//   3. every other entry to the right takes ONE rank-w update  W += U Y  on the
+//      tensor cores (cta_mm_big; U = -F, with the unit / zero pattern of the pivot
+//      rows), instead of w rank-1 passes.
+// At the end row piv[c] of the right-hand part is row c of X.
+// scr: (LQ_GJ_W) * (n + nc + 4) doubles of GLOBAL scratch (operands of the update);
+// stg: the GEMM staging ring (panel and flags live there between the products).
+// piv_s: n ints.  Barriers on entry and exit.
+// ---------------------------------------------------------------------------
+#define LQ_GJ_W 32
+#define LQ_GJ_MAXN 1024
+#ifdef LQ_GJ_STAMPS
+__device__ long long g_gj_cyc[8];  // cycles per phase, thread 0 of CTA 0 (microbenchmark builds)
+#define GJ_STAMP(i) do { if (threadIdx.x == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_gj_cyc[i] += t_ - gj_t0; gj_t0 = t_; } } while (0)
+#else
+#define GJ_STAMP(i) do { } while (0)
+#endif
+__host__ __device__ inline size_t big_gj_scratch_doubles(int nx) {
+  return (size_t)LQ_GJ_W * (4 * (size_t)nx + 8);
+}
+__device__ __forceinline__ void cta_gj_solve_blocked(double *stg, double *scr, double *W, int ldm, int n,
+                                                     int nc, double *X, int ldx, int *piv_s, int *st_s) {
+  constexpr int PW = LQ_GJ_W + 1;  // panel row stride in shared memory
+  __shared__ double red_v[32];
+  __shared__ int red_i[32];
+  __shared__ int blk_row[LQ_GJ_W];
+  __shared__ double prow[LQ_GJ_W];
+  __shared__ unsigned char used[LQ_GJ_MAXN];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  double *Pn = stg;                              // [n][PW] panel, then multipliers
+  const int ldu = (n + 1) & ~1, ldy = (nc + 1) & ~1;
+  double *Ut = scr, *Yg = scr + (size_t)LQ_GJ_W * ldu;  // [w][ldu], [w][ldy]
+  for (int i = tid; i < n; i += nthr) used[i] = 0;
+  // panel elimination: nsplit threads per row (no index arithmetic inside the pivot loop)
+  const int nsplit = nthr / n > 0 ? nthr / n : 1;
+  const int my_row = nthr >= n ? tid / nsplit : n, my_part = tid - (tid / nsplit) * nsplit;
+  __syncthreads();
+#ifdef LQ_GJ_STAMPS
+  long long gj_t0 = clock64();
+#endif
+  for (int k0 = 0; k0 < n; k0 += LQ_GJ_W) {
+    const int w = n - k0 < LQ_GJ_W ? n - k0 : LQ_GJ_W;
+    // ---- 1. panel into shared memory and eliminated there
+    for (int e = tid; e < n * w; e += nthr) {
+      const int i = e / w, q = e - i * w;
+      Pn[i * PW + q] = W[(size_t)i * ldm + k0 + q];
+    }
+    __syncthreads();
+    GJ_STAMP(0);
+    for (int p = 0; p < w; p++) {
+      // pivot of column p among the rows not used yet (ties: smaller row)
+      double best = -1.0;
+      int bi = n;
+      for (int i = tid; i < n; i += nthr) {
+        if (!used[i]) {
+          const double a = fabs(Pn[i * PW + p]);
+          if (a > best || (a == best && i < bi) || bi == n) { best = a; bi = i; }
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (oi < n && (bi == n || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { red_v[warp] = best; red_i[warp] = bi; }
+      __syncthreads();
+      if (warp == 0) {
+        // second round over the per-warp results, then the copy of the (unscaled) pivot row
+        const int nw = (nthr + 31) >> 5;
+        best = lane < nw ? red_v[lane] : -1.0;
+        bi = lane < nw ? red_i[lane] : n;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (oi < n && (bi == n || ob > best || (ob == best && oi < bi))) { best = ob; bi = oi; }
+        }
+        if (bi >= n) bi = 0;  // (cannot happen: n - k0 - p rows are unused)
+        if (lane == 0) {
+          if (!(best > 0.0)) *st_s |= LQ_FLAG_SING;
+          piv_s[k0 + p] = bi;
+          blk_row[p] = bi;
+          used[bi] = 1;
+        }
+        for (int q = lane; q < w; q += 32) prow[q] = Pn[bi * PW + q];
+      }
+      __syncthreads();
+      const int r = blk_row[p];
+      const double inv = 1.0 / prow[p];
+      // eliminate column p from every other row of the panel (columns q > p; column p
+      // keeps the multiplier); the pivot row is scaled in the same pass (the others read
+      // its copy `prow`).  `nsplit` threads share a row.
+      if (my_row < n) {
+        double *row = Pn + my_row * PW;
+        if (my_row != r) {
+          const double f = -row[p] * inv;
+          for (int q = p + 1 + my_part; q < w; q += nsplit) row[q] = fma(f, prow[q], row[q]);
+        } else {
+          for (int q = p + 1 + my_part; q < w; q += nsplit) row[q] = prow[q] * inv;
+          if (my_part == 0) row[p] = inv;
+        }
+      }
+      __syncthreads();
+    }
+    GJ_STAMP(1);
+    const int j0 = k0 + w, no = nc - j0;  // columns to the right
+    if (no <= 0) break;
+    // ---- 2. effective pivot rows  y_p = inv_p (W[r_p] - sum_{p' < p} F[r_p][p'] y_p'),
+    //         one column per thread; the pivot rows themselves are cleared (they are
+    //         rebuilt by the update below)
+    for (int j = tid; j < no; j += nthr) {
+      double y[LQ_GJ_W];
+#pragma unroll
+      for (int p = 0; p < LQ_GJ_W; p++)
+        y[p] = p < w ? W[(size_t)blk_row[p] * ldm + j0 + j] : 0.0;
+#pragma unroll
+      for (int p = 0; p < LQ_GJ_W; p++) {
+        if (p < w) {
+          const int r = blk_row[p];
+          y[p] *= Pn[r * PW + p];  // (1 / pivot)
+          Yg[(size_t)p * ldy + j] = y[p];
+          W[(size_t)r * ldm + j0 + j] = 0.0;
+          // right-looking: the later pivot rows lose their multiple of y_p now (independent updates)
+#pragma unroll
+          for (int pp = 0; pp < LQ_GJ_W; pp++)
+            if (pp > p && pp < w) y[pp] = fma(-Pn[blk_row[pp] * PW + p], y[p], y[pp]);
+        }
+      }
+    }
+    GJ_STAMP(2);
+    // U' (w x n): -F for the other rows; pivot row r_p0: unit at p0, -F right of it, 0 left
+    for (int e = tid; e < n * w; e += nthr) {
+      const int p = e / n, i = e - p * n;
+      int p0 = -1;
+#pragma unroll
+      for (int pp = 0; pp < LQ_GJ_W; pp++)
+        if (pp < w && blk_row[pp] == i) p0 = pp;
+      double u = -Pn[i * PW + p];
+      if (p0 >= 0) u = p == p0 ? 1.0 : (p > p0 ? u : 0.0);
+      Ut[(size_t)p * ldu + i] = u;
+    }
+    __syncthreads();
+    GJ_STAMP(3);
+    // ---- 3. W[:, j0 ..] += U Y
+    cta_mm_big(stg, W + j0, ldm, W + j0, ldm, 1.0, 1.0, Ut, 1, ldu, Yg, ldy, 1, n, no, w, 0,
+               (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5));
+    __syncthreads();
+    GJ_STAMP(4);
+  }
+  // X[c][:] = row piv[c] of the right-hand part
+  const int nr = nc - n;
+  for (int e = tid; e < n * nr; e += nthr) {
+    const int c = e / nr, j = e - c * nr;
+    X[(size_t)c * ldx + j] = W[(size_t)piv_s[c] * ldm + n + j];
+  }
+  __syncthreads();
+}
+
+// X = M0^{-1} R for the augmented M = [M0 | R] (n x nc, ldm), large blocks.  gjs: the
+// CTA's global scratch for the blocked elimination (NULL or n too large: M0 is inverted
+// in place, one rank-1 update per pivot, then applied to R on the tensor cores).
+__device__ __forceinline__ void cta_inverse_apply_big(double *stg, double *gjs, double *M, int ldm, int n,
                                                       int nc, double *X, int ldx, int *piv_s,
                                                       int *st_s) {
+  if (gjs && n <= LQ_GJ_MAXN && n <= (int)blockDim.x && (size_t)n * (LQ_GJ_W + 1) <= (size_t)LQ_BIG_STG) {
+    cta_gj_solve_blocked(stg, gjs, M, ldm, n, nc, X, ldx, piv_s, st_s);
+    return;
+  }
   cta_gj_inverse_big(M, ldm, n, piv_s, stg, st_s);
   cta_mm_big(stg, X, ldx, nullptr, 0, 0.0, 1.0, M, ldm, 1, M + n, ldm, 1, n, nc - n, n, 0,
              (int)(threadIdx.x >> 5), (int)(blockDim.x >> 5));
@@ -1702,6 +1909,13 @@ __device__ __forceinline__ unsigned char *cta_workspace(const LqDev &d, unsigned
   if (!d.gws) return smem_raw;
   const size_t cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
   return reinterpret_cast<unsigned char *>(d.gws + cta * d.gws_stride);
+}
+
+// the CTA's scratch for the blocked elimination: the tail of its workspace slice
+__device__ __forceinline__ double *big_gj_scratch(const LqDev &d) {
+  if (!d.gws) return nullptr;
+  const size_t cta = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+  return d.gws + (cta + 1) * d.gws_stride - big_gj_scratch_doubles(d.nx);
 }
 
 // shared-memory carve-up helper (16-byte granularity)

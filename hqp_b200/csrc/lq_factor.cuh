@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_compose_ker
     if constexpr (NX > 0)
       cta_inverse_apply<NX, NWC>(M, ldm, n3, X, inv_scr, piv_s, &st_s, ldx);
     else if (stg)
-      cta_inverse_apply_big(stg, M, ldm, nx, n3, X, ldx, piv_s, &st_s);
+      cta_inverse_apply_big(stg, big_gj_scratch(d), M, ldm, nx, n3, X, ldx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
     LQ_STAMP(4);
@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_hs_kernel(L
   if constexpr (NX > 0)
     cta_inverse_apply<NX, NWC>(M, ldm, n3, X, inv_scr, piv_s, &st_s, ldx);
   else if (stg)
-    cta_inverse_apply_big(stg, M, ldm, nx, n3, X, ldx, piv_s, &st_s);
+    cta_inverse_apply_big(stg, big_gj_scratch(d), M, ldm, nx, n3, X, ldx, piv_s, &st_s);
   else
     cta_gauss_jordan<NX>(M, n3, nx, n3, X, piv_s, inv_s, &st_s);
   // T1 = A_j X_C ; T2 = J_j X_A ; T3 = A_j X_A (the new A)
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) elem_scan_kernel
     if constexpr (NX > 0)
       cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
     else if (stg)
-      cta_inverse_apply_big(stg, M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
+      cta_inverse_apply_big(stg, big_gj_scratch(d), M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     // S <- J + A' X, symmetrised

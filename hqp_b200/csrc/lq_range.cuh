@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(NX == 0 ? LQ_BIG_NT : LQ_NT2) range_scan_facto
     if constexpr (NX > 0)
       cta_inverse_apply<NX, LQ_NT2 / 32>(M, ldm, 2 * nx, X, inv_scr, piv_s, &st_s);
     else if (stg)
-      cta_inverse_apply_big(stg, M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
+      cta_inverse_apply_big(stg, big_gj_scratch(d), M, ldm, nx, 2 * nx, X, nx, piv_s, &st_s);
     else
       cta_gauss_jordan<NX>(M, 2 * nx, nx, 2 * nx, X, piv_s, inv_s, &st_s);
     cta_mmx<TC, LQ_NT2 / 32>(stg, S, nx, E + 2 * n2, nx, 1.0, 1.0, A, 1, nx, X, nx, 1, nx, nx, nx);
