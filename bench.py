@@ -645,6 +645,75 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
     return line
 
 
+def run_hl_bfgs(local):
+    """Row f2 (next row of SURVEY section 8): the block-diagonal BFGS update of config 2's
+    Hessian -- 10^4 blocks of nx+nu = 30 and one of nx = 20 -- with Powell's damping and
+    eigenvalue control (Hqp_HL_BFGS::update, hqp/Hqp_HL_BFGS.C:149-243).  Device-resident
+    time (CUDA events, L2 flushed), end to end with host buffers through hqphl_bfgs_update,
+    and the reference's own update_b_Q on a sample of blocks on one host core."""
+    import torch
+    from hqp_b200 import hlcuda
+    K, n, nl = 10000, 30, 20
+    rng = np.random.default_rng(1234)
+    M = rng.uniform(-1, 1, (K + 1, n, n))
+    Qb = np.einsum("kij,kil->kjl", M, M) / n + 0.05 * np.eye(n)
+    bs = np.array([n] * K + [nl], dtype=np.int32)
+    Q = np.concatenate([Qb[:K].ravel(), Qb[K, :nl, :nl].ravel()])
+    nv = K * n + nl
+    s, u = rng.uniform(-1, 1, nv), rng.uniform(-1, 1, nv)
+    dev = torch.device("cuda", local)
+    qoff = np.concatenate([[0], np.cumsum(bs.astype(np.int64) ** 2)[:-1]])
+    voff = np.concatenate([[0], np.cumsum(bs)[:-1]]).astype(np.int32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_bs, d_qo, d_vo, d_Q0, d_s, d_u = t(bs), t(qoff), t(voff), t(Q), t(s), t(u)
+    d_info = torch.zeros(3, dtype=torch.int32, device=dev)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = []
+    for it in range(8):
+        d_Q = d_Q0.clone()
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hlcuda.bfgs_update_dev(d_bs, d_qo, d_vo, d_Q, d_s, d_u, d_info, n, 1.0, 0.1, 1e-8, True, stream)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            ms.append(e0.elapsed_time(e1))
+    t0 = time.perf_counter()
+    got, info = hlcuda.bfgs_update(bs, Q, s, u, 1.0, 0.1, 1e-8, True, device=local)
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    out = {"workload": "Hessian of config 2: 10000 blocks of 30 + one of 20, eigenvalue control on",
+           "blocks": int(bs.size), "ms_device": float(np.mean(ms)),
+           "blocks_per_s_device": float(bs.size / (np.mean(ms) * 1e-3)),
+           "ms_e2e_host_buffers": e2e_ms, "blocks_shifted": info[0], "sweep_limit_hits": info[2],
+           "bytes_per_call": int(2 * Q.size * 8),
+           "frac_of_hbm": float(2 * Q.size * 8 / (np.mean(ms) * 1e-3) / 1e9 / measured_peaks()[0])}
+    # correctness of what was timed: sampled blocks against the restatement
+    from oracle import hl_bfgs_oracle
+    worst = 0.0
+    for k in (0, 4321, K - 1):
+        want, _, _ = hl_bfgs_oracle.update_block(Qb[k], s[k * n:(k + 1) * n], u[k * n:(k + 1) * n], 1.0, 0.1, 1e-8, True)
+        g = got[k * n * n:(k + 1) * n * n].reshape(n, n)
+        worst = max(worst, float(np.max(np.abs(np.triu(g - want))) / np.max(np.abs(want))))
+    if not worst < 1e-10:
+        raise RuntimeError(f"hl_bfgs: sampled blocks differ from the restatement ({worst})")
+    out["max_rel_diff_vs_oracle_sampled"] = worst
+    try:
+        from oracle import refharness
+        if refharness.available():
+            nb = 300
+            t0 = time.perf_counter()
+            for k in range(nb):
+                refharness.hl_bfgs_block(Qb[k], s[k * n:(k + 1) * n], u[k * n:(k + 1) * n], 1.0, 0.1, 1e-8, True)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nb / dt, "unit": "blocks/s", "cores": 1, "kind": "reference",
+                                   "sample": f"{nb} of {bs.size} blocks through Hqp_HL_BFGS::update_b_Q (ctypes call overhead included)"}
+    except Exception as ex:
+        out["cpu_baseline"] = {"error": str(ex)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -705,6 +774,10 @@ def run_ours(args):
                 extra["c3"] = sub
             except Exception as ex:
                 extra["c3"] = {"error": str(ex)}
+            try:
+                extra["hl_bfgs"] = run_hl_bfgs(local)
+            except Exception as ex:
+                extra["hl_bfgs"] = {"error": str(ex)}
         if rank == 0:
             line.update(extra)
     if rank == 0:

@@ -2,6 +2,7 @@
 GPU box with the repository snapshot).
 
   hqp_b200/lib/libhqpcuda.so   CUDA kernels + C ABI  (nvcc, sm_100a)
+  hqp_b200/lib/libhqphl.so     block-diagonal BFGS update, CUDA + C ABI (nvcc, sm_100a)
   hqp_b200/lib/libhqpsynth.so  seeded synthetic-workload generator (g++)
   hqp_b200/lib/libhqp_ipcuda_plugin.so   Hqp_IpCuda host module; only where the
                                 reference headers exist (/root/reference)
@@ -40,7 +41,8 @@ def _run(cmd, **kw):
 def build_cuda(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libhqpcuda.so")
-    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
+            if f.endswith((".cu", ".cuh", ".inc")) and f != "hl_bfgs.cu"]  # (hl_bfgs.cu: libhqphl.so)
     srcs.append(os.path.join(ROOT, "include", "hqp_ipcuda.h"))
     if force or _newer(out, srcs):
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
@@ -51,6 +53,17 @@ def build_cuda(force=False, verbose=False):
         r = _run(cmd)
         if verbose:
             print(r.stderr)
+    return out
+
+
+def build_hl(force=False):
+    """libhqphl.so: block-diagonal BFGS update on the GPU (include/hqp_hlcuda.h)."""
+    os.makedirs(LIB, exist_ok=True)
+    out = os.path.join(LIB, "libhqphl.so")
+    src = os.path.join(CSRC, "hl_bfgs.cu")
+    if force or _newer(out, [src, os.path.join(ROOT, "include", "hqp_hlcuda.h")]):
+        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+        _run(["nvcc", *flags, "-I" + os.path.join(ROOT, "include"), src, "-o", out, "-lcudart"])
     return out
 
 
@@ -87,6 +100,7 @@ def build_plugin(force=False):
 def build_all(force=False):
     build_synth(force)
     build_cuda(force)
+    build_hl(force)
     build_plugin(force)
 
 

@@ -28,6 +28,7 @@
 #include <If_Procedure.h>
 
 #include <Hqp.h>
+#include <Hqp_HL_BFGS.h>
 #include <Hqp_IpMatrix.h>
 #include <Hqp_IpsFranke.h>
 #include <Hqp_IpsMehrotra.h>
@@ -470,4 +471,36 @@ int ref_docp_did(int kmax, const char *qp_solver, const char *mat_solver,
   return 0;
 }
 
+
+// ---- row f2: the reference's own block update Hqp_HL_BFGS::update_b_Q
+// (hqp/Hqp_HL_BFGS.C:149-213; protected, reached through a subclass), on ONE dense
+// block Q (n x n, row-major, both triangles), in place
+class RefBfgsBlock : public Hqp_HL_BFGS {
+ public:
+  void block(const VEC *s, const VEC *u, Real alpha, MAT *Q, Real gamma, bool ec, Real eps) {
+    _gamma = gamma;
+    _eigen_control = ec;
+    _eps = eps;
+    _logging = false;
+    update_b_Q(s, u, alpha, Q);
+  }
+};
+
+int ref_hl_bfgs_block(int n, double *Q, const double *s, const double *u, double alpha,
+                      double gamma, double eps, int eigen_control) {
+  if (ref_init()) return -1;
+  static RefBfgsBlock *hl = NULL;
+  if (!hl) hl = new RefBfgsBlock();
+  MAT *M = m_get(n, n);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) M->me[i][j] = Q[(size_t)i * n + j];
+  VEC *vs = vec_from(s, n), *vu = vec_from(u, n);
+  hl->block(vs, vu, alpha, M, gamma, eigen_control != 0, eps);
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) Q[(size_t)i * n + j] = M->me[i][j];
+  m_free(M);
+  v_free(vs);
+  v_free(vu);
+  return 0;
+}
 }  // extern "C"

@@ -174,3 +174,19 @@ def docp_did(kmax=60, qp_solver="", mat_solver="LQDOCP", plugin="", with_cns=1, 
     if not lines:
         raise RuntimeError(f"docp_ref failed: rc={out.returncode}\n{out.stdout}\n{out.stderr}")
     return json.loads(lines[-1])
+
+
+def hl_bfgs_block(Q, s, u, alpha, gamma=0.1, eps=1e-8, eigen_control=True):
+    """The UNMODIFIED Hqp_HL_BFGS::update_b_Q (hqp/Hqp_HL_BFGS.C:149-213) on one dense
+    block (both triangles); returns the updated block."""
+    L = lib()
+    Q = np.array(Q, dtype=np.float64, order="C", copy=True)
+    n = Q.shape[0]
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    L.ref_hl_bfgs_block.restype = ctypes.c_int
+    rc = L.ref_hl_bfgs_block(ctypes.c_int(n), _dp(Q), _dp(s), _dp(u), ctypes.c_double(alpha),
+                             ctypes.c_double(gamma), ctypes.c_double(eps), ctypes.c_int(1 if eigen_control else 0))
+    if rc:
+        raise RuntimeError("ref_hl_bfgs_block failed")
+    return Q

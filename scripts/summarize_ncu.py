@@ -36,6 +36,8 @@ WANT = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size",
         "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
         "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.sum",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "dram__bytes_read.sum", "dram__bytes_write.sum",
