@@ -85,15 +85,19 @@ def build_plugin(force=False):
     out = os.path.join(LIB, "libhqp_ipcuda_plugin.so")
     if not os.path.isdir(os.path.join(REF, "hqp")) or not os.path.exists(src):
         return out if os.path.exists(out) else None
+    hl_src = os.path.join(HERE, "host", "Hqp_HL_CudaBFGS.C")
     if force or _newer(out, [src, hdr, os.path.join(HERE, "host", "Hqp_IpsCuda.C"),
-                             os.path.join(HERE, "host", "Hqp_IpsCuda.h"),
+                             os.path.join(HERE, "host", "Hqp_IpsCuda.h"), hl_src,
+                             os.path.join(HERE, "host", "Hqp_HL_CudaBFGS.h"),
+                             os.path.join(ROOT, "include", "hqp_hlcuda.h"),
                              os.path.join(ROOT, "include", "hqp_ipcuda.h")]):
+        build_hl()
         shim = os.path.join(ROOT, "oracle", "tclshim")
         _run(["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w", "-fpermissive",
               f"-I{REF}", f"-I{shim}", f"-I{REF}/iftcl", f"-I{REF}/hqp",
               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host"), src,
-              os.path.join(HERE, "host", "Hqp_IpsCuda.C"), "-o", out,
-              "-L" + LIB, "-lhqpcuda", "-Wl,-rpath,$ORIGIN"])
+              os.path.join(HERE, "host", "Hqp_IpsCuda.C"), hl_src, "-o", out,
+              "-L" + LIB, "-lhqpcuda", "-lhqphl", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

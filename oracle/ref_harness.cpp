@@ -503,4 +503,54 @@ int ref_hl_bfgs_block(int n, double *Q, const double *s, const double *u, double
   v_free(vu);
   return 0;
 }
+
+// ---- row f2 through the module interface: an Hqp_HL module by name ("BFGS" = the
+// reference, "CudaBFGS" = hqp_b200/host/Hqp_HL_CudaBFGS.C from the plugin library) is set
+// up on the QP's Hessian and asked for one update (Hqp_HL::setup / ::update)
+#include <Hqp_SqpProgram.h>
+class HarnessSqp : public Hqp_SqpProgram {
+ public:
+  explicit HarnessSqp(Hqp_Program *q) { _qp = q; }
+  ~HarnessSqp() { _qp = NULL; }  // (the QP belongs to the caller)
+  void setup() {}
+  void init_x() {}
+  void update_fbd() {}
+  void update(const VECP, const VECP) {}
+  const char *name() { return "harness"; }
+};
+
+int ref_hl_update(const char *hela, void *qp_, const double *s, const double *u, double alpha,
+                  double gamma, double eps, int eigen_control) {
+  if (ref_init()) return -1;
+  Hqp_Program *qp = (Hqp_Program *)qp_;
+  If_ClassList<Hqp_HL> *list = If_ClassList_Hqp_HL();
+  Hqp_HL *hl = list ? list->createObject(hela) : NULL;
+  if (!hl) return -2;
+  If_SetReal("sqp_hela_gamma", gamma);
+  If_SetReal("sqp_hela_eps", eps);
+  If_SetInt("sqp_hela_eigen_control", eigen_control != 0);  // (If_Bool accepts 0 / 1)
+  int rc = 0;
+  {
+    HarnessSqp prg(qp);
+    VEC *vs = vec_from(s, qp->Q->n), *vu = vec_from(u, qp->Q->n);
+    int code = 0;
+    m_catchall(hl->setup(&prg); hl->update(vs, vu, alpha, &prg), code = 1);
+    rc = code ? -3 : 0;
+    v_free(vs);
+    v_free(vu);
+  }
+  delete hl;
+  return rc;
+}
+
+// dense copy (both triangles) of the diagonal block offs .. offs+size-1 of the QP's Hessian
+int ref_qp_get_Q_block(void *qp_, int offs, int size, double *out) {
+  Hqp_Program *qp = (Hqp_Program *)qp_;
+  MAT *M = m_get(size, size);
+  symsp_extract_mat(qp->Q, offs, M);
+  for (int i = 0; i < size; i++)
+    for (int j = 0; j < size; j++) out[(size_t)i * size + j] = M->me[i][j];
+  m_free(M);
+  return 0;
+}
 }  // extern "C"

@@ -190,3 +190,22 @@ def hl_bfgs_block(Q, s, u, alpha, gamma=0.1, eps=1e-8, eigen_control=True):
     if rc:
         raise RuntimeError("ref_hl_bfgs_block failed")
     return Q
+
+
+def hl_update(qp: "RefQP", hela, s, u, alpha, gamma=0.1, eps=1e-8, eigen_control=True):
+    """Hqp_HL::setup + ::update of the module `hela` ("BFGS", or "CudaBFGS" after
+    load_plugin) on the QP's Hessian, in place."""
+    L = lib()
+    s = np.ascontiguousarray(s, dtype=np.float64)
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    L.ref_hl_update.restype = ctypes.c_int
+    rc = L.ref_hl_update(hela.encode(), qp.h, _dp(s), _dp(u), ctypes.c_double(alpha),
+                         ctypes.c_double(gamma), ctypes.c_double(eps), ctypes.c_int(1 if eigen_control else 0))
+    if rc:
+        raise RuntimeError(f"ref_hl_update({hela}) failed: {rc}")
+
+
+def qp_get_Q_block(qp: "RefQP", offs, size):
+    out = np.zeros((size, size))
+    lib().ref_qp_get_Q_block(qp.h, ctypes.c_int(offs), ctypes.c_int(size), _dp(out))
+    return out

@@ -133,3 +133,50 @@ def test_gpu_full_size_properties():
     for k in (0, 1234, K - 1):
         want, _, _ = O.update_block(Qb[k], s[k * n:(k + 1) * n], u[k * n:(k + 1) * n], 1.0, 0.1, 1e-8, True)
         assert upper_err(G[k], want) < TOL
+
+
+def _module_worker(hela, q):
+    """one process per module: the Hessian of a small DOCP after Hqp_HL::setup + ::update"""
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, ROOT)
+    from hqp_b200.problem import synth_lqdocp
+    from oracle import refharness as R
+    if hela != "BFGS":
+        R.load_plugin(_os.path.join(ROOT, "hqp_b200", "lib", "libhqp_ipcuda_plugin.so"))
+    nx, nu, K = 7, 4, 40
+    p = synth_lqdocp(nx, nu, K)
+    rng = np.random.default_rng(9)
+    s, u = rng.uniform(-1, 1, p.N), rng.uniform(-1, 1, p.N)
+    u[::3] *= -1.0
+    out = []
+    for ec in (True, False):
+        qp = R.RefQP(p)
+        R.hl_update(qp, hela, s, u, 0.6, -0.2, 1e-8, ec)
+        out.append([R.qp_get_Q_block(qp, k * (nx + nu), nx + nu) for k in range(K)] +
+                   [R.qp_get_Q_block(qp, K * (nx + nu), nx)])
+        qp.close()
+    q.put(out)
+
+
+@pytest.mark.gpu
+def test_module_cudabfgs_matches_the_reference_module():
+    """drop-in at the module boundary: sqp_hela CudaBFGS (hqp_b200/host/Hqp_HL_CudaBFGS.C, in
+    the plugin library) against the reference's sqp_hela BFGS, both driven through
+    Hqp_HL::setup / ::update on the same Hqp_Program by the unmodified host code"""
+    from oracle import refharness as R
+    plugin = os.path.join(ROOT, "hqp_b200", "lib", "libhqp_ipcuda_plugin.so")
+    if not (R.available() and os.path.exists(plugin)):
+        pytest.skip("oracle/_ref or the plugin library were not built (needs /root/reference at build time)")
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    res = {}
+    for hela in ("BFGS", "CudaBFGS"):
+        q = ctx.Queue()
+        pr = ctx.Process(target=_module_worker, args=(hela, q))
+        pr.start()
+        res[hela] = q.get(timeout=300)
+        pr.join()
+    for a_blocks, b_blocks in zip(res["BFGS"], res["CudaBFGS"]):
+        for a, b in zip(a_blocks, b_blocks):
+            assert upper_err(b, a) < TOL
