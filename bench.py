@@ -21,7 +21,8 @@ Workloads (BASELINE.json configs):
        N > 1: strong scaling, the horizon split into N contiguous stage ranges
   c5s  nx=40 nu=10 K=100,000 host-generated slice of the same shape
 The default line (workload c2) carries the other configurations as sub-objects
-(`c5`, and at N = 1 `c4` and `c3`) unless --no-extra is given.
+(`c5`, and at N = 1 `c4`, `c3`, and the next rows of SURVEY section 8: `hl_bfgs` = the
+block-diagonal BFGS update, `sqp_ops` = grd_L / merit functions) unless --no-extra is given.
 
 Multi-GPU: one process per GPU (torchrun); the horizon split lives in
 libhqpcuda.so (hqpcu_comm_init): NCCL all-gathers of the boundary elements /
@@ -714,6 +715,57 @@ def run_hl_bfgs(local):
     return out
 
 
+def run_sqp_ops(local):
+    """Row f3: grd_L and the merit functions on config 2's QP (N = 300,020) through the
+    host-pointer calls (H2D of the vectors inside the timed region), next to the reference's
+    own Meschach code on one host core."""
+    from hqp_b200.ipcuda import IpCuda
+    from hqp_b200.problem import synth_lqdocp
+    p = synth_lqdocp(20, 10, 10000)
+    rng = np.random.default_rng(5)
+    s, y, z = rng.uniform(-1, 1, p.N), rng.uniform(-1, 1, p.me), rng.uniform(0, 1, p.m)
+    re, r = rng.uniform(0, 2, p.me), rng.uniform(0, 2, p.m)
+    e = IpCuda(p, device=local)
+    e.update()
+    for _ in range(2):
+        g = e.sqp_grd_L(p.c, y, z)
+        m8 = e.sqp_merit(1.0, p.c, s, p.b, p.d, re, r)
+    reps = 5
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        g = e.sqp_grd_L(p.c, y, z)
+    t_g = (time.perf_counter() - t0) / reps * 1e3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        m8 = e.sqp_merit(1.0, p.c, s, p.b, p.d, re, r)
+    t_m = (time.perf_counter() - t0) / reps * 1e3
+    e.close()
+    out = {"workload": "config 2's QP: N=300020, me=200020, m=200000", "ms_grd_L_e2e": t_g,
+           "ms_merit_e2e": t_m, "note": "host buffers in, results out; merit = phi, phi1, s'Qs, c's, norms in one call"}
+    from oracle import sqp_oracle
+    want = sqp_oracle.merit(p, 1.0, p.c, s, p.b, p.d, re, r)
+    err = float(np.max(np.abs(m8[:4] - want[:4]) / np.maximum(1.0, np.abs(want[:4]))))
+    errg = float(np.max(np.abs(g - sqp_oracle.grd_L(p, p.c, y, z))))
+    if not (err < 1e-10 and errg < 1e-10):
+        raise RuntimeError(f"sqp_ops: results differ from the restatement ({err}, {errg})")
+    out["max_rel_diff_vs_oracle"] = max(err, errg)
+    try:
+        from oracle import refharness
+        if refharness.available():
+            qp = refharness.RefQP(p)
+            refharness.sqp_eval(qp, 1.0, s, y, z, re, r)
+            t0 = time.perf_counter()
+            for _ in range(3):
+                refharness.sqp_eval(qp, 1.0, s, y, z, re, r)
+            out["cpu_baseline"] = {"value": (time.perf_counter() - t0) / 3 * 1e3, "unit": "ms per grd_L + phi + phi1 + s'Qs",
+                                   "cores": 1, "kind": "reference",
+                                   "sample": "Hqp_SqpSolver::grd_L, Hqp_SqpPowell::phi/phi1, sp_mv_symmlt on the same QP"}
+            qp.close()
+    except Exception as ex:
+        out["cpu_baseline"] = {"error": str(ex)}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -778,6 +830,10 @@ def run_ours(args):
                 extra["hl_bfgs"] = run_hl_bfgs(local)
             except Exception as ex:
                 extra["hl_bfgs"] = {"error": str(ex)}
+            try:
+                extra["sqp_ops"] = run_sqp_ops(local)
+            except Exception as ex:
+                extra["sqp_ops"] = {"error": str(ex)}
         if rank == 0:
             line.update(extra)
     if rank == 0:

@@ -112,6 +112,7 @@ struct hqpcu_handle {
   double *t1 = nullptr, *t2 = nullptr, *t3 = nullptr, *t4 = nullptr;
   double *e1 = nullptr, *e2 = nullptr, *e3 = nullptr, *e4 = nullptr;
   double *res_dev = nullptr;
+  double *sqp_part = nullptr, *sqp_host = nullptr;  // reduction scratch of hqpcu_sqp_* (row f3)
   double *res_host = nullptr;  // pinned
   int *status_host = nullptr;  // pinned
   int status_seen = 0;         // status word as of the last residual read-back
@@ -780,6 +781,7 @@ int hqpcu_destroy(hqpcu_handle *h) {
   ips_free(h);
   dist_free(h);
   if (h->res_host) cudaFreeHost(h->res_host);
+  if (h->sqp_host) cudaFreeHost(h->sqp_host);
   if (h->status_host) cudaFreeHost(h->status_host);
   delete h;
   return HQPCU_OK;
@@ -1756,6 +1758,7 @@ int hqpcu_get_factor(hqpcu_handle *h, double *Vxx, double *Rux) {
 
 #include "hqp_ips_host.inc"
 #include "hqp_franke_host.inc"
+#include "hqp_sqp_host.inc"
 extern "C" {
 #include "hqp_mg_host.inc"
 int hqpcu_nseg(const hqpcu_handle *h) {

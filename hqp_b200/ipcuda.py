@@ -196,6 +196,32 @@ class IpCuda:
                "hqpcu_residuum")
         return res.value
 
+    # ---- SQP-level vector operations -----------------
+    def sqp_grd_L(self, c, y, z):
+        """c - A'y - C'z (Hqp_SqpSolver::grd_L, hqp/Hqp_SqpSolver.C:430-445) from the QP
+        values on the device."""
+        a = [np.ascontiguousarray(v, np.float64) for v in (c, y, z)]
+        out = np.zeros(self.N)
+        _check(lib().hqpcu_sqp_grd_L(self.h, *[_hp(v) for v in a], _hp(out)), "hqpcu_sqp_grd_L")
+        return out
+
+    def sqp_merit(self, f, c, s, b, d, re, r):
+        """[phi, phi1, s'Qs, c's, ||b||inf, ||min(d,0)||inf, sum re|As+b|, -sum r min(0,Cs+d)]
+        (Hqp_SqpPowell::phi / ::phi1, hqp/Hqp_SqpPowell.C:189-244; Hqp_SqpSolver::norm_inf
+        and s'Qs, hqp/Hqp_SqpSolver.C:155-174, 299-301)."""
+        a = [np.ascontiguousarray(v, np.float64) for v in (c, s, b, d, re, r)]
+        out = np.zeros(8)
+        _check(lib().hqpcu_sqp_merit(self.h, ctypes.c_double(f), *[_hp(v) for v in a], _hp(out)),
+               "hqpcu_sqp_merit")
+        return out
+
+    def sqp_quad(self, x):
+        """x'Qx (hqp/Hqp_SqpSolver.C:225-226)."""
+        x = np.ascontiguousarray(x, np.float64)
+        out = ctypes.c_double(0)
+        _check(lib().hqpcu_sqp_quad(self.h, _hp(x), ctypes.byref(out)), "hqpcu_sqp_quad")
+        return out.value
+
     def mehrotra_solve(self, c=None, b=None, d=None, eps=1e-9, max_iters=0, hot=None,
                        max_warm_iters=0):
         """Hqp_IpsMehrotra cold_start + solve on the device (hqpcu_mehrotra_solve);

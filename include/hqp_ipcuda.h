@@ -267,6 +267,23 @@ int hqpcu_franke_solve(hqpcu_handle *h, const double *c, const double *b, const 
  *     roofline section).  hqpcu_profile_read synchronises and writes a JSON
  *     object {"kernel": {"ms": total, "n": launches}, ...} for everything
  *     launched since the previous read.                                         */
+/* ---- SQP-level vector operations on the device-resident QP --
+ * What Hqp_SqpSolver / Hqp_SqpPowell compute around every QP solve with sparse mat-vecs
+ * over the whole horizon (hqp/Hqp_SqpSolver.C:155-174, 225-226, 258-259, 299-301, 430-445;
+ * hqp/Hqp_SqpPowell.C:189-244), from the Q / A / C values the last hqpcu_update left in
+ * HBM.  Vectors in the ABI's layout (the one hqpcu_step uses), host pointers.
+ *   grd_L = c - A'y - C'z
+ *   merit: out8 = { phi, phi1, s'Qs, c's, ||b||inf, ||min(d,0)||inf, sum re|As+b|,
+ *                   -sum r min(0, Cs+d) }  with  phi  = f + sum re|b| - sum r min(0,d),
+ *                                                 phi1 = f + c's + out8[6] + out8[7]
+ *   quad:  x'Qx
+ * One instance, one GPU (no batch, no split horizon). */
+int hqpcu_sqp_grd_L(hqpcu_handle *h, const double *c, const double *y, const double *z,
+                    double *grd_L);
+int hqpcu_sqp_merit(hqpcu_handle *h, double f, const double *c, const double *s, const double *b,
+                    const double *d, const double *re, const double *r, double *out8);
+int hqpcu_sqp_quad(hqpcu_handle *h, const double *x, double *xQx);
+
 int hqpcu_profile(hqpcu_handle *h, int on);
 int hqpcu_profile_read(hqpcu_handle *h, char *buf, int len);
 

@@ -553,4 +553,54 @@ int ref_qp_get_Q_block(void *qp_, int offs, int size, double *out) {
   m_free(M);
   return 0;
 }
+
+// ---- row f3: the reference's own SQP-level vector operations -- Hqp_SqpSolver::grd_L
+// (hqp/Hqp_SqpSolver.C:430-445), ::norm_inf (:155-174), x'Qx / s'Qs (:225-226, 299-301) and
+// Hqp_SqpPowell::phi / ::phi1 (hqp/Hqp_SqpPowell.C:189-244); protected members, reached
+// through a subclass working on the caller's Hqp_Program
+#include <Hqp_SqpPowell.h>
+class HarnessPowell : public Hqp_SqpPowell {
+ public:
+  // out8 = { phi, phi1, s'Qs, c's, ||b||inf via norm_inf part 1, max(0,-min d), 0, 0 }
+  void eval(HarnessSqp *prg, double f, const VEC *y, const VEC *z, const VEC *re, const VEC *r,
+            double *grd, double *out8) {
+    _prg = prg;
+    prg->set_f(f);
+    _y = v_copy(y, _y);
+    _z = v_copy(z, _z);
+    _re = v_copy(re, _re);
+    _r = v_copy(r, _r);
+    Hqp_Program *qp = prg->qp();
+    VEC *g = grd_L(qp, VNULL);
+    if (grd) memcpy(grd, g->ve, sizeof(double) * g->dim);
+    v_free(g);
+    out8[0] = phi();
+    out8[1] = phi1();
+    VEC *t = sp_mv_symmlt(qp->Q, qp->x, VNULL);
+    out8[2] = in_prod(t, qp->x);
+    v_free(t);
+    out8[3] = in_prod(qp->c, qp->x);
+    out8[4] = norm_inf(qp);
+    out8[5] = out8[6] = out8[7] = 0.0;
+    _prg = NULL;
+  }
+};
+
+// qp->x must hold the step s (ref_qp_set_x); y, z multipliers; re, r penalty weights
+int ref_sqp_eval(void *qp_, double f, const double *s, const double *y, const double *z,
+                 const double *re, const double *r, double *grd_L, double *out8) {
+  if (ref_init()) return -1;
+  Hqp_Program *qp = (Hqp_Program *)qp_;
+  static HarnessPowell *sp = NULL;
+  if (!sp) sp = new HarnessPowell();
+  const int n = qp->Q->m, me = qp->A->m, m = qp->C->m;
+  memcpy(qp->x->ve, s, sizeof(double) * n);
+  VEC *vy = vec_from(y, me), *vz = vec_from(z, m), *vre = vec_from(re, me), *vr = vec_from(r, m);
+  {
+    HarnessSqp prg(qp);
+    sp->eval(&prg, f, vy, vz, vre, vr, grd_L, out8);
+  }
+  v_free(vy); v_free(vz); v_free(vre); v_free(vr);
+  return 0;
+}
 }  // extern "C"

@@ -209,3 +209,19 @@ def qp_get_Q_block(qp: "RefQP", offs, size):
     out = np.zeros((size, size))
     lib().ref_qp_get_Q_block(qp.h, ctypes.c_int(offs), ctypes.c_int(size), _dp(out))
     return out
+
+
+def sqp_eval(qp: "RefQP", f, s, y, z, re, r):
+    """Row f3 on the reference: (grd_L, out8) with out8 = [phi, phi1, s'Qs, c's, norm_inf, ...]
+    from the UNMODIFIED Hqp_SqpSolver::grd_L / ::norm_inf and Hqp_SqpPowell::phi / ::phi1
+    (hqp/Hqp_SqpSolver.C:155-174, 430-445; hqp/Hqp_SqpPowell.C:189-244) on this QP with
+    qp->x = s."""
+    L = lib()
+    a = [np.ascontiguousarray(v, dtype=np.float64) for v in (s, y, z, re, r)]
+    grd = np.zeros(qp.n)
+    out8 = np.zeros(8)
+    L.ref_sqp_eval.restype = ctypes.c_int
+    rc = L.ref_sqp_eval(qp.h, ctypes.c_double(f), *[_dp(v) if v.size else None for v in a], _dp(grd), _dp(out8))
+    if rc:
+        raise RuntimeError("ref_sqp_eval failed")
+    return grd, out8
