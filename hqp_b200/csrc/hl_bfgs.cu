@@ -55,12 +55,13 @@ __device__ __forceinline__ double warp_min(double v) {
 }
 
 // smallest eigenvalue of the symmetric n x n matrix W (ld = n, destroyed) by one warp.
-// rot: 2 * (n/2 + 1) doubles of scratch (c, s per pair).  Returns the sweep count in *sweeps.
+// rot: 3 * (n/2 + 1) doubles of scratch (c, s and the index pair per rotation).  Returns the sweep count in *sweeps.
 __device__ double warp_jacobi_min_eig(double *W, int n, double *rot, int *sweeps) {
   const int lane = threadIdx.x & 31;
   const int ne = (n + 1) & ~1;  // players of the tournament (one dummy for odd n)
   const int np = ne >> 1;
   double *cs = rot, *sn = rot + np;
+  int *pq = reinterpret_cast<int *>(rot + 2 * np);  // [np][2]
   int sw = 0;
   for (; sw < 40; sw++) {
     // off-diagonal and total Frobenius norms
@@ -75,7 +76,8 @@ __device__ double warp_jacobi_min_eig(double *W, int n, double *rot, int *sweeps
     tot = warp_sum(tot);
     if (!(off > 1e-30 * tot) || !(tot > 0.0)) break;  // (relative 1e-15 on the norms; also NaN)
     for (int r = 0; r < ne - 1; r++) {
-      // pairs of round r: player ne-1 stays, the others rotate
+      // pairs of round r: player ne-1 stays, the others rotate; (p, q, c, s) per pair in
+      // shared memory, so that the two passes below carry no index arithmetic
       for (int k = lane; k < np; k += 32) {
         int p = k == 0 ? ne - 1 : (r + k) % (ne - 1);
         int q = (r + ne - 1 - k) % (ne - 1);
@@ -89,36 +91,38 @@ __device__ double warp_jacobi_min_eig(double *W, int n, double *rot, int *sweeps
             c = 1.0 / sqrt(1.0 + t * t);
             s = t * c;
           }
+        } else {
+          q = p;  // the dummy player of an odd n: identity on row p
         }
         cs[k] = c;
         sn[k] = s;
+        pq[2 * k] = p;
+        pq[2 * k + 1] = q;
       }
       __syncwarp();
-      // rows: (row p, row q) <- (c row p - s row q, s row p + c row q)
-      for (int e = lane; e < np * n; e += 32) {
-        const int k = e / n, j = e - k * n;
-        int p = k == 0 ? ne - 1 : (r + k) % (ne - 1);
-        int q = (r + ne - 1 - k) % (ne - 1);
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q < n) {
-          const double c = cs[k], s = sn[k];
-          const double x = W[p * n + j], y = W[q * n + j];
-          W[p * n + j] = c * x - s * y;
-          W[q * n + j] = s * x + c * y;
+      // rows: (row p, row q) <- (c row p - s row q, s row p + c row q); lanes along the row
+      for (int k = 0; k < np; k++) {
+        const int p = pq[2 * k], q = pq[2 * k + 1];
+        const double c = cs[k], s = sn[k];
+        if (s != 0.0) {
+          for (int j = lane; j < n; j += 32) {
+            const double x = W[p * n + j], y = W[q * n + j];
+            W[p * n + j] = c * x - s * y;
+            W[q * n + j] = s * x + c * y;
+          }
         }
       }
       __syncwarp();
-      // columns
-      for (int e = lane; e < np * n; e += 32) {
-        const int k = e / n, i = e - k * n;
-        int p = k == 0 ? ne - 1 : (r + k) % (ne - 1);
-        int q = (r + ne - 1 - k) % (ne - 1);
-        if (p > q) { const int t = p; p = q; q = t; }
-        if (q < n) {
-          const double c = cs[k], s = sn[k];
-          const double x = W[i * n + p], y = W[i * n + q];
-          W[i * n + p] = c * x - s * y;
-          W[i * n + q] = s * x + c * y;
+      // columns; lanes along the column
+      for (int k = 0; k < np; k++) {
+        const int p = pq[2 * k], q = pq[2 * k + 1];
+        const double c = cs[k], s = sn[k];
+        if (s != 0.0) {
+          for (int i = lane; i < n; i += 32) {
+            const double x = W[i * n + p], y = W[i * n + q];
+            W[i * n + p] = c * x - s * y;
+            W[i * n + q] = s * x + c * y;
+          }
         }
       }
       __syncwarp();
@@ -130,11 +134,35 @@ __device__ double warp_jacobi_min_eig(double *W, int n, double *rot, int *sweeps
   return warp_min(mn);
 }
 
-// one warp per block; dynamic shared memory: per warp 2 max_n^2 + 5 max_n + 4 doubles
+// true iff W - theta I is positive definite: LDL' without interchanges, all pivots > 0
+// (W destroyed).  lambda_min(W) > theta then needs no eigenvalue at all -- the usual case
+// for a damped BFGS matrix; only blocks that fail pay for the Jacobi iteration.
+__device__ bool warp_pd_certificate(double *W, int n, double theta) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) W[i * n + i] -= theta;
+  __syncwarp();
+  for (int p = 0; p < n; p++) {
+    const double d = W[p * n + p];
+    if (!(d > 0.0)) return false;  // (the same value on every lane)
+    const double inv = 1.0 / d;
+    const int r = n - p - 1;
+    for (int e = lane; e < r * r; e += 32) {
+      const int ii = e / r, jj = e - ii * r;
+      if (jj <= ii) {
+        const int i = p + 1 + ii, j = p + 1 + jj;
+        W[i * n + j] = fma(-W[i * n + p] * inv, W[j * n + p], W[i * n + j]);
+      }
+    }
+    __syncwarp();
+  }
+  return true;
+}
+
+// one warp per block; dynamic shared memory: per warp 2 max_n^2 + 6 max_n + 8 doubles
 __global__ void hl_bfgs_kernel(BfgsArgs a) {
   extern __shared__ __align__(16) double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  const size_t per = (size_t)2 * a.max_n * a.max_n + 5 * a.max_n + 4;
+  const size_t per = (size_t)2 * a.max_n * a.max_n + 6 * a.max_n + 8;
   double *Qb = smem + warp * per;
   double *W = Qb + (size_t)a.max_n * a.max_n;
   double *sv_ = W + (size_t)a.max_n * a.max_n;   // s
@@ -203,12 +231,17 @@ __global__ void hl_bfgs_kernel(BfgsArgs a) {
       if (sQs < theta && sQs >= 0.0) theta = sQs;
       for (int e = lane; e < n * n; e += 32) W[e] = Qb[e];
       __syncwarp();
-      int sweeps;
-      const double lmin = warp_jacobi_min_eig(W, n, rot, &sweeps) - theta;
-      if (lmin < 0.0) shift = -lmin;
-      if (lane == 0) {
-        if (shift != 0.0) atomicAdd(&a.info[0], 1);
-        if (sweeps >= 40) atomicAdd(&a.info[2], 1);
+      if (!warp_pd_certificate(W, n, theta)) {
+        __syncwarp();
+        for (int e = lane; e < n * n; e += 32) W[e] = Qb[e];
+        __syncwarp();
+        int sweeps;
+        const double lmin = warp_jacobi_min_eig(W, n, rot, &sweeps) - theta;
+        if (lmin < 0.0) shift = -lmin;
+        if (lane == 0) {
+          if (shift != 0.0) atomicAdd(&a.info[0], 1);
+          if (sweeps >= 40) atomicAdd(&a.info[2], 1);
+        }
       }
     }
     for (int e = lane; e < n * n; e += 32) {
@@ -235,7 +268,7 @@ int launch(const BfgsArgs &a, cudaStream_t st) {
   int dev = 0, sms = 148;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  const size_t per = ((size_t)2 * a.max_n * a.max_n + 5 * a.max_n + 4) * sizeof(double);
+  const size_t per = ((size_t)2 * a.max_n * a.max_n + 6 * a.max_n + 8) * sizeof(double);
   int warps = (int)std::min<size_t>(8, (200 * 1024) / per);
   if (warps < 1) return fail("hqphl: block too large for the shared-memory kernel", HQPHL_E_UNSUPPORTED);
   CU(cudaFuncSetAttribute(hl_bfgs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per * warps)));
