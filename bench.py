@@ -410,7 +410,7 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
     # ---- warm-up ---------------------------------------------------------
     # (clocks are sampled by rank 0 only, from before the warm-up until after the e2e
     #  loops: the timed region of a 0.7 ms unit is shorter than nvidia-smi's period)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("HQP_BENCH_NOCLOCKS") else None
     if sampler:
         sampler.start()
     # a split horizon gets a few extra untimed units: the first replays of graphs
@@ -436,6 +436,7 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
     gpu_launches = eng.launches - launches0
     ms = [e0.elapsed_time(e1) for e0, e1 in ev]
     ms_step = float(np.mean(ms))
+    ms_spread = {"min": float(np.min(ms)), "median": float(np.median(ms)), "max": float(np.max(ms))}
 
     # ---- correctness of what was timed: refined solve, KKT residual (max over the
     # ranks, all-reduced inside the library) -- asserted before anything is printed
@@ -625,6 +626,7 @@ def run_workload(args, key, steps, warmup, dist_group, extras=True):
             "config": cfg,
             "details": {"segments_per_instance": nseg, "parallelism": parallelism,
                         "l2": "flushed (256 MiB write) between timed iterations",
+                        "ms_per_step_spread_rank0": ms_spread,
                         "kkt_residual_after_refined_solve": res, "kkt_steps_in_that_solve": nsolve},
             "roofline": roofline,
             "e2e": {"value": Kg / e2e_max["pinned"], "unit": UNIT,
