@@ -546,27 +546,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, const double *C0,
-                                           int ldc0, double beta, double alpha, const double *A,
-                                           int ar, int ac, const double *B, int br, int bc, int M,
-                                           int N, int Kd, int wofs, int warp_log, int nwarps) {
-  (void)wofs;
+// (the core is not inlined: ~40 call sites in the large-block kernels; four copies -- one per
+//  pair of operand orientations, so that the fragment addressing keeps constant strides --
+//  hold the build of the library at a third of the time of full inlining, and a call costs
+//  nothing next to a 10^5-cycle product)
+template <bool TA, bool TB>
+__device__ __noinline__ void cta_mm_big_core(double *stg, double *C, int crs, int ccs, const double *C0,
+                                             int c0rs, int c0cs, double beta, double alpha,
+                                             const double *A, int ar, int ac, const double *B, int br,
+                                             int bc, int M, int N, int Kd, int warp_log, int nwarps) {
   constexpr int KC = LQ_BIG_KC, NS = LQ_BIG_NS, LDS = LQ_BIG_LDS, RT = LQ_BIG_RT, CT = LQ_BIG_CT;
   constexpr int WR = 8 * RT, WC = 8 * CT;  // rows / columns of a warp block
   __shared__ __align__(8) uint64_t bars[2 * NS];  // full[NS] (bytes landed), empty[NS] (warps done)
   uint64_t *full = bars, *empty = bars + NS;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int lt = warp_log * 32 + lane, nt = nwarps * 32;
-  // a product with few rows is computed as C' = B' A' (the CTA tile is tall): the
-  // operands swap roles and the result is stored through transposed strides
-  int crs = ldc, ccs = 1, c0rs = ldc0, c0cs = 1;
-  if (M <= 2 * WR && N > M) {
-    const double *tp = A; A = B; B = tp;
-    int ti = ar; ar = bc; bc = ti;
-    ti = ac; ac = br; br = ti;
-    ti = M; M = N; N = ti;
-    crs = 1; ccs = ldc; c0rs = 1; c0cs = ldc0;
-  }
   // warp grid of a CTA tile
   int wnb = nwarps >= 15 ? 3 : (nwarps >= 8 ? 2 : 1);
   int wmb = nwarps / wnb < 5 ? nwarps / wnb : 5;
@@ -575,7 +569,7 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
   const int wr = warp_log / wnb, wc = warp_log - wr * wnb;
   const bool cw = warp_log < ncw;  // this warp computes
   // operand orientation -> panel layout; bulk copies where the 16-byte rules hold
-  const bool ta = ar == 1 && ac != 1, tb = bc == 1 && br != 1;
+  constexpr bool ta = TA, tb = TB;
   // (a subset of the CTA's warps takes the plain path as well)
 #ifndef LQ_BIG_SUBFAST
 #define LQ_BIG_SUBFAST 0
@@ -895,6 +889,33 @@ __device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, cons
       }
     }
   }
+}
+
+// C (M x N, ldc) = beta * C0 + alpha * A * B: orientation dispatch in front of the core
+__device__ __forceinline__ void cta_mm_big(double *stg, double *C, int ldc, const double *C0,
+                                           int ldc0, double beta, double alpha, const double *A,
+                                           int ar, int ac, const double *B, int br, int bc, int M,
+                                           int N, int Kd, int wofs, int warp_log, int nwarps) {
+  (void)wofs;
+  // a product with few rows is computed as C' = B' A' (the CTA tile is tall): the
+  // operands swap roles and the result is stored through transposed strides
+  int crs = ldc, ccs = 1, c0rs = ldc0, c0cs = 1;
+  if (M <= 2 * 8 * LQ_BIG_RT && N > M) {
+    const double *tp = A; A = B; B = tp;
+    int ti = ar; ar = bc; bc = ti;
+    ti = ac; ac = br; br = ti;
+    ti = M; M = N; N = ti;
+    crs = 1; ccs = ldc; c0rs = 1; c0cs = ldc0;
+  }
+  const bool ta = ar == 1 && ac != 1, tb = bc == 1 && br != 1;
+  if (ta && tb)
+    cta_mm_big_core<true, true>(stg, C, crs, ccs, C0, c0rs, c0cs, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, warp_log, nwarps);
+  else if (ta)
+    cta_mm_big_core<true, false>(stg, C, crs, ccs, C0, c0rs, c0cs, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, warp_log, nwarps);
+  else if (tb)
+    cta_mm_big_core<false, true>(stg, C, crs, ccs, C0, c0rs, c0cs, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, warp_log, nwarps);
+  else
+    cta_mm_big_core<false, false>(stg, C, crs, ccs, C0, c0rs, c0cs, beta, alpha, A, ar, ac, B, br, bc, M, N, Kd, warp_log, nwarps);
 }
 
 // compile-time choice between the tensor-core and the FMA product
