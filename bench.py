@@ -683,9 +683,11 @@ def run_hl_bfgs(local):
         torch.cuda.synchronize()
         if it >= 3:
             ms.append(e0.elapsed_time(e1))
-    t0 = time.perf_counter()
-    got, info = hlcuda.bfgs_update(bs, Q, s, u, 1.0, 0.1, 1e-8, True, device=local)
-    e2e_ms = (time.perf_counter() - t0) * 1e3
+    e2e_ms = float("inf")
+    for _ in range(3):  # (best of three: the call allocates and frees its device buffers)
+        t0 = time.perf_counter()
+        got, info = hlcuda.bfgs_update(bs, Q, s, u, 1.0, 0.1, 1e-8, True, device=local)
+        e2e_ms = min(e2e_ms, (time.perf_counter() - t0) * 1e3)
     out = {"workload": "Hessian of config 2: 10000 blocks of 30 + one of 20, eigenvalue control on",
            "blocks": int(bs.size), "ms_device": float(np.mean(ms)),
            "blocks_per_s_device": float(bs.size / (np.mean(ms) * 1e-3)),

@@ -258,6 +258,25 @@ def test_large_blocks_match_cpu_oracle(cfg):
     e.close(); o.close()
 
 
+def test_large_blocks_two_sweep_tree(monkeypatch):
+    """the up / down sweep of the binary tree (HQPCU_HS=0) on the global-workspace path:
+    elem_compose_kernel<0> / elem_scan_kernel<0> with the blocked elimination"""
+    monkeypatch.setenv("HQPCU_HS", "0")
+    p = make_problem(70, 20, 48, 1, 0, 1)
+    z, w, r1, r2, r3, r4 = rhs_for(p, seed=43)
+    o = PortOracle(p)
+    o.factor(z, w)
+    ref = o.step(r1, r2, r3, r4)
+    e = IpCuda(p)
+    assert e.nseg > 2
+    e.update()
+    e.factor(z, w)
+    mine = e.step(r1, r2, r3, r4)
+    for a, b in zip(mine, ref):
+        assert relerr(a, b) < TOL
+    e.close(); o.close()
+
+
 @pytest.mark.skipif(not _ref_available(), reason="compiled reference (oracle/_ref) not present")
 def test_c4_truncated_horizon_matches_live_reference():
     """BASELINE config 4 (nx=200 nu=50) on a K=100 truncation against the
