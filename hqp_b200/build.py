@@ -3,6 +3,7 @@ GPU box with the repository snapshot).
 
   hqp_b200/lib/libhqpcuda.so   CUDA kernels + C ABI  (nvcc, sm_100a)
   hqp_b200/lib/libhqphl.so     block-diagonal BFGS update, CUDA + C ABI (nvcc, sm_100a)
+  hqp_b200/lib/libhqpdocp.so   stage loop of Hqp_Docp::update for device models (nvcc, sm_100a)
   hqp_b200/lib/libhqpsynth.so  seeded synthetic-workload generator (g++)
   hqp_b200/lib/libhqp_ipcuda_plugin.so   Hqp_IpCuda host module; only where the
                                 reference headers exist (/root/reference)
@@ -42,7 +43,7 @@ def build_cuda(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
     out = os.path.join(LIB, "libhqpcuda.so")
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)
-            if f.endswith((".cu", ".cuh", ".inc")) and f != "hl_bfgs.cu"]  # (hl_bfgs.cu: libhqphl.so)
+            if f.endswith((".cu", ".cuh", ".inc")) and f not in ("hl_bfgs.cu", "docp_update.cu", "docp_models.cuh")]  # (own libraries)
     srcs.append(os.path.join(ROOT, "include", "hqp_ipcuda.h"))
     if force or _newer(out, srcs):
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
@@ -64,6 +65,19 @@ def build_hl(force=False):
     if force or _newer(out, [src, os.path.join(ROOT, "include", "hqp_hlcuda.h")]):
         flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
         _run(["nvcc", *flags, "-I" + os.path.join(ROOT, "include"), src, "-o", out, "-lcudart"])
+    return out
+
+
+def build_docp(force=False):
+    """libhqpdocp.so: the stage loop of Hqp_Docp::update on the GPU (include/hqp_docpcuda.h).
+    -fmad=false: the model code must round like its CPU restatements (docp_models.cuh)."""
+    os.makedirs(LIB, exist_ok=True)
+    out = os.path.join(LIB, "libhqpdocp.so")
+    src = os.path.join(CSRC, "docp_update.cu")
+    if force or _newer(out, [src, os.path.join(CSRC, "docp_models.cuh"),
+                             os.path.join(ROOT, "include", "hqp_docpcuda.h")]):
+        flags = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+        _run(["nvcc", *flags, "-fmad=false", "-I" + os.path.join(ROOT, "include"), src, "-o", out, "-lcudart"])
     return out
 
 
@@ -105,6 +119,7 @@ def build_all(force=False):
     build_synth(force)
     build_cuda(force)
     build_hl(force)
+    build_docp(force)
     build_plugin(force)
 
 

@@ -225,3 +225,50 @@ def sqp_eval(qp: "RefQP", f, s, y, z, re, r):
     if rc:
         raise RuntimeError("ref_sqp_eval failed")
     return grd, out8
+
+
+class RefDocp:
+    """Row f4: the UNMODIFIED Hqp_Docp (setup / update / update_fbd / update_grds /
+    update_bounds) driven for the reference's Prg_DID (model 0) or for the synthetic model
+    restated as an Hqp_Docp subclass in oracle/prg_synthnl.cpp (model 1).  prob: an
+    hqp_b200.docpcuda.DocpProblem (dimensions, parameters, start values)."""
+
+    def __init__(self, prob):
+        L = lib()
+        L.ref_docp_create.restype = ctypes.c_void_p
+        par = np.ascontiguousarray(prob.par, dtype=np.float64)
+        spar = np.ascontiguousarray(prob.spar, dtype=np.float64)
+        xin = np.ascontiguousarray(prob.x_init, dtype=np.float64)
+        nspar = spar.shape[1] if spar.ndim == 2 else 0
+        self.h = ctypes.c_void_p(L.ref_docp_create(
+            int(prob.model), prob.K, prob.nx, prob.nu, prob.nc, prob.ncK, _dp(par), par.size,
+            _dp(spar) if spar.size else None, nspar, _dp(xin)))
+        if not self.h:
+            raise RuntimeError("ref_docp_create failed")
+        n, me, m = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        L.ref_docp_sizes(self.h, ctypes.byref(n), ctypes.byref(me), ctypes.byref(m))
+        self.N, self.me, self.m = n.value, me.value, m.value
+
+    def x(self):
+        out = np.empty(self.N)
+        lib().ref_docp_get_x(self.h, _dp(out))
+        return out
+
+    def update(self, x=None, fbd_only=False, matrices=True):
+        """Returns dict f, b, d, c (qp->c) and -- unless fbd_only -- dense A [me,N], C [m,N]."""
+        f = ctypes.c_double()
+        b, d, c = np.empty(self.me), np.empty(max(1, self.m)), np.empty(self.N)
+        want = matrices and not fbd_only
+        A = np.empty((self.me, self.N)) if want else None
+        C = np.empty((max(1, self.m), self.N)) if want else None
+        xa = np.ascontiguousarray(x, dtype=np.float64) if x is not None else None
+        rc = lib().ref_docp_update(self.h, _dp(xa), int(bool(fbd_only)), ctypes.byref(f), _dp(b), _dp(d),
+                                   _dp(c), _dp(A), _dp(C))
+        if rc:
+            raise RuntimeError(f"ref_docp_update: {rc}")
+        return dict(f=f.value, b=b, d=d[:self.m], c=c, A=A, C=C[:self.m] if C is not None else None)
+
+    def close(self):
+        if self.h:
+            lib().ref_docp_free(self.h)
+            self.h = None
