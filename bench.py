@@ -22,7 +22,7 @@ Workloads (BASELINE.json configs):
   c5s  nx=40 nu=10 K=100,000 host-generated slice of the same shape
 The default line (workload c2) carries the other configurations as sub-objects
 (`c5`, and at N = 1 `c4`, `c3`, and the next rows of SURVEY section 8: `hl_bfgs` = the
-block-diagonal BFGS update, `sqp_ops` = grd_L / merit functions) unless --no-extra is given.
+block-diagonal BFGS update, `sqp_ops` = grd_L / merit functions, `docp_update` = the stage loop of Hqp_Docp::update) unless --no-extra is given.
 
 Multi-GPU: one process per GPU (torchrun); the horizon split lives in
 libhqpcuda.so (hqpcu_comm_init): NCCL all-gathers of the boundary elements /
@@ -719,6 +719,98 @@ def run_hl_bfgs(local):
     return out
 
 
+def run_docp_update(local):
+    """Row f4: the stage loop of Hqp_Docp::update (values + derivatives of every stage, bounds)
+    for the synthetic nonlinear model at config 2's shape (K = 10^4, nx 20, nu 10, one path
+    constraint) and at a slice of config 5's (K = 10^5, nx 40, nu 10).  Device-resident time per
+    call (CUDA events, L2 flushed), end to end with host buffers through hqpdocp_update, and the
+    unmodified Hqp_Docp::update on one host core for a truncated horizon."""
+    import torch
+    from hqp_b200 import docpcuda as dc
+    from oracle import docp_oracle
+    dev = torch.device("cuda", local)
+    flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    peak = measured_peaks()[0]
+    out = {}
+    for key, (K, nx, nu) in (("c2_shape", (10000, 20, 10)), ("c5_slice", (100000, 40, 10))):
+        p = dc.synthnl_problem(K, nx, nu, 1, 1, seed=3)
+        e = dc.DocpCuda(p, device=local)
+        e.set_stream(stream)
+        t = lambda n: torch.empty(max(1, n), dtype=torch.float64, device=dev)
+        xd = torch.from_numpy(p.x_init).to(dev)
+        fo, b, d, g = t(1), t(p.me), t(p.m), t(p.N)
+        fx, fu, cx, cu = t(K * nx * nx), t(K * nx * nu), t(p.ncns * nx), t(K * p.nc * nu)
+        res = {"workload": f"synthetic nonlinear DOCP, K={K} nx={nx} nu={nu} nc=1: N={p.N}, me={p.me}, m={p.m}"}
+        # algorithmic bytes of one update: every output written once, x and the stage
+        # parameters read once (the model matrices A, B are shared by all stages)
+        nd = nx + nu
+        bytes_upd = 8 * (K * (nx * nx + nx * nu + p.nc * nd) + 2 * p.N + p.me + p.m + (K + 1) * nx)
+        bytes_fbd = 8 * (p.N + p.me + p.m + (K + 1) * nx)
+        for name, call, nbytes in (
+                ("update_ad", lambda: e.update_dev(xd, fo, b, d, g, fx, fu, cx, cu, dc.GRAD_AD), bytes_upd),
+                ("update_fd", lambda: e.update_dev(xd, fo, b, d, g, fx, fu, cx, cu, dc.GRAD_FD), bytes_upd),
+                ("update_fbd", lambda: e.update_fbd_dev(xd, fo, b, d), bytes_fbd)):
+            ms = []
+            for it in range(8):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                call()
+                e1.record()
+                torch.cuda.synchronize()
+                if it >= 3:
+                    ms.append(e0.elapsed_time(e1))
+            m = float(np.mean(ms))
+            res[name] = {"ms_device": m, "stages_per_s": (K + 1) / (m * 1e-3), "algorithmic_bytes": int(nbytes),
+                         "frac_of_hbm": float(nbytes / (m * 1e-3) / 1e9 / peak)}
+        if key == "c2_shape":
+            e2e = float("inf")
+            for _ in range(3):
+                t0 = time.perf_counter()
+                got = e.update(p.x_init, dc.GRAD_FD)
+                e2e = min(e2e, (time.perf_counter() - t0) * 1e3)
+            res["update_fd"]["ms_e2e_host_buffers"] = e2e
+            # correctness of what was timed: sampled stages against the restatement
+            worst = 0.0
+            for k in (0, 4321, K - 1, K):
+                x, u = docp_oracle._stage(p, p.x_init, k)
+                jfx, jfu, f0x, f0u, jcx, jcu = docp_oracle.grds_fd(p, k, x, u)
+                if k < K:
+                    worst = max(worst, float(np.max(np.abs(got["fx"][k] - jfx))), float(np.max(np.abs(got["fu"][k] - jfu))))
+                worst = max(worst, float(np.max(np.abs(got["g"][k * nd:k * nd + nx] - f0x))))
+            if not worst < 1e-9:
+                raise RuntimeError(f"docp_update: sampled stages differ from the restatement ({worst})")
+            res["max_abs_diff_vs_oracle_sampled"] = worst
+            try:
+                from oracle import refharness
+                if refharness.available():
+                    Ks = 1000
+                    ps = dc.synthnl_problem(Ks, nx, nu, 1, 1, seed=3)
+                    r = refharness.RefDocp(ps)
+                    r.update(ps.x_init, matrices=False)
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        r.update(ps.x_init, matrices=False)
+                    dt = (time.perf_counter() - t0) / 3
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        r.update(ps.x_init, fbd_only=True)
+                    dtv = (time.perf_counter() - t0) / 3
+                    r.close()
+                    res["cpu_baseline"] = {"value": (Ks + 1) / dt, "unit": "stages/s (update)", "cores": 1,
+                                           "kind": "reference", "update_fbd_stages_per_s": (Ks + 1) / dtv,
+                                           "sample": f"K={Ks} of {K}: unmodified Hqp_Docp::update (default update_grds) "
+                                                     "with the model restated as an Hqp_Docp subclass"}
+            except Exception as ex:
+                res["cpu_baseline"] = {"error": str(ex)}
+        res["gpu_launches_per_update"] = 4
+        e.close()
+        del fx, fu, cx, cu, xd, b, d, g
+        out[key] = res
+    return out
+
+
 def run_sqp_ops(local):
     """Row f3: grd_L and the merit functions on config 2's QP (N = 300,020) through the
     host-pointer calls (H2D of the vectors inside the timed region), next to the reference's
@@ -838,6 +930,10 @@ def run_ours(args):
                 extra["sqp_ops"] = run_sqp_ops(local)
             except Exception as ex:
                 extra["sqp_ops"] = {"error": str(ex)}
+            try:
+                extra["docp_update"] = run_docp_update(local)
+            except Exception as ex:
+                extra["docp_update"] = {"error": str(ex)}
         if rank == 0:
             line.update(extra)
     if rank == 0:

@@ -100,18 +100,22 @@ def build_plugin(force=False):
     if not os.path.isdir(os.path.join(REF, "hqp")) or not os.path.exists(src):
         return out if os.path.exists(out) else None
     hl_src = os.path.join(HERE, "host", "Hqp_HL_CudaBFGS.C")
+    did_src = os.path.join(HERE, "host", "Prg_DIDCuda.C")
     if force or _newer(out, [src, hdr, os.path.join(HERE, "host", "Hqp_IpsCuda.C"),
                              os.path.join(HERE, "host", "Hqp_IpsCuda.h"), hl_src,
-                             os.path.join(HERE, "host", "Hqp_HL_CudaBFGS.h"),
+                             os.path.join(HERE, "host", "Hqp_HL_CudaBFGS.h"), did_src,
+                             os.path.join(HERE, "host", "Hqp_DocpCuda.h"),
+                             os.path.join(ROOT, "include", "hqp_docpcuda.h"),
                              os.path.join(ROOT, "include", "hqp_hlcuda.h"),
                              os.path.join(ROOT, "include", "hqp_ipcuda.h")]):
         build_hl()
+        build_docp()
         shim = os.path.join(ROOT, "oracle", "tclshim")
         _run(["g++", "-std=c++11", "-O2", "-fPIC", "-shared", "-w", "-fpermissive",
-              f"-I{REF}", f"-I{shim}", f"-I{REF}/iftcl", f"-I{REF}/hqp",
+              f"-I{REF}", f"-I{shim}", f"-I{REF}/iftcl", f"-I{REF}/hqp", f"-I{REF}/hqp_docp",
               "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(HERE, "host"), src,
-              os.path.join(HERE, "host", "Hqp_IpsCuda.C"), hl_src, "-o", out,
-              "-L" + LIB, "-lhqpcuda", "-lhqphl", "-Wl,-rpath,$ORIGIN"])
+              os.path.join(HERE, "host", "Hqp_IpsCuda.C"), hl_src, did_src, "-o", out,
+              "-L" + LIB, "-lhqpcuda", "-lhqphl", "-lhqpdocp", "-Wl,-rpath,$ORIGIN"])
     return out
 
 

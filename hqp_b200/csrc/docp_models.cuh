@@ -2,11 +2,15 @@
 // row f4).  A model is the device counterpart of an Hqp_Docp subclass' update_vals()
 // (hqp/Hqp_Docp.h:75-76): ONE function template over the scalar type,
 //
-//   template <class T> static __device__ void vals(const ModelArgs &m, int k,
-//                                                  const T *x, const T *u, T *f, T &f0, T *c);
+//   template <class T, class In, class Out>
+//   static __device__ void vals(const ModelArgs &m, int k, const In &x, const In &u,
+//                               Out &f, T &f0, Out &c);
 //
-// instantiated with double (values, forward differences) and with Dual (forward-mode
-// derivatives).  Operation order is part of the contract: the CPU restatements
+// instantiated with T = double (values, forward differences) and T = Dual (forward-mode
+// derivatives).  x[i] / u[i] yield a T; f[i] = ... / c[i] = ... accept a T and are WRITE-ONLY
+// (the kernels hand in views: inputs come from a stage vector shared by all column threads
+// with the thread's own column perturbed or seeded, outputs go straight to a shared-memory
+// tile or to HBM -- no per-thread arrays, nothing in local memory).  Operation order is part of the contract: the CPU restatements
 // (oracle/docp_oracle.py, oracle/prg_synthnl.cpp) evaluate the same expressions in the same
 // order, the library is compiled with -fmad=false, so values agree to the last bit and
 // differences quotients (which amplify rounding by 1e4..1e6) stay comparable.
@@ -51,8 +55,8 @@ struct ModelDID {
   static bool dims_ok(int nx, int nu, int nc, int ncK, int npar, int nspar) {
     return nx == 2 && nu == 1 && (nc == 0 || nc == 1) && ncK == 0 && npar == 1 && nspar == 0;
   }
-  template <class T>
-  static __device__ void vals(const ModelArgs &m, int k, const T *x, const T *u, T *f, T &f0, T *c) {
+  template <class T, class In, class Out>
+  static __device__ void vals(const ModelArgs &m, int k, const In &x, const In &u, Out &f, T &f0, Out &c) {
     const double dt = m.par[0];
     if (k < m.K) {
       f[0] = x[0] + u[0] * dt;
@@ -78,8 +82,8 @@ struct ModelSynthNL {
     return nx >= 1 && nu >= 1 && nc <= nx && ncK <= nx &&
            npar == 1 + nx * nx + nx * nu + nx + nu && nspar == nx;
   }
-  template <class T>
-  static __device__ void vals(const ModelArgs &m, int k, const T *x, const T *u, T *f, T &f0, T *c) {
+  template <class T, class In, class Out>
+  static __device__ void vals(const ModelArgs &m, int k, const In &x, const In &u, Out &f, T &f0, Out &c) {
     const int nx = m.nx, nu = m.nu;
     const double eps = m.par[0];
     const double *A = m.par + 1, *B = A + nx * nx, *qw = B + nx * nu, *rw = qw + nx;

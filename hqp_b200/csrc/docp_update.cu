@@ -6,11 +6,12 @@
 //
 // Kernels (all streaming; nothing is re-read from HBM except the iterate x, which the
 // nx+nu column threads of a stage share through L1/L2):
-//   docp_vals_kernel   one thread per stage: f_k, f0_k, c_k; writes b's dynamics rows
-//                      (f_k - x_{k+1}), the stage objective and the constraint values
-//   docp_grds_kernel   one thread per (stage, variable): one perturbed evaluation (FD) or one
-//                      dual-number evaluation (AD); lanes of a warp hold neighbouring columns
-//                      of the same stage, so the row-major fx/fu/cx/cu stores coalesce
+//   docp_vals_kernel   (update_fbd) one thread per stage: f_k, f0_k, c_k; writes b's dynamics
+//                      rows (f_k - x_{k+1}), the stage objective and the constraint values
+//   docp_stage_kernel  (update) one thread per (stage, variable) plus one for the plain values:
+//                      one perturbed evaluation (FD) or one dual-number evaluation (AD) each,
+//                      results into a shared-memory tile per stage, then coalesced row stores of
+//                      fx fu cx cu g b -- inputs and outputs through views, no local memory
 //   docp_assoc_kernel  the association tables -> b, d (update_bounds + the c_k rows)
 //   docp_sum_kernel    f = sum_k f0_k, fixed order (one CTA)
 #include <cuda_runtime.h>
@@ -55,82 +56,163 @@ struct UpdArgs {
   double *g, *fx, *fu, *cx, *cu;
 };
 
+// ---- views handed to Model::vals (docp_models.cuh)
+// input: a stage vector shared by all column threads; element `col` is the thread's own
+// (perturbed by the forward difference, or carrying the dual seed)
+template <class T> struct InView;
+template <> struct InView<double> {
+  const double *base;
+  int col;       // -1: no perturbation
+  double pert;   // the perturbed value x_col + dv
+  __device__ double operator[](int i) const { return i == col ? pert : base[i]; }
+};
+template <> struct InView<Dual> {
+  const double *base;
+  int col;
+  double pert;  // unused
+  __device__ Dual operator[](int i) const { return Dual(base[i], i == col ? 1.0 : 0.0); }
+};
+// output: element i goes to p[i * stride]; a Dual leaves its derivative
+struct OutRef {
+  double *p;
+  __device__ void operator=(double v) { *p = v; }
+  __device__ void operator=(Dual v) { *p = v.d; }
+};
+struct OutView {
+  double *p;
+  int stride;
+  __device__ OutRef operator[](int i) const { return OutRef{p + (size_t)i * stride}; }
+};
+
+// values only (Hqp_Docp::update_fbd): one thread per stage, inputs read in place, outputs
+// written in place
 template <class Model>
 __global__ void __launch_bounds__(128) docp_vals_kernel(UpdArgs a) {
   const ModelArgs &m = a.m;
   const int nd = m.nx + m.nu;
   for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k <= m.K;
        k += (long long)gridDim.x * blockDim.x) {
-    double x[MAXX], u[MAXU], f[MAXX], c[MAXC], f0 = 0.0;
     const double *xs = a.x + k * nd;
-    for (int i = 0; i < m.nx; i++) x[i] = xs[i];
-    const int nu = k < m.K ? m.nu : 0, nc = k < m.K ? m.nc : m.ncK;
-    for (int j = 0; j < nu; j++) u[j] = xs[m.nx + j];
-    for (int i = 0; i < m.nx; i++) f[i] = 0.0;  // v_zero(fk), hqp/Hqp_Docp.C:856
-    for (int i = 0; i < nc; i++) c[i] = 0.0;
+    const bool last = k == m.K;
+    const int nc = last ? m.ncK : m.nc;
+    InView<double> x{xs, -1, 0.0}, u{xs + m.nx, -1, 0.0};
+    OutView f{a.fbase + k * m.nx, 1}, c{a.cval + k * m.nc, 1};
+    if (!last)
+      for (int i = 0; i < m.nx; i++) a.fbase[k * m.nx + i] = 0.0;  // v_zero(fk), hqp/Hqp_Docp.C:856
+    for (int i = 0; i < nc; i++) a.cval[k * m.nc + i] = 0.0;
+    double f0 = 0.0;
     Model::template vals<double>(m, (int)k, x, u, f, f0, c);
     a.f0k[k] = f0;
-    if (k < m.K) {
+    if (!last) {
       const double *xn = xs + nd;
-      for (int i = 0; i < m.nx; i++) {
-        a.fbase[k * m.nx + i] = f[i];
-        a.b[k * m.nx + i] = f[i] - xn[i];  // v_sub(fk, x_{k+1}), :861
-      }
+      for (int i = 0; i < m.nx; i++) a.b[k * m.nx + i] = a.fbase[k * m.nx + i] - xn[i];  // v_sub(fk, x_{k+1}), :861
     }
-    for (int i = 0; i < nc; i++) a.cval[k * m.nc + i] = c[i];
   }
 }
 
-// one thread per (stage k, variable j of [x_k u_k]); stage K has its nx states only
+// values + derivatives (Hqp_Docp::update): a CTA takes S consecutive stages; thread (s, j) of a
+// stage evaluates the model once -- j < nd: column j (perturbed: Hqp_Docp::update_grds,
+// hqp/Hqp_Docp.C:1127-1171; or seeded: dual numbers), j = nd: the plain values -- and leaves its
+// nx + nc + 1 results in column j of the stage's shared-memory tile.  After the barrier the CTA
+// forms the quotients (FD) and streams rows of fx, fu, cx, cu, g, b out with coalesced stores.
+// Shared memory: [ par copy | per stage: x_k u_k (nd) | tile (nx + ncm + 1) x (nd + 1) ].
 template <class Model, int MODE>
-__global__ void __launch_bounds__(128) docp_grds_kernel(UpdArgs a, long long total) {
-  const ModelArgs &m = a.m;
-  const int nd = m.nx + m.nu;
-  for (long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x; w < total;
-       w += (long long)gridDim.x * blockDim.x) {
-    long long k = w / nd;
-    if (k > m.K) k = m.K;
-    const int j = (int)(w - k * nd);
-    const bool last = k == m.K;
-    const int nu = last ? 0 : m.nu, nc = last ? m.ncK : m.nc, nf = last ? 0 : m.nx;
-    const double *xs = a.x + k * nd;
-    const double *fb = a.fbase + k * m.nx;
-    const double *cb = a.cval + k * m.nc;
-    double gj;
-    if constexpr (MODE == HQPDOCP_GRAD_FD) {
-      // Hqp_Docp::update_grds, hqp/Hqp_Docp.C:1127-1171
-      double x[MAXX], u[MAXU], f[MAXX], c[MAXC], f0 = 0.0;
-      for (int i = 0; i < m.nx; i++) x[i] = xs[i];
-      for (int i = 0; i < nu; i++) u[i] = xs[m.nx + i];
-      double *v = j < m.nx ? &x[j] : &u[j - m.nx];
-      const double dvj = 1e-4 * fabs(*v) + 1e-6;
-      *v += dvj;
-      for (int i = 0; i < nf; i++) f[i] = 0.0;
-      for (int i = 0; i < nc; i++) c[i] = 0.0;
-      Model::template vals<double>(m, (int)k, x, u, f, f0, c);
-      if (j < m.nx) {
-        for (int i = 0; i < nf; i++) a.fx[(k * m.nx + i) * m.nx + j] = (f[i] - fb[i]) / dvj;
-        for (int i = 0; i < nc; i++) a.cx[(k * m.nc + i) * m.nx + j] = (c[i] - cb[i]) / dvj;
-      } else {
-        for (int i = 0; i < nf; i++) a.fu[(k * m.nx + i) * m.nu + (j - m.nx)] = (f[i] - fb[i]) / dvj;
-        for (int i = 0; i < nc; i++) a.cu[(k * m.nc + i) * m.nu + (j - m.nx)] = (c[i] - cb[i]) / dvj;
-      }
-      gj = (f0 - a.f0k[k]) / dvj;
-    } else {
-      Dual x[MAXX], u[MAXU], f[MAXX], c[MAXC], f0;
-      for (int i = 0; i < m.nx; i++) x[i] = Dual(xs[i], i == j ? 1.0 : 0.0);
-      for (int i = 0; i < nu; i++) u[i] = Dual(xs[m.nx + i], m.nx + i == j ? 1.0 : 0.0);
-      Model::template vals<Dual>(m, (int)k, x, u, f, f0, c);
-      if (j < m.nx) {
-        for (int i = 0; i < nf; i++) a.fx[(k * m.nx + i) * m.nx + j] = f[i].d;
-        for (int i = 0; i < nc; i++) a.cx[(k * m.nc + i) * m.nx + j] = c[i].d;
-      } else {
-        for (int i = 0; i < nf; i++) a.fu[(k * m.nx + i) * m.nu + (j - m.nx)] = f[i].d;
-        for (int i = 0; i < nc; i++) a.cu[(k * m.nc + i) * m.nu + (j - m.nx)] = c[i].d;
-      }
-      gj = f0.d;
+__global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int npar_sh, int ncm) {
+  extern __shared__ double sh[];
+  ModelArgs m = a.m;
+  const int nx = m.nx, nd = m.nx + m.nu, ld = nd + 1, rows = nx + ncm + 1;
+  double *par_sh = sh;
+  double *stage_sh = sh + npar_sh;
+  const int per_stage = nd + rows * ld;
+  for (int i = threadIdx.x; i < npar_sh; i += blockDim.x) par_sh[i] = m.par[i];
+  if (npar_sh) m.par = par_sh;
+  const long long k0 = (long long)blockIdx.x * S;
+  const int ns = (int)(k0 + S <= m.K + 1 ? S : m.K + 1 - k0);
+  // stage vectors: ns * nd contiguous doubles of x (the final stage has nx only)
+  {
+    const long long lo = k0 * nd, n_all = (long long)m.K * nd + nx;
+    for (int t = threadIdx.x; t < ns * nd; t += blockDim.x) {
+      const int s = t / nd, i = t - s * nd;
+      stage_sh[s * per_stage + i] = lo + t < n_all ? a.x[lo + t] : 0.0;
     }
-    a.g[k * nd + j] = gj;  // f0x / f0u written in place into qp->c (:965-966)
+  }
+  __syncthreads();
+  const int s = threadIdx.x / ld, j = threadIdx.x - s * ld;
+  if (s < ns) {
+    const long long k = k0 + s;
+    const bool last = k == m.K;
+    const int ncols = last ? nx : nd;
+    if (j < ncols || j == nd) {
+      const double *xs = stage_sh + s * per_stage;
+      double *tile = stage_sh + s * per_stage + nd;
+      const int nf = last ? 0 : nx, nc = last ? m.ncK : m.nc;
+      OutView f{tile + j, ld}, c{tile + nx * ld + j, ld};
+      for (int i = 0; i < nf; i++) tile[i * ld + j] = 0.0;  // v_zero(df) / v_zero(dc), :1136-1138
+      for (int i = 0; i < nc; i++) tile[(nx + i) * ld + j] = 0.0;
+      double *f0_out = tile + (nx + ncm) * ld + j;
+      if (j == nd || MODE == HQPDOCP_GRAD_FD) {
+        double pert = 0.0;
+        int col = -1;
+        if (j < nd) {
+          const double v = xs[j];
+          pert = v + (1e-4 * fabs(v) + 1e-6);  // x->ve[j] += dvj, :1129-1131
+          col = j;
+        }
+        InView<double> x{xs, col, pert}, u{xs + nx, col - nx, pert};
+        double f0 = 0.0;
+        Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+        *f0_out = f0;
+      } else {
+        InView<Dual> x{xs, j, 0.0}, u{xs + nx, j - nx, 0.0};
+        Dual f0(0.0);
+        Model::template vals<Dual>(m, (int)k, x, u, f, f0, c);
+        *f0_out = f0.d;
+      }
+    }
+  }
+  __syncthreads();
+  // write-out: rows of the tiles, consecutive threads on consecutive columns
+  for (int s2 = 0; s2 < ns; s2++) {
+    const long long k = k0 + s2;
+    const bool last = k == m.K;
+    const double *xs = stage_sh + s2 * per_stage;
+    const double *tile = xs + nd;
+    const int nf = last ? 0 : nx, nc = last ? m.ncK : m.nc, ncols = last ? nx : nd;
+    const int nrow = nf + nc + 1;  // f rows, c rows, the objective row
+    for (int t = threadIdx.x; t < nrow * ld; t += blockDim.x) {
+      int r = t / ld;
+      const int jj = t - r * ld;
+      if (jj >= ncols && jj != nd) continue;
+      // tile row: f rows 0..nf-1, c rows nx.., objective row nx + ncm
+      const int trow = r < nf ? r : (r < nf + nc ? nx + (r - nf) : nx + ncm);
+      const double v = tile[trow * ld + jj];
+      if (jj == nd) {  // the plain values
+        if (r < nf) {
+          a.fbase[k * nx + r] = v;
+          a.b[k * nx + r] = v - a.x[(k + 1) * nd + r];  // v_sub(fk, x_{k+1}), :1018
+        } else if (r < nf + nc) {
+          a.cval[k * m.nc + (r - nf)] = v;
+        } else {
+          a.f0k[k] = v;
+        }
+        continue;
+      }
+      double q = v;
+      if (MODE == HQPDOCP_GRAD_FD) {
+        const double dvj = 1e-4 * fabs(xs[jj]) + 1e-6;
+        q = (v - tile[trow * ld + nd]) / dvj;  // (df - f) / dvj, :1140-1148
+      }
+      if (r < nf) {
+        if (jj < nx) a.fx[(k * nx + r) * nx + jj] = q;
+        else a.fu[(k * nx + r) * m.nu + (jj - nx)] = q;
+      } else if (r < nf + nc) {
+        const long long ci = k * m.nc + (r - nf);
+        if (jj < nx) a.cx[ci * nx + jj] = q;
+        else a.cu[ci * m.nu + (jj - nx)] = q;
+      } else {
+        a.g[k * nd + jj] = q;  // f0x / f0u written in place into qp->c (:965-966)
+      }
+    }
   }
 }
 
@@ -222,23 +304,41 @@ int upload_assoc(const hqpdocp_assoc &src, Assoc &dst, long long idx_limit, cons
 template <class Model>
 int launch_model(hqpdocp_handle *h, bool grads, int mode, const UpdArgs &a) {
   const long long K = h->dims.K;
-  const int nd = h->dims.nx + h->dims.nu;
-  {
+  const hqpdocp_dims &D = h->dims;
+  const int nd = D.nx + D.nu, ld = nd + 1;
+  if (!grads) {
     const int thr = 128;
     const long long want = (K + 1 + thr - 1) / thr;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sms * 16));
     docp_vals_kernel<Model><<<grid, thr, 0, h->stream>>>(a);
     h->launches++;
-  }
-  if (grads) {
-    const long long total = K * nd + h->dims.nx;
-    const int thr = 128;
-    const long long want = (total + thr - 1) / thr;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sms * 16));
-    if (mode == HQPDOCP_GRAD_FD)
-      docp_grds_kernel<Model, HQPDOCP_GRAD_FD><<<grid, thr, 0, h->stream>>>(a, total);
-    else
-      docp_grds_kernel<Model, HQPDOCP_GRAD_AD><<<grid, thr, 0, h->stream>>>(a, total);
+  } else {
+    // S stages per CTA: as many as fit 256 threads and ~48 KB next to the parameter copy
+    const int ncm = std::max(D.nc, D.ncK);
+    const size_t per_stage = (size_t)nd + (size_t)(D.nx + ncm + 1) * ld;
+    const int npar_sh = (size_t)D.npar * 8 <= 64 * 1024 ? D.npar : 0;
+    // S stages per CTA (<= 256 threads): the S that keeps the most evaluation threads resident
+    // on an SM (227 KB of shared memory, 2048 threads, 32 CTAs)
+    int S = 1;
+    long long best = -1;
+    for (int c = 1; c <= std::max(1, 256 / ld); c++) {
+      const size_t sm = (npar_sh + c * per_stage) * 8 + 1024;
+      if (sm > 200 * 1024) break;
+      const int thr_c = ((c * ld + 31) / 32) * 32;
+      const long long ctas = std::min<long long>({(long long)(227 * 1024 / sm), 2048 / thr_c, 32});
+      if (ctas * c * ld > best) {
+        best = ctas * c * ld;
+        S = c;
+      }
+    }
+    const size_t smem = (npar_sh + S * per_stage) * sizeof(double);
+    const int thr = ((S * ld + 31) / 32) * 32;
+    const long long grid = (K + 1 + S - 1) / S;
+    if (grid > 0x7fffffffLL) return fail("hqpdocp: horizon too long for one launch", HQPDOCP_E_UNSUPPORTED);
+    auto kern = mode == HQPDOCP_GRAD_FD ? docp_stage_kernel<Model, HQPDOCP_GRAD_FD>
+                                        : docp_stage_kernel<Model, HQPDOCP_GRAD_AD>;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    kern<<<(unsigned)grid, thr, smem, h->stream>>>(a, S, npar_sh, ncm);
     h->launches++;
   }
   CU(cudaGetLastError());

@@ -12,8 +12,11 @@
 
 #include <Hqp_Docp.h>
 #include <Hqp_Program.h>
+#include <If_Class.h>
 #include <If_Element.h>
 #include <Prg_DID.h>
+
+#include "../hqp_b200/host/Hqp_DocpCuda.h"  // (the product's host mix-in under test)
 
 extern "C" int ref_init(void);
 
@@ -98,6 +101,18 @@ class Prg_SynthNL : public Hqp_Docp {
   }
 };
 
+// the same program with its stage loop on the GPU (the mix-in under test)
+class Prg_SynthNLCuda : public Hqp_DocpCuda<Prg_SynthNL> {
+ public:
+  const char *name() { return "SynthNLCuda"; }
+  int cuda_model() { return HQPDOCP_MODEL_SYNTHNL; }
+  void cuda_params(int, std::vector<double> &p, int &nspar, std::vector<double> &sp) {
+    p = par;
+    nspar = nx;
+    sp = spar;
+  }
+};
+
 struct DocpRef {
   Hqp_SqpProgram *prg;
 };
@@ -107,18 +122,25 @@ struct DocpRef {
 extern "C" {
 
 // model 0: the reference's Prg_DID (par[0] unused: dt = 1/K inside Prg_DID; nc = prg_with_cns);
-// model 1: Prg_SynthNL.  xinit [N] = the iterate the program is set up at (model 1 only; Prg_DID
+// model 1: Prg_SynthNL; models 2 / 3: the same two programs with the stage loop on the GPU
+// ("DIDCuda" from the plugin library, ref_load_plugin first; Prg_SynthNLCuda above).  xinit [N] = the iterate the program is set up at (model 1 only; Prg_DID
 // has its own initial values, hqp_docp/Prg_DID.C:43-49).
 void *ref_docp_create(int model, int K, int nx, int nu, int nc, int ncK, const double *par, int npar,
                       const double *spar, int nspar, const double *xinit) {
   if (ref_init()) return NULL;
   Hqp_SqpProgram *prg = NULL;
-  if (model == 0) {
-    prg = new Prg_DID();
+  if (model == 0 || model == 2) {
+    if (model == 0)
+      prg = new Prg_DID();
+    else {
+      If_ClassList<Hqp_SqpProgram> *list = If_ClassList_Hqp_SqpProgram();
+      prg = list ? list->createObject("DIDCuda") : NULL;
+      if (!prg) return NULL;
+    }
     If_SetInt("prg_kmax", K);
     If_SetInt("prg_with_cns", nc != 0);
-  } else if (model == 1) {
-    Prg_SynthNL *p = new Prg_SynthNL();
+  } else if (model == 1 || model == 3) {
+    Prg_SynthNL *p = model == 1 ? new Prg_SynthNL() : new Prg_SynthNLCuda();
     p->K = K; p->nx = nx; p->nu = nu; p->nc = nc; p->ncK = ncK;
     p->par.assign(par, par + npar);
     p->spar.assign(spar, spar + (size_t)(K + 1) * nspar);

@@ -472,6 +472,31 @@ int ref_docp_did(int kmax, const char *qp_solver, const char *mat_solver,
 }
 
 
+// ---- row f4: hqp_solve for the program created last (ref_docp_create: the constructor of an
+// Hqp_SqpProgram hands itself to theSqpSolver, hqp/Hqp_SqpProgram.C:63-64); the calls of
+// hqp_docp/Docp_Main.C:68-76 after prg_setup
+int ref_prg_solve(double sqp_eps, int simulate, const char *qp_solver, const char *mat_solver,
+                  double *objective, int *sqp_iters, int *qp_iters, char *result, int result_len) {
+  If_SetReal("sqp_eps", sqp_eps);
+  if (qp_solver && *qp_solver && If_SetString("sqp_qp_solver", qp_solver) != IF_OK) return -1;
+  if (mat_solver && *mat_solver && If_SetString("qp_mat_solver", mat_solver) != IF_OK) return -2;
+  if (simulate && If_Eval("prg_simulate") != IF_OK) return -4;
+  if (If_Eval("sqp_init") != IF_OK) {
+    fprintf(stderr, "ref_prg_solve sqp_init: %s\n", If_ResultString());
+    return -5;
+  }
+  g_solve_result = "";
+  g_qp_iters_total = 0;
+  if (If_Eval("hqp_solve") != IF_OK)
+    snprintf(result, result_len, "error: %s", If_ResultString());
+  else
+    snprintf(result, result_len, "%s", g_solve_result);
+  *objective = getr("prg_f");
+  *sqp_iters = geti("sqp_iter");
+  *qp_iters = g_qp_iters_total;
+  return 0;
+}
+
 // ---- row f2: the reference's own block update Hqp_HL_BFGS::update_b_Q
 // (hqp/Hqp_HL_BFGS.C:149-213; protected, reached through a subclass), on ONE dense
 // block Q (n x n, row-major, both triangles), in place

@@ -233,15 +233,22 @@ class RefDocp:
     restated as an Hqp_Docp subclass in oracle/prg_synthnl.cpp (model 1).  prob: an
     hqp_b200.docpcuda.DocpProblem (dimensions, parameters, start values)."""
 
-    def __init__(self, prob):
+    def __init__(self, prob, cuda=False):
+        """cuda: the same program with its stage loop on the GPU -- Prg_DIDCuda from the plugin
+        library / Prg_SynthNLCuda (the host mix-in hqp_b200/host/Hqp_DocpCuda.h under test)."""
         L = lib()
         L.ref_docp_create.restype = ctypes.c_void_p
+        if cuda and int(prob.model) == 0:
+            from hqp_b200 import build
+            path = os.path.join(build.LIB, "libhqp_ipcuda_plugin.so")
+            if L.ref_load_plugin(path.encode()):
+                raise RuntimeError(f"cannot load {path}: {L.ref_last_error().decode()}")
         par = np.ascontiguousarray(prob.par, dtype=np.float64)
         spar = np.ascontiguousarray(prob.spar, dtype=np.float64)
         xin = np.ascontiguousarray(prob.x_init, dtype=np.float64)
         nspar = spar.shape[1] if spar.ndim == 2 else 0
         self.h = ctypes.c_void_p(L.ref_docp_create(
-            int(prob.model), prob.K, prob.nx, prob.nu, prob.nc, prob.ncK, _dp(par), par.size,
+            int(prob.model) + (2 if cuda else 0), prob.K, prob.nx, prob.nu, prob.nc, prob.ncK, _dp(par), par.size,
             _dp(spar) if spar.size else None, nspar, _dp(xin)))
         if not self.h:
             raise RuntimeError("ref_docp_create failed")
@@ -253,6 +260,20 @@ class RefDocp:
         out = np.empty(self.N)
         lib().ref_docp_get_x(self.h, _dp(out))
         return out
+
+    def solve(self, sqp_eps=1e-6, simulate=True, qp_solver="", mat_solver=""):
+        """hqp_solve on this program (it must be the one created last): the calls of
+        hqp_docp/Docp_Main.C:68-76.  Returns dict result, objective, sqp_iters, qp_iters, x."""
+        obj = ctypes.c_double()
+        it, qit = ctypes.c_int(), ctypes.c_int()
+        res = ctypes.create_string_buffer(256)
+        rc = lib().ref_prg_solve(ctypes.c_double(sqp_eps), int(bool(simulate)), qp_solver.encode(),
+                                 mat_solver.encode(), ctypes.byref(obj), ctypes.byref(it), ctypes.byref(qit),
+                                 res, 256)
+        if rc:
+            raise RuntimeError(f"ref_prg_solve: {rc}")
+        return dict(result=res.value.decode(), objective=obj.value, sqp_iters=it.value, qp_iters=qit.value,
+                    x=self.x())
 
     def update(self, x=None, fbd_only=False, matrices=True):
         """Returns dict f, b, d, c (qp->c) and -- unless fbd_only -- dense A [me,N], C [m,N]."""

@@ -251,3 +251,78 @@ def test_gpu_update_full_size_properties():
         assert np.array_equal(b.cpu().numpy(), ad["b"])
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------ GPU: the host mix-in
+# hqp_b200/host/Hqp_DocpCuda.h under the UNMODIFIED reference: the same program once as the
+# reference runs it (Hqp_Docp::update on the host) and once with the stage loop on the GPU.
+
+def _ref_and_cuda(p, x, grad=None):
+    r = rh.RefDocp(p)
+    try:
+        want = r.update(x)
+        want_fbd = r.update(x * 0.9, fbd_only=True)
+    finally:
+        r.close()
+    c = rh.RefDocp(p, cuda=True)
+    try:
+        if grad is not None:
+            assert rh.lib().ref_set_int(b"prg_cuda_grad", grad) == 0
+        got = c.update(x)
+        got_fbd = c.update(x * 0.9, fbd_only=True)
+    finally:
+        c.close()
+    return want, got, want_fbd, got_fbd
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+def test_gpu_host_module_did_update_is_the_reference_update():
+    p = dc.did_problem(60, True)
+    x = p.x_init + 0.05 * np.random.default_rng(4).uniform(-1, 1, p.N)
+    want, got, wf, gf = _ref_and_cuda(p, x)
+    assert abs(got["f"] - want["f"]) <= 1e-13 * max(1.0, abs(want["f"]))
+    for key in ("b", "d", "c", "A", "C"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(gf["b"], wf["b"]) and np.array_equal(gf["d"], wf["d"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("grad,tol", [(0, 1e-9), (1, 5e-4)])
+def test_gpu_host_module_synthnl_update(grad, tol):
+    p = dc.synthnl_problem(9, 6, 3, 3, 2, seed=21)
+    x = p.x_init + 0.1 * np.random.default_rng(6).uniform(-1, 1, p.N)
+    want, got, wf, gf = _ref_and_cuda(p, x, grad)
+    assert abs(got["f"] - want["f"]) <= 1e-13 * max(1.0, abs(want["f"]))
+    assert np.array_equal(got["b"], want["b"]) and np.array_equal(got["d"], want["d"])
+    for key in ("c", "A", "C"):
+        assert np.max(np.abs(got[key] - want[key])) <= tol, key
+    assert np.array_equal(gf["b"], wf["b"]) and np.array_equal(gf["d"], wf["d"])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+def test_gpu_host_module_sqp_solves_match_the_reference():
+    """hqp_solve (the unmodified Hqp_SqpPowell + Hqp_IpsFranke + Hqp_IpLQDOCP) on the program with
+    its stage loop on the GPU: the shipped example reproduces the reference run (SURVEY.md
+    section 6: objective 98.3999988628, 1 SQP iteration, 57 QP iterations), the nonlinear
+    program takes the reference's iterations to the reference's optimum."""
+    for make, grad in ((lambda: dc.did_problem(60, True), 1), (lambda: dc.synthnl_problem(20, 4, 2, 1, 0), 0)):
+        p = make()
+        r = rh.RefDocp(p)
+        try:
+            want = r.solve()
+        finally:
+            r.close()
+        c = rh.RefDocp(p, cuda=True)
+        try:
+            assert rh.lib().ref_set_int(b"prg_cuda_grad", grad) == 0
+            got = c.solve()
+        finally:
+            c.close()
+        assert want["result"] == "optimal" and got["result"] == "optimal"
+        assert got["sqp_iters"] == want["sqp_iters"] and got["qp_iters"] == want["qp_iters"]
+        assert abs(got["objective"] - want["objective"]) <= 1e-9 * abs(want["objective"])
+        assert np.max(np.abs(got["x"] - want["x"])) <= 1e-7
+    assert abs(want["objective"] - 14.814107952743184) < 1e-9  # (the CPU run of this container)
