@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -54,22 +55,29 @@ struct UpdArgs {
   double *cval;     // [K nc + ncK] constraint values (scratch)
   double *b;        // [me]
   double *g, *fx, *fu, *cx, *cu;
+  int npar;
 };
 
 // ---- views handed to Model::vals (docp_models.cuh)
-// input: a stage vector shared by all column threads; element `col` is the thread's own
-// (perturbed by the forward difference, or carrying the dual seed)
-template <class T> struct InView;
-template <> struct InView<double> {
-  const double *base;
-  int col;       // -1: no perturbation
-  double pert;   // the perturbed value x_col + dv
-  __device__ double operator[](int i) const { return i == col ? pert : base[i]; }
+// input, plain: element i at p[i * stride] -- a stage vector in shared memory (stride 1), a
+// column of the transposed stage block (values kernel) or a thread's own perturbed copy
+struct ColView {
+  const double *p;
+  int stride;
+  __device__ double operator[](int i) const { return p[i * stride]; }
 };
-template <> struct InView<Dual> {
+// input, perturbed in place: the stage vector shared by all column threads, element `col`
+// replaced by the thread's own perturbed value (when the per-column copies do not fit)
+struct PertView {
   const double *base;
   int col;
-  double pert;  // unused
+  const double *slot;  // the thread's perturbed value, in shared memory like base
+  __device__ double operator[](int i) const { return *(i == col ? slot : base + i); }
+};
+// input, dual numbers: the shared stage vector, the thread's own column carries the seed
+struct SeedView {
+  const double *base;
+  int col;
   __device__ Dual operator[](int i) const { return Dual(base[i], i == col ? 1.0 : 0.0); }
 };
 // output: element i goes to p[i * stride]; a Dual leaves its derivative
@@ -81,32 +89,58 @@ struct OutRef {
 struct OutView {
   double *p;
   int stride;
-  __device__ OutRef operator[](int i) const { return OutRef{p + (size_t)i * stride}; }
+  __device__ OutRef operator[](int i) const { return OutRef{p + i * stride}; }
 };
 
-// values only (Hqp_Docp::update_fbd): one thread per stage, inputs read in place, outputs
-// written in place
-template <class Model>
-__global__ void __launch_bounds__(128) docp_vals_kernel(UpdArgs a) {
-  const ModelArgs &m = a.m;
-  const int nd = m.nx + m.nu;
-  for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k <= m.K;
-       k += (long long)gridDim.x * blockDim.x) {
-    const double *xs = a.x + k * nd;
-    const bool last = k == m.K;
-    const int nc = last ? m.ncK : m.nc;
-    InView<double> x{xs, -1, 0.0}, u{xs + m.nx, -1, 0.0};
-    OutView f{a.fbase + k * m.nx, 1}, c{a.cval + k * m.nc, 1};
-    if (!last)
-      for (int i = 0; i < m.nx; i++) a.fbase[k * m.nx + i] = 0.0;  // v_zero(fk), hqp/Hqp_Docp.C:856
-    for (int i = 0; i < nc; i++) a.cval[k * m.nc + i] = 0.0;
+constexpr int VT = 128;        // stages per CTA of the values kernel
+constexpr int VLD = VT + 1;    // padded leading dimension of its transposed tiles
+
+// values only (Hqp_Docp::update_fbd): a CTA takes VT consecutive stages, one thread each.  The
+// stages' x_k u_k arrive with coalesced loads and are transposed into shared memory (element i
+// of stage s at [i][s]: conflict-free for the evaluation), results leave the same way.
+// Shared memory: [ par copy | xT nd x VLD | outT (nx + ncm) x VLD ].
+template <class Model, bool PARSH>
+__global__ void __launch_bounds__(VT) docp_vals_kernel(UpdArgs a, int ncm) {
+  extern __shared__ double sh[];
+  ModelArgs m = a.m;
+  const int nx = m.nx, nd = m.nx + m.nu;
+  const int npar_sh = PARSH ? a.npar : 0;
+  double *xT = sh + npar_sh, *outT = xT + nd * VLD;
+  if (PARSH) {
+    for (int i = threadIdx.x; i < npar_sh; i += VT) sh[i] = m.par[i];
+    m.par = sh;
+  }
+  const long long k0 = (long long)blockIdx.x * VT;
+  const int ns = (int)(k0 + VT <= m.K + 1 ? VT : m.K + 1 - k0);
+  const long long lo = k0 * nd, n_all = (long long)m.K * nd + nx;
+  for (int t = threadIdx.x; t < ns * nd; t += VT) {
+    const int s = t / nd, i = t - s * nd;
+    xT[i * VLD + s] = lo + t < n_all ? a.x[lo + t] : 0.0;
+  }
+  for (int i = 0; i < nx + ncm; i++) outT[i * VLD + threadIdx.x] = 0.0;  // v_zero(fk), hqp/Hqp_Docp.C:856
+  __syncthreads();
+  if ((int)threadIdx.x < ns) {
+    const long long k = k0 + threadIdx.x;
+    ColView x{xT + threadIdx.x, VLD}, u{xT + nx * VLD + threadIdx.x, VLD};
+    OutView f{outT + threadIdx.x, VLD}, c{outT + nx * VLD + threadIdx.x, VLD};
     double f0 = 0.0;
     Model::template vals<double>(m, (int)k, x, u, f, f0, c);
     a.f0k[k] = f0;
-    if (!last) {
-      const double *xn = xs + nd;
-      for (int i = 0; i < m.nx; i++) a.b[k * m.nx + i] = a.fbase[k * m.nx + i] - xn[i];  // v_sub(fk, x_{k+1}), :861
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < ns * nx; t += VT) {
+    const int s = t / nx, i = t - s * nx;
+    const long long k = k0 + s;
+    if (k < m.K) {
+      const double v = outT[i * VLD + s];
+      a.fbase[k * nx + i] = v;
+      a.b[k * nx + i] = v - a.x[(k + 1) * nd + i];  // v_sub(fk, x_{k+1}), :861
     }
+  }
+  for (int t = threadIdx.x; t < ns * ncm; t += VT) {
+    const int s = t / ncm, i = t - s * ncm;
+    const long long k = k0 + s;
+    if (i < (k < m.K ? m.nc : m.ncK)) a.cval[k * m.nc + i] = outT[(nx + i) * VLD + s];
   }
 }
 
@@ -115,17 +149,22 @@ __global__ void __launch_bounds__(128) docp_vals_kernel(UpdArgs a) {
 // hqp/Hqp_Docp.C:1127-1171; or seeded: dual numbers), j = nd: the plain values -- and leaves its
 // nx + nc + 1 results in column j of the stage's shared-memory tile.  After the barrier the CTA
 // forms the quotients (FD) and streams rows of fx, fu, cx, cu, g, b out with coalesced stores.
-// Shared memory: [ par copy | per stage: x_k u_k (nd) | tile (nx + ncm + 1) x (nd + 1) ].
-template <class Model, int MODE>
-__global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int npar_sh, int ncm) {
+// XCOPY (FD): every column thread reads its own perturbed copy of the stage vector (element i of
+// column j at [i][j]: one conflict-free LDS per access instead of compare + select + LDS).
+// Shared memory: [ par copy | per stage: x_k u_k (nd) | tile (nx + ncm + 1) x (nd + 1) |
+//                  XCOPY: copies nd x (nd + 1) ] | one perturbed value per thread ].
+template <class Model, int MODE, bool PARSH, bool XCOPY>
+__global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int ncm) {
   extern __shared__ double sh[];
   ModelArgs m = a.m;
   const int nx = m.nx, nd = m.nx + m.nu, ld = nd + 1, rows = nx + ncm + 1;
-  double *par_sh = sh;
+  const int npar_sh = PARSH ? a.npar : 0;
   double *stage_sh = sh + npar_sh;
-  const int per_stage = nd + rows * ld;
-  for (int i = threadIdx.x; i < npar_sh; i += blockDim.x) par_sh[i] = m.par[i];
-  if (npar_sh) m.par = par_sh;
+  const int per_stage = nd + rows * ld + (XCOPY ? nd * ld : 0);
+  if (PARSH) {
+    for (int i = threadIdx.x; i < npar_sh; i += blockDim.x) sh[i] = m.par[i];
+    m.par = sh;
+  }
   const long long k0 = (long long)blockIdx.x * S;
   const int ns = (int)(k0 + S <= m.K + 1 ? S : m.K + 1 - k0);
   // stage vectors: ns * nd contiguous doubles of x (the final stage has nx only)
@@ -137,6 +176,16 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
     }
   }
   __syncthreads();
+  if (XCOPY) {
+    for (int t = threadIdx.x; t < ns * nd * nd; t += blockDim.x) {
+      const int s = t / (nd * nd), r = t - s * nd * nd, i = r / nd, jj = r - i * nd;
+      const double *xs = stage_sh + s * per_stage;
+      const double v = xs[i];
+      // x->ve[j] += dvj with dvj = 1e-4 |v| + 1e-6, hqp/Hqp_Docp.C:1129-1131
+      stage_sh[s * per_stage + nd + rows * ld + i * ld + jj] = i == jj ? v + (1e-4 * fabs(v) + 1e-6) : v;
+    }
+    __syncthreads();
+  }
   const int s = threadIdx.x / ld, j = threadIdx.x - s * ld;
   if (s < ns) {
     const long long k = k0 + s;
@@ -151,19 +200,25 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
       for (int i = 0; i < nc; i++) tile[(nx + i) * ld + j] = 0.0;
       double *f0_out = tile + (nx + ncm) * ld + j;
       if (j == nd || MODE == HQPDOCP_GRAD_FD) {
-        double pert = 0.0;
-        int col = -1;
-        if (j < nd) {
-          const double v = xs[j];
-          pert = v + (1e-4 * fabs(v) + 1e-6);  // x->ve[j] += dvj, :1129-1131
-          col = j;
-        }
-        InView<double> x{xs, col, pert}, u{xs + nx, col - nx, pert};
         double f0 = 0.0;
-        Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+        if (XCOPY) {
+          const double *xc = tile + rows * ld + j;
+          ColView x{j == nd ? xs : xc, j == nd ? 1 : ld}, u{j == nd ? xs + nx : xc + nx * ld, j == nd ? 1 : ld};
+          Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+        } else {
+          int col = -1;
+          double *slot = sh + npar_sh + S * per_stage + threadIdx.x;
+          if (j < nd) {
+            const double v = xs[j];
+            *slot = v + (1e-4 * fabs(v) + 1e-6);  // x->ve[j] += dvj, :1129-1131
+            col = j;
+          }
+          PertView x{xs, col, slot}, u{xs + nx, col - nx, slot};
+          Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+        }
         *f0_out = f0;
       } else {
-        InView<Dual> x{xs, j, 0.0}, u{xs + nx, j - nx, 0.0};
+        SeedView x{xs, j}, u{xs + nx, j - nx};
         Dual f0(0.0);
         Model::template vals<Dual>(m, (int)k, x, u, f, f0, c);
         *f0_out = f0.d;
@@ -276,6 +331,7 @@ struct hqpdocp_handle {
   cudaStream_t stream = nullptr;
   long long N = 0, me = 0, m = 0, ncns = 0;
   long long launches = 0;
+  int xcopy_mode = -1;  // HQPDOCP_XCOPY: -1 choose, 0 never, 1 always (when it fits)
   double *d_par = nullptr, *d_spar = nullptr;
   Assoc t[6];  // xu_eq xu_lb xu_ub cns_eq cns_lb cns_ub
   double *fbase = nullptr, *f0k = nullptr, *cval = nullptr;
@@ -301,46 +357,91 @@ int upload_assoc(const hqpdocp_assoc &src, Assoc &dst, long long idx_limit, cons
   return HQPDOCP_OK;
 }
 
+// the S (stages per CTA, <= 256 threads) that keeps the most evaluation threads resident on an
+// SM (227 KB of shared memory, 2048 threads, 32 CTAs); 0 if not even one stage fits
+int pick_stages(int ld, size_t fixed, size_t per_stage, long long *resident) {
+  int S = 0;
+  long long best = -1;
+  for (int c = 1; c <= std::max(1, 256 / ld); c++) {
+    const size_t sm = (fixed + c * per_stage + 256) * 8 + 1024;
+    if (sm > 200 * 1024) break;
+    const int thr_c = ((c * ld + 31) / 32) * 32;
+    const long long ctas = std::min<long long>({(long long)(227 * 1024 / sm), 2048 / thr_c, 32});
+    if (ctas * c * ld > best) {
+      best = ctas * c * ld;
+      S = c;
+    }
+  }
+  if (resident) *resident = best;
+  return S;
+}
+
+template <class Model, bool PARSH>
+int launch_vals(hqpdocp_handle *h, const UpdArgs &a, int ncm, size_t smem) {
+  CU(cudaFuncSetAttribute(docp_vals_kernel<Model, PARSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  const long long grid = (h->dims.K + 1 + VT - 1) / VT;
+  docp_vals_kernel<Model, PARSH><<<(unsigned)grid, VT, smem, h->stream>>>(a, ncm);
+  return HQPDOCP_OK;
+}
+
+template <class Model, int MODE, bool PARSH, bool XCOPY>
+int launch_stage(hqpdocp_handle *h, const UpdArgs &a, int S, int ncm, size_t smem) {
+  const int ld = h->dims.nx + h->dims.nu + 1;
+  CU(cudaFuncSetAttribute(docp_stage_kernel<Model, MODE, PARSH, XCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          200 * 1024));
+  const long long grid = ((long long)h->dims.K + 1 + S - 1) / S;
+  docp_stage_kernel<Model, MODE, PARSH, XCOPY><<<(unsigned)grid, ((S * ld + 31) / 32) * 32, smem, h->stream>>>(a, S, ncm);
+  return HQPDOCP_OK;
+}
+
 template <class Model>
 int launch_model(hqpdocp_handle *h, bool grads, int mode, const UpdArgs &a) {
-  const long long K = h->dims.K;
   const hqpdocp_dims &D = h->dims;
   const int nd = D.nx + D.nu, ld = nd + 1;
+  const int ncm = std::max(D.nc, D.ncK);
+  if (((long long)D.K + 1) > 0x7fffffffLL) return fail("hqpdocp: horizon too long for one launch", HQPDOCP_E_UNSUPPORTED);
+  int rc;
   if (!grads) {
-    const int thr = 128;
-    const long long want = (K + 1 + thr - 1) / thr;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)h->sms * 16));
-    docp_vals_kernel<Model><<<grid, thr, 0, h->stream>>>(a);
-    h->launches++;
+    const size_t tiles = (size_t)(nd + D.nx + ncm) * VLD;
+    const bool parsh = (D.npar + tiles) * 8 <= 200 * 1024;
+    const size_t smem = ((parsh ? D.npar : 0) + tiles) * 8;
+    if (smem > 200 * 1024) return fail("hqpdocp: stage too large for the values kernel", HQPDOCP_E_UNSUPPORTED);
+    rc = parsh ? launch_vals<Model, true>(h, a, ncm, smem) : launch_vals<Model, false>(h, a, ncm, smem);
   } else {
-    // S stages per CTA: as many as fit 256 threads and ~48 KB next to the parameter copy
-    const int ncm = std::max(D.nc, D.ncK);
-    const size_t per_stage = (size_t)nd + (size_t)(D.nx + ncm + 1) * ld;
-    const int npar_sh = (size_t)D.npar * 8 <= 64 * 1024 ? D.npar : 0;
-    // S stages per CTA (<= 256 threads): the S that keeps the most evaluation threads resident
-    // on an SM (227 KB of shared memory, 2048 threads, 32 CTAs)
-    int S = 1;
-    long long best = -1;
-    for (int c = 1; c <= std::max(1, 256 / ld); c++) {
-      const size_t sm = (npar_sh + c * per_stage) * 8 + 1024;
-      if (sm > 200 * 1024) break;
-      const int thr_c = ((c * ld + 31) / 32) * 32;
-      const long long ctas = std::min<long long>({(long long)(227 * 1024 / sm), 2048 / thr_c, 32});
-      if (ctas * c * ld > best) {
-        best = ctas * c * ld;
-        S = c;
+    const size_t tile = (size_t)nd + (size_t)(D.nx + ncm + 1) * ld, copies = (size_t)nd * ld;
+    const bool fd = mode == HQPDOCP_GRAD_FD;
+    // parameter copy in shared memory unless it crowds out the stages; per-column copies of the
+    // stage vector (FD) only when they cost no resident threads (measured at C2 / C5: with half
+    // the threads resident the copies lose, 0.229 vs 0.157 ms and 10.8 vs 5.5 ms)
+    bool parsh = (size_t)D.npar * 8 <= 64 * 1024;
+    long long r_plain = 0, r_copy = 0;
+    int S = pick_stages(ld, parsh ? D.npar : 0, tile, &r_plain);
+    if (S == 0 && parsh) {
+      parsh = false;
+      S = pick_stages(ld, 0, tile, &r_plain);
+    }
+    if (S == 0) return fail("hqpdocp: stage too large for the update kernel", HQPDOCP_E_UNSUPPORTED);
+    bool xcopy = false;
+    if (fd && h->xcopy_mode != 0) {
+      const int Sc = pick_stages(ld, parsh ? D.npar : 0, tile + copies, &r_copy);
+      if (Sc > 0 && (h->xcopy_mode == 1 || r_copy >= r_plain)) {
+        xcopy = true;
+        S = Sc;
       }
     }
-    const size_t smem = (npar_sh + S * per_stage) * sizeof(double);
-    const int thr = ((S * ld + 31) / 32) * 32;
-    const long long grid = (K + 1 + S - 1) / S;
-    if (grid > 0x7fffffffLL) return fail("hqpdocp: horizon too long for one launch", HQPDOCP_E_UNSUPPORTED);
-    auto kern = mode == HQPDOCP_GRAD_FD ? docp_stage_kernel<Model, HQPDOCP_GRAD_FD>
-                                        : docp_stage_kernel<Model, HQPDOCP_GRAD_AD>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    kern<<<(unsigned)grid, thr, smem, h->stream>>>(a, S, npar_sh, ncm);
-    h->launches++;
+    const size_t smem = ((parsh ? D.npar : 0) + S * (tile + (xcopy ? copies : 0)) + 256) * sizeof(double);
+    if (fd) {
+      if (xcopy) rc = parsh ? launch_stage<Model, HQPDOCP_GRAD_FD, true, true>(h, a, S, ncm, smem)
+                            : launch_stage<Model, HQPDOCP_GRAD_FD, false, true>(h, a, S, ncm, smem);
+      else rc = parsh ? launch_stage<Model, HQPDOCP_GRAD_FD, true, false>(h, a, S, ncm, smem)
+                      : launch_stage<Model, HQPDOCP_GRAD_FD, false, false>(h, a, S, ncm, smem);
+    } else {
+      rc = parsh ? launch_stage<Model, HQPDOCP_GRAD_AD, true, false>(h, a, S, ncm, smem)
+                 : launch_stage<Model, HQPDOCP_GRAD_AD, false, false>(h, a, S, ncm, smem);
+    }
   }
+  if (rc) return rc;
+  h->launches++;
   CU(cudaGetLastError());
   return HQPDOCP_OK;
 }
@@ -365,6 +466,7 @@ int run(hqpdocp_handle *h, bool grads, int mode, const double *x, double *f, dou
   a.cval = h->cval;
   a.b = b;
   a.g = g; a.fx = fx; a.fu = fu; a.cx = cx; a.cu = cu;
+  a.npar = D.npar;
   int rc;
   switch (D.model) {
     case HQPDOCP_MODEL_DID: rc = launch_model<ModelDID>(h, grads, mode, a); break;
@@ -444,6 +546,7 @@ int hqpdocp_create(const hqpdocp_dims *dims, hqpdocp_handle **out) {
   h->dims = D;
   h->device = D.device;
   cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, D.device);
+  if (const char *e = getenv("HQPDOCP_XCOPY")) h->xcopy_mode = atoi(e);
   const long long K = D.K;
   h->N = K * (D.nx + D.nu) + D.nx;
   h->ncns = K * D.nc + D.ncK;
