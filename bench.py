@@ -804,7 +804,10 @@ def run_docp_update(local):
                                                      "with the model restated as an Hqp_Docp subclass"}
             except Exception as ex:
                 res["cpu_baseline"] = {"error": str(ex)}
-        res["gpu_launches_per_update"] = 4
+        n0 = e.launches
+        e.update_fbd_dev(xd, fo, b, d)
+        res["gpu_launches_per_call"] = e.launches - n0
+        torch.cuda.synchronize()
         e.close()
         del fx, fu, cx, cu, xd, b, d, g
         out[key] = res
