@@ -326,3 +326,40 @@ def test_gpu_host_module_sqp_solves_match_the_reference():
         assert abs(got["objective"] - want["objective"]) <= 1e-9 * abs(want["objective"])
         assert np.max(np.abs(got["x"] - want["x"])) <= 1e-7
     assert abs(want["objective"] - 14.814107952743184) < 1e-9  # (the CPU run of this container)
+
+
+def _run_stack(which, K, nx, nu, grad=1):
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sqp_stack_runner.py"), which, str(K), str(nx),
+                          str(nu), str(grad)], capture_output=True, text=True, timeout=900)
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert lines, f"sqp_stack_runner {which} failed: rc={out.returncode}\n{out.stdout[-2000:]}\n{out.stderr[-2000:]}"
+    return json.loads(lines[-1])
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not rh.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("K,nx,nu,grad", [(20, 4, 2, 0), (40, 6, 3, 0), (100, 8, 4, 0), (40, 6, 3, 1)])
+def test_gpu_sqp_with_every_device_module(K, nx, nu, grad):
+    """The SQP-driven workload (config 5's kind, small): the unmodified Hqp_SqpPowell runs the
+    nonlinear DOCP once with the reference's modules only (Prg_SynthNL, Hqp_HL_BFGS,
+    Hqp_IpsMehrotra + Hqp_IpLQDOCP) and once with every device module of this repository
+    plugged in -- program on Hqp_DocpCuda<> (row f4), sqp_hela CudaBFGS (row f2), sqp_qp_solver
+    CudaMehrotra (device-resident IP solver + KKT engine).  The programs are ones on which the
+    reference's own solver variants agree (LQDOCP / RedSpBKP / Franke: same SQP iterations,
+    objective to 1e-13); on less well-posed instances (K = 60, nx = 4: 114 SQP iterations) the
+    reference's variants already end 0.4 % apart and no parity can be asked for.
+    grad 0 (the reference's forward differences): identical SQP and IP iteration counts;
+    grad 1 (dual numbers): derivatives differ by the truncation error of the differences."""
+    want, got = _run_stack("ref", K, nx, nu), _run_stack("cuda", K, nx, nu, grad)
+    print({k: (want[k], got[k]) for k in ("result", "objective", "sqp_iters", "qp_iters")})
+    assert want["result"] == "optimal" and got["result"] == "optimal"
+    if grad == 0:
+        assert (got["sqp_iters"], got["qp_iters"]) == (want["sqp_iters"], want["qp_iters"])
+        assert abs(got["objective"] - want["objective"]) <= 1e-8 * abs(want["objective"])
+        assert np.max(np.abs(np.array(got["x"]) - np.array(want["x"]))) <= 1e-6
+    else:
+        assert abs(got["objective"] - want["objective"]) <= 1e-5 * abs(want["objective"])
+        assert abs(got["sqp_iters"] - want["sqp_iters"]) <= 3
