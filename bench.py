@@ -814,6 +814,38 @@ def run_docp_update(local):
     return out
 
 
+def run_sqp_stack(local):
+    """SQP-driven workload, end to end: hqp_solve of the synthetic nonlinear DOCP (K = 300, nx 20,
+    nu 10) by the UNMODIFIED reference SQP solver (oracle/_ref is the host program here, as HQP
+    would be), once with the reference's modules only (cpu_baseline) and once with every device
+    module of this repository plugged in: program on Hqp_DocpCuda<> (row f4), sqp_hela CudaBFGS
+    (row f2), sqp_qp_solver CudaMehrotra (device-resident IP solver on the KKT engine).  Wall clock
+    of setup + solve; the host still assembles SPMATs between the device calls."""
+    import subprocess
+    K, nx, nu = 300, 20, 10
+    runner = os.path.join(ROOT, "tests", "sqp_stack_runner.py")
+    env = dict(os.environ, STACK_SIM="0", CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local)))
+    res = {}
+    for which in ("ref", "cuda"):
+        out = subprocess.run([sys.executable, runner, which, str(K), str(nx), str(nu), "0"], capture_output=True,
+                             text=True, timeout=600, env=env)
+        lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if not lines:
+            raise RuntimeError(f"sqp_stack {which}: rc={out.returncode} {out.stderr[-400:]}")
+        d = json.loads(lines[-1])
+        d.pop("x", None)
+        res[which] = d
+    r, c = res["ref"], res["cuda"]
+    return {"workload": f"hqp_solve, synthetic nonlinear DOCP K={K} nx={nx} nu={nu}, Powell SQP + BFGS + Mehrotra",
+            "device_modules": {k: c[k] for k in ("result", "objective", "sqp_iters", "qp_iters", "seconds_setup_and_solve")},
+            "cpu_baseline": {"value": r["seconds_setup_and_solve"], "unit": "s per solve", "cores": 1, "kind": "reference",
+                             "sample": "the same solve with Prg_SynthNL / Hqp_HL_BFGS / Hqp_IpsMehrotra + Hqp_IpLQDOCP",
+                             "result": r["result"], "objective": r["objective"], "sqp_iters": r["sqp_iters"],
+                             "qp_iters": r["qp_iters"]},
+            "same_iteration_counts": (r["sqp_iters"], r["qp_iters"]) == (c["sqp_iters"], c["qp_iters"]),
+            "objective_rel_diff": abs(c["objective"] - r["objective"]) / abs(r["objective"])}
+
+
 def run_sqp_ops(local):
     """Row f3: grd_L and the merit functions on config 2's QP (N = 300,020) through the
     host-pointer calls (H2D of the vectors inside the timed region), next to the reference's
@@ -937,6 +969,10 @@ def run_ours(args):
                 extra["docp_update"] = run_docp_update(local)
             except Exception as ex:
                 extra["docp_update"] = {"error": str(ex)}
+            try:
+                extra["sqp_stack"] = run_sqp_stack(local)
+            except Exception as ex:
+                extra["sqp_stack"] = {"error": str(ex)}
         if rank == 0:
             line.update(extra)
     if rank == 0:

@@ -18,6 +18,9 @@ if __name__ == "__main__":
     which, K, nx, nu = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     grad = int(sys.argv[5]) if len(sys.argv) > 5 else 1
     p = dc.synthnl_problem(K, nx, nu, 1, 0)
+    SIM = os.environ.get("STACK_SIM", "1") != "0"  # prg_simulate before sqp_init (Docp_Main.C:69)
+    import time
+    t0 = time.perf_counter()
     L = rh.lib()
     if which == "cuda":
         rh.load_plugin(os.path.join(build.LIB, "libhqp_ipcuda_plugin.so"))
@@ -25,9 +28,10 @@ if __name__ == "__main__":
         assert L.ref_set_int(b"prg_cuda_grad", grad) == 0
         hela = os.environ.get("STACK_HELA", "CudaBFGS")
         assert L.ref_set_string(b"sqp_hela", hela.encode()) == 0
-        out = prg.solve(qp_solver=os.environ.get("STACK_QPS", "CudaMehrotra"), mat_solver=os.environ.get("STACK_MAT", ""))
+        out = prg.solve(simulate=SIM, qp_solver=os.environ.get("STACK_QPS", "CudaMehrotra"), mat_solver=os.environ.get("STACK_MAT", ""))
     else:
         prg = rh.RefDocp(p)
-        out = prg.solve(qp_solver=os.environ.get("STACK_QPS", "Mehrotra"), mat_solver=os.environ.get("STACK_MAT", "LQDOCP"))
+        out = prg.solve(simulate=SIM, qp_solver=os.environ.get("STACK_QPS", "Mehrotra"), mat_solver=os.environ.get("STACK_MAT", "LQDOCP"))
+    out["seconds_setup_and_solve"] = time.perf_counter() - t0
     out["x"] = [float(v) for v in out["x"]]
     print(json.dumps(out))
