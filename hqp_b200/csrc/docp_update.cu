@@ -378,7 +378,11 @@ int pick_stages(int ld, size_t fixed, size_t per_stage, long long *resident) {
 
 template <class Model, bool PARSH>
 int launch_vals(hqpdocp_handle *h, const UpdArgs &a, int ncm, size_t smem) {
-  CU(cudaFuncSetAttribute(docp_vals_kernel<Model, PARSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static thread_local int optin_dev = -1;  // (the attribute is per function and device)
+  if (optin_dev != h->device) {
+    CU(cudaFuncSetAttribute(docp_vals_kernel<Model, PARSH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    optin_dev = h->device;
+  }
   const long long grid = (h->dims.K + 1 + VT - 1) / VT;
   docp_vals_kernel<Model, PARSH><<<(unsigned)grid, VT, smem, h->stream>>>(a, ncm);
   return HQPDOCP_OK;
@@ -387,8 +391,12 @@ int launch_vals(hqpdocp_handle *h, const UpdArgs &a, int ncm, size_t smem) {
 template <class Model, int MODE, bool PARSH, bool XCOPY>
 int launch_stage(hqpdocp_handle *h, const UpdArgs &a, int S, int ncm, size_t smem) {
   const int ld = h->dims.nx + h->dims.nu + 1;
-  CU(cudaFuncSetAttribute(docp_stage_kernel<Model, MODE, PARSH, XCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                          200 * 1024));
+  static thread_local int optin_dev = -1;
+  if (optin_dev != h->device) {
+    CU(cudaFuncSetAttribute(docp_stage_kernel<Model, MODE, PARSH, XCOPY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            200 * 1024));
+    optin_dev = h->device;
+  }
   const long long grid = ((long long)h->dims.K + 1 + S - 1) / S;
   docp_stage_kernel<Model, MODE, PARSH, XCOPY><<<(unsigned)grid, ((S * ld + 31) / 32) * 32, smem, h->stream>>>(a, S, ncm);
   return HQPDOCP_OK;
