@@ -331,6 +331,7 @@ struct hqpdocp_handle {
   cudaStream_t stream = nullptr;
   long long N = 0, me = 0, m = 0, ncns = 0;
   long long launches = 0;
+  bool staged = false;
   int xcopy_mode = -1;  // HQPDOCP_XCOPY: -1 choose, 0 never, 1 always (when it fits)
   double *d_par = nullptr, *d_spar = nullptr;
   Assoc t[6];  // xu_eq xu_lb xu_ub cns_eq cns_lb cns_ub
@@ -495,19 +496,27 @@ int run(hqpdocp_handle *h, bool grads, int mode, const double *x, double *f, dou
   return HQPDOCP_OK;
 }
 
+// device staging of the host-pointer entry points, allocated on first use; all or nothing
 int stage_alloc(hqpdocp_handle *h) {
-  if (h->s_x) return HQPDOCP_OK;
+  if (h->staged) return HQPDOCP_OK;
   const hqpdocp_dims &D = h->dims;
   const size_t K = D.K;
-  CU(cudaMalloc(&h->s_x, sizeof(double) * h->N));
-  CU(cudaMalloc(&h->s_f, sizeof(double)));
-  CU(cudaMalloc(&h->s_b, sizeof(double) * std::max<long long>(1, h->me)));
-  CU(cudaMalloc(&h->s_d, sizeof(double) * std::max<long long>(1, h->m)));
-  CU(cudaMalloc(&h->s_g, sizeof(double) * h->N));
-  CU(cudaMalloc(&h->s_fx, sizeof(double) * std::max<size_t>(1, K * D.nx * D.nx)));
-  CU(cudaMalloc(&h->s_fu, sizeof(double) * std::max<size_t>(1, K * D.nx * D.nu)));
-  CU(cudaMalloc(&h->s_cx, sizeof(double) * std::max<size_t>(1, (size_t)h->ncns * D.nx)));
-  CU(cudaMalloc(&h->s_cu, sizeof(double) * std::max<size_t>(1, K * D.nc * D.nu)));
+  struct { double **p; size_t n; } want[] = {
+      {&h->s_x, (size_t)h->N}, {&h->s_f, 1}, {&h->s_b, (size_t)std::max<long long>(1, h->me)},
+      {&h->s_d, (size_t)std::max<long long>(1, h->m)}, {&h->s_g, (size_t)h->N},
+      {&h->s_fx, std::max<size_t>(1, K * D.nx * D.nx)}, {&h->s_fu, std::max<size_t>(1, K * D.nx * D.nu)},
+      {&h->s_cx, std::max<size_t>(1, (size_t)h->ncns * D.nx)}, {&h->s_cu, std::max<size_t>(1, K * D.nc * D.nu)}};
+  for (auto &w : want) {
+    cudaError_t e = cudaMalloc(w.p, sizeof(double) * w.n);
+    if (e != cudaSuccess) {
+      for (auto &v : want) {
+        cudaFree(*v.p);
+        *v.p = nullptr;
+      }
+      return fail(std::string("hqpdocp: staging buffers: ") + cudaGetErrorString(e), HQPDOCP_E_CUDA);
+    }
+  }
+  h->staged = true;
   return HQPDOCP_OK;
 }
 
