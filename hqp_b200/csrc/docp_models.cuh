@@ -17,10 +17,12 @@
 #pragma once
 
 struct ModelArgs {
-  int K, nx, nu, nc, ncK;
+  int K;               // stages with controls of the WHOLE horizon; vals() gets the global stage k
+  int nx, nu, nc, ncK;
   const double *par;   // [npar]   global parameters (device)
   const double *spar;  // [(K+1)][nspar] per-stage parameters (device) or nullptr
   int nspar;
+  int k0;              // global index of the handle's first stage (spar row 0)
 };
 
 // forward-mode dual number: value and ONE directional derivative
@@ -87,7 +89,7 @@ struct ModelSynthNL {
     const int nx = m.nx, nu = m.nu;
     const double eps = m.par[0];
     const double *A = m.par + 1, *B = A + nx * nx, *qw = B + nx * nu, *rw = qw + nx;
-    const double *r = m.spar + (size_t)k * m.nspar;
+    const double *r = m.spar + (size_t)(k - m.k0) * m.nspar;
     T s(0.0);
     for (int i = 0; i < nx; i++) {
       T e = x[i] - r[i];

@@ -56,6 +56,8 @@ struct UpdArgs {
   double *b;        // [me]
   double *g, *fx, *fu, *cx, *cu;
   int npar;
+  int KL;    // stages with controls of THIS handle (local indices 0 .. KL)
+  int halo;  // 1: local stage KL belongs to the next stage range -- only its x is read
 };
 
 // ---- views handed to Model::vals (docp_models.cuh)
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(VT) docp_vals_kernel(UpdArgs a, int ncm) {
     m.par = sh;
   }
   const long long k0 = (long long)blockIdx.x * VT;
-  const int ns = (int)(k0 + VT <= m.K + 1 ? VT : m.K + 1 - k0);
-  const long long lo = k0 * nd, n_all = (long long)m.K * nd + nx;
+  const int ns = (int)(k0 + VT <= a.KL + 1 ? VT : a.KL + 1 - k0);
+  const long long lo = k0 * nd, n_all = (long long)a.KL * nd + nx;
   for (int t = threadIdx.x; t < ns * nd; t += VT) {
     const int s = t / nd, i = t - s * nd;
     xT[i * VLD + s] = lo + t < n_all ? a.x[lo + t] : 0.0;
@@ -124,14 +126,14 @@ __global__ void __launch_bounds__(VT) docp_vals_kernel(UpdArgs a, int ncm) {
     ColView x{xT + threadIdx.x, VLD}, u{xT + nx * VLD + threadIdx.x, VLD};
     OutView f{outT + threadIdx.x, VLD}, c{outT + nx * VLD + threadIdx.x, VLD};
     double f0 = 0.0;
-    Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+    if (!(k == a.KL && a.halo)) Model::template vals<double>(m, (int)k + m.k0, x, u, f, f0, c);
     a.f0k[k] = f0;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < ns * nx; t += VT) {
     const int s = t / nx, i = t - s * nx;
     const long long k = k0 + s;
-    if (k < m.K) {
+    if (k < a.KL) {
       const double v = outT[i * VLD + s];
       a.fbase[k * nx + i] = v;
       a.b[k * nx + i] = v - a.x[(k + 1) * nd + i];  // v_sub(fk, x_{k+1}), :861
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(VT) docp_vals_kernel(UpdArgs a, int ncm) {
   for (int t = threadIdx.x; t < ns * ncm; t += VT) {
     const int s = t / ncm, i = t - s * ncm;
     const long long k = k0 + s;
-    if (i < (k < m.K ? m.nc : m.ncK)) a.cval[k * m.nc + i] = outT[(nx + i) * VLD + s];
+    if (i < (k < a.KL ? m.nc : (a.halo ? 0 : m.ncK))) a.cval[k * m.nc + i] = outT[(nx + i) * VLD + s];
   }
 }
 
@@ -166,10 +168,10 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
     m.par = sh;
   }
   const long long k0 = (long long)blockIdx.x * S;
-  const int ns = (int)(k0 + S <= m.K + 1 ? S : m.K + 1 - k0);
+  const int ns = (int)(k0 + S <= a.KL + 1 ? S : a.KL + 1 - k0);
   // stage vectors: ns * nd contiguous doubles of x (the final stage has nx only)
   {
-    const long long lo = k0 * nd, n_all = (long long)m.K * nd + nx;
+    const long long lo = k0 * nd, n_all = (long long)a.KL * nd + nx;
     for (int t = threadIdx.x; t < ns * nd; t += blockDim.x) {
       const int s = t / nd, i = t - s * nd;
       stage_sh[s * per_stage + i] = lo + t < n_all ? a.x[lo + t] : 0.0;
@@ -189,9 +191,9 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
   const int s = threadIdx.x / ld, j = threadIdx.x - s * ld;
   if (s < ns) {
     const long long k = k0 + s;
-    const bool last = k == m.K;
+    const bool last = k == a.KL;
     const int ncols = last ? nx : nd;
-    if (j < ncols || j == nd) {
+    if (!(last && a.halo) && (j < ncols || j == nd)) {
       const double *xs = stage_sh + s * per_stage;
       double *tile = stage_sh + s * per_stage + nd;
       const int nf = last ? 0 : nx, nc = last ? m.ncK : m.nc;
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
         if (XCOPY) {
           const double *xc = tile + rows * ld + j;
           ColView x{j == nd ? xs : xc, j == nd ? 1 : ld}, u{j == nd ? xs + nx : xc + nx * ld, j == nd ? 1 : ld};
-          Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+          Model::template vals<double>(m, (int)k + m.k0, x, u, f, f0, c);
         } else {
           int col = -1;
           double *slot = sh + npar_sh + S * per_stage + threadIdx.x;
@@ -214,13 +216,13 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
             col = j;
           }
           PertView x{xs, col, slot}, u{xs + nx, col - nx, slot};
-          Model::template vals<double>(m, (int)k, x, u, f, f0, c);
+          Model::template vals<double>(m, (int)k + m.k0, x, u, f, f0, c);
         }
         *f0_out = f0;
       } else {
         SeedView x{xs, j}, u{xs + nx, j - nx};
         Dual f0(0.0);
-        Model::template vals<Dual>(m, (int)k, x, u, f, f0, c);
+        Model::template vals<Dual>(m, (int)k + m.k0, x, u, f, f0, c);
         *f0_out = f0.d;
       }
     }
@@ -229,7 +231,11 @@ __global__ void __launch_bounds__(256) docp_stage_kernel(UpdArgs a, int S, int n
   // write-out: rows of the tiles, consecutive threads on consecutive columns
   for (int s2 = 0; s2 < ns; s2++) {
     const long long k = k0 + s2;
-    const bool last = k == m.K;
+    const bool last = k == a.KL;
+    if (last && a.halo) {  // the next range's stage: nothing of it is ours
+      if (threadIdx.x == 0) a.f0k[k] = 0.0;
+      continue;
+    }
     const double *xs = stage_sh + s2 * per_stage;
     const double *tile = xs + nd;
     const int nf = last ? 0 : nx, nc = last ? m.ncK : m.nc, ncols = last ? nx : nd;
@@ -468,7 +474,9 @@ int run(hqpdocp_handle *h, bool grads, int mode, const double *x, double *f, dou
   }
   CU(cudaSetDevice(h->device));
   UpdArgs a{};
-  a.m = ModelArgs{D.K, D.nx, D.nu, D.nc, D.ncK, h->d_par, h->d_spar, D.nspar};
+  a.m = ModelArgs{D.K_total, D.nx, D.nu, D.nc, D.ncK, h->d_par, h->d_spar, D.nspar, D.k_first};
+  a.KL = D.K;
+  a.halo = D.k_first + D.K < D.K_total;
   a.x = x;
   a.fbase = h->fbase;
   a.f0k = h->f0k;
@@ -546,6 +554,9 @@ int hqpdocp_create(const hqpdocp_dims *dims, hqpdocp_handle **out) {
   if (D.K < 1 || D.nx < 1 || D.nu < 0 || D.nc < 0 || D.ncK < 0 || D.npar < 0 || D.nspar < 0 ||
       (D.npar > 0 && !D.par) || (D.nspar > 0 && !D.spar))
     return fail("hqpdocp_create: bad dimensions", HQPDOCP_E_ARG);
+  if (D.K_total < 0 || D.k_first < 0 || (D.K_total > 0 && D.k_first + D.K > D.K_total) ||
+      (D.K_total == 0 && D.k_first != 0))
+    return fail("hqpdocp_create: bad stage range", HQPDOCP_E_ARG);
   if (D.nx > MAXX || D.nu > MAXU || D.nc > MAXC || D.ncK > MAXC)
     return fail("hqpdocp_create: nx <= 64, nu <= 32, nc <= 8 per stage", HQPDOCP_E_UNSUPPORTED);
   bool ok;
@@ -561,12 +572,17 @@ int hqpdocp_create(const hqpdocp_dims *dims, hqpdocp_handle **out) {
   CU(cudaSetDevice(D.device));
   hqpdocp_handle *h = new hqpdocp_handle();
   h->dims = D;
+  if (h->dims.K_total == 0) {  // the whole horizon
+    h->dims.K_total = D.K;
+    h->dims.k_first = 0;
+  }
+  const bool halo = h->dims.k_first + D.K < h->dims.K_total;
   h->device = D.device;
   cudaDeviceGetAttribute(&h->sms, cudaDevAttrMultiProcessorCount, D.device);
   if (const char *e = getenv("HQPDOCP_XCOPY")) h->xcopy_mode = atoi(e);
   const long long K = D.K;
   h->N = K * (D.nx + D.nu) + D.nx;
-  h->ncns = K * D.nc + D.ncK;
+  h->ncns = K * D.nc + (halo ? 0 : D.ncK);
   h->me = K * D.nx + D.xu_eq.dim + D.cns_eq.dim;
   h->m = (long long)D.xu_lb.dim + D.xu_ub.dim + D.cns_lb.dim + D.cns_ub.dim;
   int rc = HQPDOCP_OK;

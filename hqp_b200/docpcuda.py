@@ -34,7 +34,8 @@ class _Dims(ctypes.Structure):
                 ("par", ctypes.POINTER(ctypes.c_double)), ("nspar", ctypes.c_int),
                 ("spar", ctypes.POINTER(ctypes.c_double)),
                 ("xu_eq", _Assoc), ("xu_lb", _Assoc), ("xu_ub", _Assoc),
-                ("cns_eq", _Assoc), ("cns_lb", _Assoc), ("cns_ub", _Assoc), ("device", ctypes.c_int)]
+                ("cns_eq", _Assoc), ("cns_lb", _Assoc), ("cns_ub", _Assoc), ("device", ctypes.c_int),
+                ("k_first", ctypes.c_int), ("K_total", ctypes.c_int)]
 
 
 def lib():
@@ -106,6 +107,13 @@ class DocpProblem:
     cns_eq: Assoc = field(default_factory=Assoc)
     cns_lb: Assoc = field(default_factory=Assoc)
     cns_ub: Assoc = field(default_factory=Assoc)
+    k_first: int = 0            # a stage range of a longer horizon (hqpdocp_dims.k_first / K_total)
+    K_total: int = 0            # 0: the whole horizon
+
+    @property
+    def owns_final(self):
+        """False: local stage K belongs to the next range, only its x is read (a halo)."""
+        return self.K_total == 0 or self.k_first + self.K == self.K_total
 
     @property
     def nd(self):
@@ -117,7 +125,7 @@ class DocpProblem:
 
     @property
     def ncns(self):
-        return self.K * self.nc + self.ncK
+        return self.K * self.nc + (self.ncK if self.owns_final else 0)
 
     @property
     def me(self):
@@ -133,14 +141,64 @@ class DocpProblem:
         for t in (self.xu_eq, self.xu_lb, self.xu_ub, self.cns_eq, self.cns_lb, self.cns_ub):
             t.idxs.clear()
             t.vals.clear()
-        for k in range(self.K + 1):
-            x_min, x_max, u_min, u_max, c_min, c_max = stage_bounds(k)
+        for k in range(self.K + 1 if self.owns_final else self.K):
+            x_min, x_max, u_min, u_max, c_min, c_max = stage_bounds(self.k_first + k)
             assert len(x_min) == self.nx and len(u_min) == (self.nu if k < self.K else 0)
             assert len(c_min) == (self.nc if k < self.K else self.ncK)
+            # (indices below are LOCAL to the range)
             parse_constr(x_min, x_max, k * self.nd, self.xu_eq, self.xu_lb, self.xu_ub)
             parse_constr(u_min, u_max, k * self.nd + self.nx, self.xu_eq, self.xu_lb, self.xu_ub)
             parse_constr(c_min, c_max, k * self.nc, self.cns_eq, self.cns_lb, self.cns_ub)
+        self._stage_bounds = stage_bounds
         return self
+
+    def shard(self, rank, world):
+        """The contiguous stage range of rank `rank` out of `world` (the split hqp_b200/dist.py
+        uses for the KKT horizon): a DocpProblem with local indices, x_init = the range's states
+        and controls plus the next state (halo).  Results of the ranges concatenate group by
+        group -- b: dynamics rows | x/u fixings | constraint equalities; d: the four bound groups
+        -- and the objective adds up (assemble_shards)."""
+        assert self.K_total == 0 and 0 <= rank < world <= self.K
+        base, rem = divmod(self.K, world)  # (hqp_b200/dist.py:stage_ranges)
+        k0 = rank * base + min(rank, rem)
+        k1 = k0 + base + (1 if rank < rem else 0)
+        q = DocpProblem(self.model, k1 - k0, self.nx, self.nu, self.nc, self.ncK, self.par,
+                        np.ascontiguousarray(self.spar[k0:k1 + 1]), self.x_slice(self.x_init, k0, k1),
+                        k_first=k0, K_total=self.K)
+        return q.set_bounds(self._stage_bounds)
+
+    def x_slice(self, x, k0, k1):
+        """[x_k0 u_k0 ... x_k1] of a full-horizon vector."""
+        return np.ascontiguousarray(x[k0 * self.nd:k1 * self.nd + self.nx])
+
+
+def assemble_shards(full: "DocpProblem", shards, outs):
+    """Full-horizon results from the per-range results (dicts as DocpCuda.update returns, or
+    (f, b, d) tuples of update_fbd) of shards = [full.shard(r, world) ...]."""
+    if isinstance(outs[0], tuple):
+        outs = [dict(f=o[0], b=o[1], d=o[2]) for o in outs]
+    res = {"f": float(sum(o["f"] for o in outs))}
+    nb = [(q.K * q.nx, len(q.xu_eq.idxs), len(q.cns_eq.idxs)) for q in shards]
+    nd_ = [(len(q.xu_lb.idxs), len(q.xu_ub.idxs), len(q.cns_lb.idxs), len(q.cns_ub.idxs)) for q in shards]
+
+    def groups(key, sizes):
+        cols = []
+        for g in range(len(sizes[0])):
+            for o, sz in zip(outs, sizes):
+                off = sum(sz[:g])
+                cols.append(o[key][off:off + sz[g]])
+        return np.concatenate(cols) if cols else np.zeros(0)
+
+    res["b"], res["d"] = groups("b", nb), groups("d", nd_)
+    if "g" in outs[0]:
+        gs = []
+        for q, o in zip(shards, outs):  # the halo state's gradient entries belong to the next range
+            gs.append(o["g"] if q.owns_final else o["g"][:q.K * q.nd])
+        res["g"] = np.concatenate(gs)
+        for key in ("fx", "fu", "cu"):
+            res[key] = np.concatenate([o[key] for o in outs])
+        res["cx"] = np.concatenate([o["cx"][:q.ncns] for q, o in zip(shards, outs)])
+    return res
 
 
 def did_problem(kmax=60, with_cns=True) -> DocpProblem:
@@ -228,7 +286,8 @@ class DocpCuda:
         d = _Dims(prob.K, prob.nx, prob.nu, prob.nc, prob.ncK, prob.model, par.size, _dp(par),
                   spar.shape[1] if spar.ndim == 2 else 0, _dp(spar) if spar.size else None,
                   assoc(prob.xu_eq), assoc(prob.xu_lb), assoc(prob.xu_ub),
-                  assoc(prob.cns_eq), assoc(prob.cns_lb), assoc(prob.cns_ub), device)
+                  assoc(prob.cns_eq), assoc(prob.cns_lb), assoc(prob.cns_ub), device,
+                  prob.k_first, prob.K_total)
         self.h = ctypes.c_void_p()
         _check(lib().hqpdocp_create(ctypes.byref(d), ctypes.byref(self.h)), "hqpdocp_create")
 

@@ -98,7 +98,7 @@ class Hqp_DocpCuda : public Base {
     std::vector<double> par, spar;
     int nspar = 0;
     cuda_params(_K, par, nspar, spar);
-    hqpdocp_dims D;
+    hqpdocp_dims D = hqpdocp_dims();
     D.K = _K; D.nx = _nx; D.nu = _nu; D.nc = _nc; D.ncK = _ncK;
     D.model = cuda_model();
     D.npar = (int)par.size(); D.par = par.empty() ? NULL : &par[0];

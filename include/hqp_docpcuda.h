@@ -84,6 +84,15 @@ typedef struct hqpdocp_dims {
   hqpdocp_assoc xu_eq, xu_lb, xu_ub;    /* _xu_eq / _xu_lb / _xu_ub              */
   hqpdocp_assoc cns_eq, cns_lb, cns_ub; /* _cns_eq / _cns_lb / _cns_ub           */
   int device;         /* CUDA device ordinal                                     */
+  /* A handle may own a contiguous RANGE of the stages of a longer horizon (one handle per GPU,
+   * the same split as hqpcu_comm_init's, include/hqp_ipcuda.h): K_total > 0 is the horizon's K
+   * and k_first the global index of this handle's first stage; the handle then evaluates the
+   * global stages k_first .. k_first+K-1 and, only if k_first+K == K_total, the final stage.
+   * x still holds K (nx+nu) + nx values: x_{k_first+K} is read for the last dynamics rows (a halo
+   * of nx values when the stage belongs to the next range).  spar, the tables and all outputs
+   * are those of the range, with LOCAL indices.  No exchange between ranges is needed: the
+   * objective is the sum of the ranges' f.  K_total = 0: the whole horizon (k_first = 0).      */
+  int k_first, K_total;
 } hqpdocp_dims;
 
 const char *hqpdocp_last_error(void);

@@ -12,9 +12,11 @@ may import it.  Scalar Python loops: small cases only.
                 ::update_stage (:101-165): constant Jacobians, f0u = 2 u dt
   vals_synthnl  the synthetic model (hqp_b200/csrc/docp_models.cuh) in the same operation order;
                 grds_synthnl_exact: its derivatives in closed form (numpy)
+A DocpProblem may be a stage range of a longer horizon (DocpProblem.shard): stage indices are
+local, the range's last state is a halo that is only read.
 Pinned against the compiled reference (oracle/_ref: ref_docp_update drives the UNMODIFIED
 Hqp_Docp for Prg_DID and for oracle/prg_synthnl.cpp) in tests/test_docp_update.py, and against
-the golden vectors tests/golden/docp_update_*.npz made from it by scripts/gen_golden_docp.py.
+the golden vectors tests/golden/docp_update_*.npz made from it by tests/golden/make_docp_update_golden.py.
 """
 from __future__ import annotations
 
@@ -107,7 +109,7 @@ def update_fbd(p, xv):
     b, d, cval = np.zeros(p.me), np.zeros(p.m), np.zeros(p.ncns)
     nd = p.nx + p.nu
     fsum = 0.0
-    for k in range(p.K + 1):
+    for k in range(p.K + 1 if p.owns_final else p.K):  # (a stage range: the halo stage is not ours)
         x, u = _stage(p, xv, k)
         f, f0, c = _vals(p, k, x, u)
         fsum += f0
@@ -194,7 +196,7 @@ def update(p, xv, grads="fd"):
     fx = np.zeros((p.K, p.nx, p.nx)); fu = np.zeros((p.K, p.nx, p.nu))
     cx = np.zeros((p.ncns, p.nx)); cu = np.zeros((p.K * p.nc, p.nu))
     fn = {"fd": grds_fd, "did": grds_did, "exact": grds_synthnl_exact}[grads]
-    for k in range(p.K + 1):
+    for k in range(p.K + 1 if p.owns_final else p.K):
         x, u = _stage(p, xv, k)
         jfx, jfu, f0x, f0u, jcx, jcu = fn(p, k, x, u)
         g[k * nd:k * nd + p.nx] = f0x

@@ -70,3 +70,48 @@ def test_stage_ranges_cover_the_horizon():
         assert r[0][0] == 0 and r[-1][1] == K
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+
+
+# ---- row f4: the DOCP update over stage ranges (one hqpdocp handle per GPU).  The ranges need no
+# exchange -- only a halo of one state -- so the N > 1 logic is the partition itself: local
+# index maps of the bound tables, the halo stage that is read but not evaluated, and the
+# group-wise concatenation of b and d.  Engine here: the plain-Python restatement.
+
+def docp_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hqp_b200 import docpcuda as dc
+    from oracle import docp_oracle
+    p = dc.synthnl_problem(11, 5, 2, 3, 2, seed=9)
+    x = p.x_init + 0.1 * np.random.default_rng(0).uniform(-1, 1, p.N)
+    q = p.shard(rank, world)
+    out = docp_oracle.update(q, p.x_slice(x, q.k_first, q.k_first + q.K), "fd")
+    # the objective is the one quantity that needs a reduction
+    f = torch.tensor([out["f"]], dtype=torch.float64)
+    dist.all_reduce(f)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, out)
+    if rank == 0:
+        full = dc.assemble_shards(p, [p.shard(r, world) for r in range(world)], gathered)
+        np.savez(os.path.join(out_dir, "docp.npz"), f_allreduce=f.numpy(), **full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_docp_update_over_stage_ranges_matches_full_horizon(world, tmp_path):
+    from hqp_b200 import docpcuda as dc
+    from hqp_b200.dist import stage_ranges
+    from oracle import docp_oracle
+    port = 31500 + os.getpid() % 2000 + world
+    mp.spawn(docp_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    p = dc.synthnl_problem(11, 5, 2, 3, 2, seed=9)
+    x = p.x_init + 0.1 * np.random.default_rng(0).uniform(-1, 1, p.N)
+    want = docp_oracle.update(p, x, "fd")
+    got = np.load(os.path.join(str(tmp_path), "docp.npz"))
+    for key in ("b", "d", "g", "fx", "fu", "cx", "cu"):
+        assert np.array_equal(got[key], want[key]), key
+    assert abs(float(got["f_allreduce"][0]) - want["f"]) <= 1e-13 * abs(want["f"])
+    # the ranges are the ones the KKT horizon split uses
+    assert [(q.k_first, q.k_first + q.K) for q in (p.shard(r, world) for r in range(world))] == stage_ranges(p.K, world)

@@ -363,3 +363,39 @@ def test_gpu_sqp_with_every_device_module(K, nx, nu, grad):
     else:
         assert abs(got["objective"] - want["objective"]) <= 1e-5 * abs(want["objective"])
         assert abs(got["sqp_iters"] - want["sqp_iters"]) <= 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("make,world", [(lambda: dc.synthnl_problem(11, 5, 2, 3, 2, seed=9), 3),
+                                        (lambda: dc.synthnl_problem(300, 20, 10, 1, 1, seed=2), 4),
+                                        (lambda: dc.did_problem(60, True), 2)])
+def test_gpu_update_over_stage_ranges_equals_full_horizon(make, world):
+    """One handle per stage range (hqpdocp_dims.k_first / K_total: one per GPU on a split horizon;
+    here all on device 0): the ranges' results, concatenated group by group, are bit-identical
+    to the full-horizon handle's; the objective is the sum of the ranges'."""
+    p = make()
+    x = p.x_init + 0.1 * np.random.default_rng(0).uniform(-1, 1, p.N)
+    e = dc.DocpCuda(p)
+    try:
+        full = {m: e.update(x, m) for m in (dc.GRAD_FD, dc.GRAD_AD)}
+        full_fbd = e.update_fbd(x)
+    finally:
+        e.close()
+    shards = [p.shard(r, world) for r in range(world)]
+    outs, fbd = {dc.GRAD_FD: [], dc.GRAD_AD: []}, []
+    for q in shards:
+        eq = dc.DocpCuda(q)
+        try:
+            xs = p.x_slice(x, q.k_first, q.k_first + q.K)
+            for m in outs:
+                outs[m].append(eq.update(xs, m))
+            fbd.append(eq.update_fbd(xs))
+        finally:
+            eq.close()
+    for m in outs:
+        asm = dc.assemble_shards(p, shards, outs[m])
+        for key in ("b", "d", "g", "fx", "fu", "cx", "cu"):
+            assert np.array_equal(asm[key], full[m][key]), (m, key)
+        assert abs(asm["f"] - full[m]["f"]) <= 1e-13 * max(1.0, abs(full[m]["f"]))
+    a2 = dc.assemble_shards(p, shards, fbd)
+    assert np.array_equal(a2["b"], full_fbd[1]) and np.array_equal(a2["d"], full_fbd[2])
