@@ -804,6 +804,8 @@ def run_docp_update(local):
                                                      "with the model restated as an Hqp_Docp subclass"}
             except Exception as ex:
                 res["cpu_baseline"] = {"error": str(ex)}
+        res["bound"] = ("instruction issue, not HBM: nx+nu+1 model evaluations per stage (ncu of the FD kernel: "
+                        "issue slots 75 % busy, FP64 pipe 25 %, DRAM < 1 %; profiles/r02_ncu_full_docp.md)")
         n0 = e.launches
         e.update_fbd_dev(xd, fo, b, d)
         res["gpu_launches_per_call"] = e.launches - n0
