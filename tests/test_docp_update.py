@@ -115,6 +115,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/hqp_docpcuda.h but not exported"
 
 
+def test_library_is_sm100a_sass_without_local_memory():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", dc.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in out.stdout
+    # the views keep every model evaluation in registers / shared memory
+    res = subprocess.run(["cuobjdump", "-res-usage", dc.LIB_PATH], capture_output=True, text=True).stdout
+    kernels = re.findall(r"Function (\S*docp_(?:stage|vals)_kernel\S*):\s*\n\s*(.*)", res)
+    assert kernels
+    for name, usage in kernels:
+        assert "LOCAL:0" in usage, (name, usage)
+
+
 def test_bad_arguments_and_no_cpu_fallback():
     lib = dc.lib()
     h = ctypes.c_void_p()
@@ -122,6 +136,10 @@ def test_bad_arguments_and_no_cpu_fallback():
     p = dc.did_problem(4)
     p.model = 99
     with pytest.raises(RuntimeError, match="status 2"):
+        dc.DocpCuda(p)
+    p = dc.did_problem(4)
+    p.k_first, p.K_total = 3, 5  # a stage range that does not fit its horizon
+    with pytest.raises(RuntimeError, match="status 1"):
         dc.DocpCuda(p)
     p = dc.did_problem(4)
     p.nx = 3  # does not fit the model
